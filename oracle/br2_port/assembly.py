@@ -91,6 +91,7 @@ class FreeAssembly:
         self.env = env
         self.simulator = BR2Simulator()
         self.actuation = defaultdict(list)
+        self.simulator._actuation_lists = self.actuation  # for oracle.fused's extractor
         self.free = {}
         self.toggle_gravity = gravity
         # free_simulator.py:88-91 ("t_multiplier" is the reference's spelling)
