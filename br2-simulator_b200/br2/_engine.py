@@ -1,0 +1,120 @@
+"""Device engine: owns the batch state in HBM (a PyTorch tensor) and drives libbr2cuda through the
+C ABI.  PyTorch is used for device memory, streams and copies only; every step is the hand-written
+kernel behind ``br2_step``.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _native
+from .hooks.rod import DYNAMIC_FIELDS, STATE_IO
+
+_SHAPES = {short: shape for short, shape in DYNAMIC_FIELDS.values()}
+
+
+class Engine:
+    def __init__(self, program, batch=1, device=None):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise _native.Br2Error(
+                "br2 (B200 build) needs a CUDA device: rod integration runs only in the sm_100a kernels "
+                "of libbr2cuda.so and there is no CPU fallback")
+        self.torch = torch
+        self.lib = _native.load()
+        self.program = program
+        self.batch = int(batch)
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        self.words = program.words
+
+        self._cprog = _native.make_program(program)
+        handle = ctypes.c_void_p()
+        _native.check(self.lib.br2_create(ctypes.byref(self._cprog), self.device.index or 0, ctypes.byref(handle)))
+        self.handle = handle
+
+        template = np.zeros(self.words)
+        self._template = template
+        self.state = torch.zeros((self.batch, self.words), dtype=torch.float64, device=self.device)
+        self.n_actions = program.counts["n_actions"]
+        self.pressures = torch.zeros((max(self.n_actions, 1), self.batch), dtype=torch.float64, device=self.device)
+        _native.check(self.lib.br2_bind_state(self.handle, self.state.data_ptr(), self.batch))
+        _native.check(self.lib.br2_set_actuation(self.handle, self.pressures.data_ptr()))
+        self.launches = 0
+
+    # ------------------------------------------------------------------ state access
+    def load_template(self, rods):
+        """Initial state of every instance = the host rods' arrays."""
+        for r, rod in enumerate(rods):
+            for short, (off, size) in self.program.layout[r].items():
+                self._template[off:off + size] = np.asarray(rod._host[short], dtype=np.float64).ravel()
+        row = self.torch.from_numpy(self._template).to(self.device)
+        self.state[:] = row.unsqueeze(0)
+
+    def view(self, rod_index, short):
+        """[batch, ...] device view of one field of one rod (no copy)."""
+        off, size = self.program.layout[rod_index][short]
+        shape = _SHAPES[short](self.program.n_elems[rod_index])
+        return self.state[:, off:off + size].view((self.batch,) + tuple(shape))
+
+    def fetch(self, rod_index, short):
+        arr = self.view(rod_index, short).cpu().numpy()
+        return arr[0] if self.batch == 1 else arr
+
+    def upload(self, rod_index, short, value):
+        view = self.view(rod_index, short)
+        tensor = self.torch.from_numpy(np.ascontiguousarray(value, dtype=np.float64)).to(self.device)
+        view.copy_(tensor.expand_as(view) if tensor.dim() < view.dim() else tensor)
+
+    def snapshot(self):
+        """Host copy of the whole batch state, split per rod / field (for diagnostics callbacks)."""
+        host = self.state.cpu().numpy()
+        out = []
+        for r, fields in enumerate(self.program.layout):
+            n = self.program.n_elems[r]
+            arrays = {}
+            for short, (off, size) in fields.items():
+                a = host[:, off:off + size].reshape((self.batch,) + tuple(_SHAPES[short](n)))
+                arrays[short] = a[0].copy() if self.batch == 1 else a.copy()
+            out.append(arrays)
+        return out
+
+    # ------------------------------------------------------------------ actuation
+    def set_pressures(self, values):
+        """``values``: per action slot a scalar or a length-batch array."""
+        if self.n_actions == 0:
+            return
+        host = np.zeros((self.n_actions, self.batch))
+        for a, value in enumerate(values):
+            host[a, :] = np.asarray(value, dtype=np.float64)
+        self.pressures[: self.n_actions].copy_(self.torch.from_numpy(host), non_blocking=False)
+
+    # ------------------------------------------------------------------ stepping
+    def step(self, n_steps, t0, dt):
+        """Advance all instances ``n_steps`` steps on the current stream; returns the end time."""
+        t_end = ctypes.c_double(0.0)
+        stream = self.torch.cuda.current_stream(self.device).cuda_stream
+        with self.torch.cuda.device(self.device):
+            _native.check(self.lib.br2_step(self.handle, int(n_steps), float(t0), float(dt),
+                                            ctypes.c_void_p(stream), ctypes.byref(t_end)))
+        if n_steps > 0:
+            self.launches += 1
+        return t_end.value
+
+    def kernel_info(self):
+        vals = [ctypes.c_int32(0) for _ in range(5)]
+        _native.check(self.lib.br2_kernel_info(self.handle, *[ctypes.byref(v) for v in vals]))
+        keys = ("registers", "smem_bytes", "threads", "blocks_per_sm", "sm_count")
+        return dict(zip(keys, (v.value for v in vals)))
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.lib.br2_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

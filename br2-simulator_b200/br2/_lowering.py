@@ -1,0 +1,249 @@
+"""Lower a finalized system collection to the flat tables of include/br2cuda.h.
+
+The reference keeps Python operator objects and walks them every step
+(/root/reference/br2/environment.py:279-285 -> PyElastica ``do_step``).  Here the same information --
+which operator acts on which rod / element, with which parameters, in which order -- becomes a
+handful of int32 / fp64 arrays that the CUDA kernel interprets (table formats: include/br2cuda.h).
+
+Notes on semantics that the tables must carry:
+* forcing rows are grouped per rod in registration order (upstream sorts stably by rod index);
+* joint rows keep registration order; each element's external torque and each node's external
+  force receive their joint contributions in that order (CSR gather lists);
+* a tip-to-base joint *overwrites* the director and omega of rod two's first element with those of
+  rod one's last element while ``synchronize`` runs (legacy_surface_connection_parallel_rod_numba.py:474-478);
+  any later joint sees the overwritten director.  ``Q1/Q2`` of a joint row and ``overwrite_src``
+  resolve these chains statically to "element whose start-of-synchronize value is used".
+"""
+import numpy as np
+
+from .hooks import ops as _ops
+from .hooks.rod import STATE_ORDER, field_sizes, rod_words
+
+ABI_VERSION = 1
+ROD_NI, ROD_ND = 8, 2
+SC_COUNT = 25
+SC_MASS, SC_REST_LEN, SC_VOLUME, SC_SHEAR, SC_J, SC_JINV, SC_LN_CR, SC_REST_SIGMA = 0, 1, 2, 3, 6, 9, 12, 15
+SC_REST_VLEN, SC_BEND, SC_REST_KAPPA = 18, 19, 22
+F_NI, F_ND = 4, 6
+C_NI, C_ND = 2, 14
+J_NI, J_ND = 8, 10
+ROD_HAS_DAMPER = 1
+MAX_SLOTS = 1024
+
+
+def _diagonal_only(matrix, what):
+    off = matrix.copy()
+    for axis in range(3):
+        off[axis, axis] = 0.0
+    if off.any():
+        raise _ops.NotLowerable("%s has off-diagonal entries; the device kernel supports diagonal "
+                                "constitutive matrices only" % what)
+    return np.stack([matrix[0, 0], matrix[1, 1], matrix[2, 2]])
+
+
+class Program:
+    """The lowered assembly: numpy tables + bookkeeping the engine needs."""
+
+    def __init__(self):
+        self.tables = {}
+        self.layout = []       # per rod: {short: (offset, size)}
+        self.n_elems = []
+        self.words = 0
+        self.n_slots = 0
+        self.action_lists = []  # python lists, one per action slot (the reference's shared lists)
+        self.action_names = []
+        self.total_elements = 0
+
+
+class LoweringContext:
+    def __init__(self, rods):
+        self.rods = rods
+        self.slot0 = []
+        slot = 0
+        for rod in rods:
+            self.slot0.append(slot)
+            slot += rod.n_elems + 1
+        self.n_slots = slot
+        self.forcing = [[] for _ in rods]      # per rod: (type, action, node, d)
+        self.constraints = [[] for _ in rods]  # per rod: (type, d)
+        self.dampers = {}
+        self.joints = []                       # (type, s1, s2, q1, q2, d, torque)
+        self.director_source = {}              # (rod, elem) -> (rod, elem) after overwrites so far
+        self.action_lists = []
+
+    # -- helpers the operator descriptors call ---------------------------------------------
+    def action_index(self, actuation_ref):
+        if not isinstance(actuation_ref, list):
+            raise TypeError("actuation_ref must be the shared python list handed out by "
+                            "FreeAssembly.get_actuation_reference")
+        for idx, known in enumerate(self.action_lists):
+            if known is actuation_ref:
+                return idx
+        self.action_lists.append(actuation_ref)
+        return len(self.action_lists) - 1
+
+    def add_forcing(self, rod_index, kind, action=-1, node=0, d=()):
+        row = np.zeros(F_ND)
+        row[:len(d)] = d
+        self.forcing[rod_index].append((kind, action, node, row))
+
+    def add_constraint(self, rod_index, kind, fixed_position, fixed_directors, k=0.0, nu=0.0):
+        row = np.zeros(C_ND)
+        row[0:3] = np.asarray(fixed_position, dtype=np.float64).reshape(3)
+        row[3:12] = np.asarray(fixed_directors, dtype=np.float64).reshape(3, 3).ravel()
+        row[12], row[13] = k, nu
+        self.constraints[rod_index].append((kind, row))
+
+    def set_damper(self, rod_index, c_t, ln_c_r):
+        if rod_index in self.dampers:
+            raise _ops.NotLowerable("more than one damper on a rod is not supported")
+        self.dampers[rod_index] = (c_t, np.asarray(ln_c_r, dtype=np.float64))
+
+    def _element(self, rod_index, idx):
+        n = self.rods[rod_index].n_elems
+        if not -n <= idx < n:
+            raise IndexError("connection index %d out of range for a rod with %d elements" % (idx, n))
+        return idx % n
+
+    def _resolve(self, rod_index, elem):
+        return self.director_source.get((rod_index, elem), (rod_index, elem))
+
+    def slot(self, rod_index, elem):
+        return self.slot0[rod_index] + elem
+
+    def add_joint(self, kind, rod_one, index_one, rod_two, index_two, d, overwrite, torque):
+        e1 = self._element(rod_one, index_one)
+        e2 = self._element(rod_two, index_two)
+        q1 = self._resolve(rod_one, e1)
+        q2 = self._resolve(rod_two, e2)
+        row = np.zeros(J_ND)
+        row[:len(d)] = d
+        self.joints.append((kind, self.slot(rod_one, e1), self.slot(rod_two, e2), self.slot(*q1), self.slot(*q2), row, torque))
+        if overwrite:
+            self.director_source[(rod_two, e2)] = q1
+
+
+def lower_collection(collection):
+    rods = list(collection._systems)
+    if not rods:
+        raise ValueError("nothing to integrate: no rod was appended")
+    ctx = LoweringContext(rods)
+    if ctx.n_slots > MAX_SLOTS:
+        raise _ops.NotLowerable(
+            "assembly has %d node slots; one CTA integrates one assembly and holds at most %d "
+            "(e.g. triple_br2 at n_elements=200 needs the multi-CTA cluster kernel, not built yet)"
+            % (ctx.n_slots, MAX_SLOTS))
+
+    for rod_index, op in collection._forcing:
+        op.lower_forcing(ctx, rod_index)
+    for rod_index, op in collection._constraint_ops:
+        op.lower_constraint(ctx, rod_index)
+    for rod_index, op in collection._damper_ops:
+        op.lower_damper(ctx, rod_index)
+    for rod_one, rod_two, idx_one, idx_two, op in collection._joints:
+        op.lower_joint(ctx, rod_one, idx_one, rod_two, idx_two)
+
+    prog = Program()
+    S = ctx.n_slots
+    prog.n_slots = S
+    slot_rod = np.zeros(S, dtype=np.int32)
+    rod_i = np.zeros((len(rods), ROD_NI), dtype=np.int32)
+    rod_d = np.zeros((len(rods), ROD_ND))
+    slot_c = np.zeros((SC_COUNT, S))
+    slot_c[SC_MASS] = 1.0
+    slot_c[SC_REST_LEN] = 1.0
+    slot_c[SC_VOLUME] = 1.0
+    slot_c[SC_REST_VLEN] = 1.0
+    slot_c[SC_J:SC_J + 3] = 1.0
+
+    forcing_rows, cons_rows = [], []
+    w_off = 0
+    for r, rod in enumerate(rods):
+        n = rod.n_elems
+        s0 = ctx.slot0[r]
+        slot_rod[s0:s0 + n + 1] = r
+        fields, off = {}, w_off
+        sizes = field_sizes(n)
+        for short in STATE_ORDER:
+            fields[short] = (off, sizes[short])
+            off += sizes[short]
+        prog.layout.append(fields)
+        prog.n_elems.append(n)
+        flags = 0
+        f_begin = len(forcing_rows)
+        forcing_rows.extend(ctx.forcing[r])
+        c_begin = len(cons_rows)
+        cons_rows.extend(ctx.constraints[r])
+        rod_d[r, 0] = 1.0
+        if r in ctx.dampers:
+            flags |= ROD_HAS_DAMPER
+            c_t, ln_c_r = ctx.dampers[r]
+            rod_d[r, 0] = c_t
+            slot_c[SC_LN_CR:SC_LN_CR + 3, s0:s0 + n] = ln_c_r
+        rod_i[r] = (n, s0, w_off, flags, f_begin, len(forcing_rows), c_begin, len(cons_rows))
+        w_off = off
+
+        slot_c[SC_MASS, s0:s0 + n + 1] = rod.mass
+        slot_c[SC_REST_LEN, s0:s0 + n] = rod.rest_lengths
+        slot_c[SC_VOLUME, s0:s0 + n] = rod.volume
+        slot_c[SC_SHEAR:SC_SHEAR + 3, s0:s0 + n] = _diagonal_only(rod.shear_matrix, "shear_matrix")
+        slot_c[SC_J:SC_J + 3, s0:s0 + n] = _diagonal_only(rod.mass_second_moment_of_inertia, "mass_second_moment_of_inertia")
+        slot_c[SC_JINV:SC_JINV + 3, s0:s0 + n] = _diagonal_only(rod.inv_mass_second_moment_of_inertia, "inv_mass_second_moment_of_inertia")
+        slot_c[SC_REST_SIGMA:SC_REST_SIGMA + 3, s0:s0 + n] = rod.rest_sigma
+        if n > 1:
+            slot_c[SC_REST_VLEN, s0:s0 + n - 1] = rod.rest_voronoi_lengths
+            slot_c[SC_BEND:SC_BEND + 3, s0:s0 + n - 1] = _diagonal_only(rod.bend_matrix, "bend_matrix")
+            slot_c[SC_REST_KAPPA:SC_REST_KAPPA + 3, s0:s0 + n - 1] = rod.rest_kappa
+    prog.words = w_off
+    assert w_off == sum(rod_words(rod.n_elems) for rod in rods)
+    prog.total_elements = int(sum(rod.n_elems for rod in rods))
+
+    forcing_i = np.zeros((len(forcing_rows), F_NI), dtype=np.int32)
+    forcing_d = np.zeros((len(forcing_rows), F_ND))
+    for f, (kind, action, node, row) in enumerate(forcing_rows):
+        forcing_i[f, :3] = (kind, action, node)
+        forcing_d[f] = row
+    cons_i = np.zeros((len(cons_rows), C_NI), dtype=np.int32)
+    cons_d = np.zeros((len(cons_rows), C_ND))
+    for c, (kind, row) in enumerate(cons_rows):
+        cons_i[c, 0] = kind
+        cons_d[c] = row
+
+    NJ = len(ctx.joints)
+    joint_i = np.zeros((NJ, J_NI), dtype=np.int32)
+    joint_d = np.zeros((NJ, J_ND))
+    node_lists = [[] for _ in range(S)]
+    elem_lists = [[] for _ in range(S)]
+    for j, (kind, s1, s2, q1, q2, row, torque) in enumerate(ctx.joints):
+        joint_i[j, :5] = (kind, s1, s2, q1, q2)
+        joint_d[j] = row
+        node_lists[s1].append((j << 1) | 0)
+        node_lists[s1 + 1].append((j << 1) | 0)
+        node_lists[s2].append((j << 1) | 1)
+        node_lists[s2 + 1].append((j << 1) | 1)
+        if torque:
+            elem_lists[s1].append((j << 1) | 0)
+            elem_lists[s2].append((j << 1) | 1)
+
+    def csr(lists):
+        ptr = np.zeros(S + 1, dtype=np.int32)
+        ptr[1:] = np.cumsum([len(items) for items in lists])
+        flat = [item for items in lists for item in items]
+        return ptr, np.array(flat, dtype=np.int32).reshape(-1)
+
+    node_ptr, node_items = csr(node_lists)
+    elem_ptr, elem_items = csr(elem_lists)
+    overwrite_src = np.full(S, -1, dtype=np.int32)
+    for (rod_index, elem), src in ctx.director_source.items():
+        overwrite_src[ctx.slot(rod_index, elem)] = ctx.slot(*src)
+
+    prog.action_lists = ctx.action_lists
+    prog.tables = dict(
+        slot_rod=slot_rod, rod_i=rod_i, rod_d=rod_d, slot_c=slot_c, forcing_i=forcing_i, forcing_d=forcing_d,
+        cons_i=cons_i, cons_d=cons_d, joint_i=joint_i, joint_d=joint_d, node_ptr=node_ptr,
+        node_items=node_items, elem_ptr=elem_ptr, elem_items=elem_items, overwrite_src=overwrite_src,
+    )
+    prog.tables = {k: np.ascontiguousarray(v) for k, v in prog.tables.items()}
+    prog.counts = dict(n_slots=S, n_rods=len(rods), n_forcing=len(forcing_rows), n_constraints=len(cons_rows),
+                       n_joints=NJ, n_actions=len(ctx.action_lists))
+    return prog

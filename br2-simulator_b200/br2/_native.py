@@ -1,0 +1,102 @@
+"""ctypes binding of libbr2cuda.so (C ABI: include/br2cuda.h).
+
+The library is built in-tree (``br2-simulator_b200/lib/libbr2cuda.so``) by
+``__graft_entry__.build()``.  If it is missing or fails to load this module raises: the package has
+no CPU fallback.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(PKG_DIR, "lib", "libbr2cuda.so")
+ABI_VERSION = 1
+
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_f64p = ctypes.POINTER(ctypes.c_double)
+
+
+class Br2Program(ctypes.Structure):
+    """``struct br2_program`` of include/br2cuda.h."""
+
+    _fields_ = [
+        ("abi_version", ctypes.c_int32),
+        ("n_slots", ctypes.c_int32), ("n_rods", ctypes.c_int32), ("n_forcing", ctypes.c_int32),
+        ("n_constraints", ctypes.c_int32), ("n_joints", ctypes.c_int32), ("n_actions", ctypes.c_int32),
+        ("words_per_instance", ctypes.c_int64),
+        ("slot_rod", ctypes.c_void_p), ("rod_i", ctypes.c_void_p), ("rod_d", ctypes.c_void_p),
+        ("slot_c", ctypes.c_void_p), ("forcing_i", ctypes.c_void_p), ("forcing_d", ctypes.c_void_p),
+        ("cons_i", ctypes.c_void_p), ("cons_d", ctypes.c_void_p), ("joint_i", ctypes.c_void_p),
+        ("joint_d", ctypes.c_void_p), ("node_ptr", ctypes.c_void_p), ("node_items", ctypes.c_void_p),
+        ("elem_ptr", ctypes.c_void_p), ("elem_items", ctypes.c_void_p), ("overwrite_src", ctypes.c_void_p),
+    ]
+
+
+class Br2Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+EXPORTS = (
+    "br2_last_error", "br2_abi_version", "br2_create", "br2_destroy", "br2_words_per_instance",
+    "br2_bind_state", "br2_set_actuation", "br2_step", "br2_step_host", "br2_count_steps",
+    "br2_kernel_info", "br2_fp64_peak_tflops",
+)
+
+
+def load():
+    """Load (once) and return the library; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Br2Error(
+            "CUDA library %s not found. Build it with `python -c \"import __graft_entry__ as g; g.build()\"` "
+            "from the repo root. This package has no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.br2_last_error.restype = ctypes.c_char_p
+    lib.br2_abi_version.restype = ctypes.c_int
+    lib.br2_create.argtypes = [ctypes.POINTER(Br2Program), ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+    lib.br2_destroy.argtypes = [ctypes.c_void_p]
+    lib.br2_words_per_instance.argtypes = [ctypes.c_void_p]
+    lib.br2_words_per_instance.restype = ctypes.c_int64
+    lib.br2_bind_state.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+    lib.br2_set_actuation.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    lib.br2_step.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_void_p, _f64p]
+    lib.br2_step_host.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                  ctypes.c_int64, ctypes.c_double, ctypes.c_double, _f64p]
+    lib.br2_count_steps.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                    ctypes.POINTER(ctypes.c_int64), _f64p]
+    lib.br2_kernel_info.argtypes = [ctypes.c_void_p] + [_i32p] * 5
+    lib.br2_fp64_peak_tflops.argtypes = [ctypes.c_int, ctypes.c_int32, _f64p]
+    if lib.br2_abi_version() != ABI_VERSION:
+        raise Br2Error("libbr2cuda.so ABI %d != expected %d; rebuild" % (lib.br2_abi_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise Br2Error("libbr2cuda error %d: %s" % (rc, load().br2_last_error().decode("utf-8", "replace")))
+
+
+def make_program(prog):
+    """ctypes view of a ``br2._lowering.Program`` (the numpy tables stay owned by ``prog``)."""
+    t, c = prog.tables, prog.counts
+    return Br2Program(
+        ABI_VERSION, c["n_slots"], c["n_rods"], c["n_forcing"], c["n_constraints"], c["n_joints"], c["n_actions"],
+        prog.words,
+        *[t[name].ctypes.data for name in (
+            "slot_rod", "rod_i", "rod_d", "slot_c", "forcing_i", "forcing_d", "cons_i", "cons_d", "joint_i",
+            "joint_d", "node_ptr", "node_items", "elem_ptr", "elem_items", "overwrite_src")])
+
+
+def count_steps(t0, duration, dt):
+    """(n_steps, t_end) of ``while time < t0 + duration`` with two ``+dt/2`` per step
+    (/root/reference/br2/environment.py:278-286)."""
+    n = ctypes.c_int64(0)
+    t_end = ctypes.c_double(0.0)
+    check(load().br2_count_steps(float(t0), float(duration), float(dt), ctypes.byref(n), ctypes.byref(t_end)))
+    return n.value, t_end.value

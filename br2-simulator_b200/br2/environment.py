@@ -1,0 +1,251 @@
+"""User-facing environment, drop-in for /root/reference/br2/environment.py.
+
+Same constructor, ``reset`` / ``run`` / ``save_state`` / ``load_state`` / ``save_data`` / ``render_video`` /
+``close`` and the same attributes (``assy``, ``simulator``, ``shearable_rods``, ``data_rods``, ``time``,
+``time_step``, ``step_skip``, thresholds).  Extensions: ``batch`` (number of independent assembly
+instances integrated side by side on the GPU) and ``device``; with ``batch > 1`` an ``action`` value
+may be a length-``batch`` array and per-instance results are returned next to the reference's scalars.
+
+The reference's hot loop (``while time < self.time + duration: time = self.do_step(...)``,
+:278-286) is replaced by a handful of kernel launches: the number of steps is fixed up front by the
+same fp64 accumulation the loop performs, and launches are split only where a diagnostics callback
+has to fire (every ``step_skip`` steps, ``current_step = round(time / dt)``).
+"""
+import logging
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _native
+from .free_simulator import FreeAssembly
+from .hooks import PositionVerlet, extend_stepper_interface
+
+
+@dataclass
+class DataPaths:
+    """Result directories of one run tag: ``result_<tag>/{simulation_saves,renderings,data}``."""
+
+    tag: str
+
+    @property
+    def paths(self) -> str:
+        return "result_%s" % self.tag
+
+    @property
+    def simulation(self) -> str:
+        return os.path.join(self.paths, "simulation_saves")
+
+    @property
+    def renderings(self) -> str:
+        return os.path.join(self.paths, "renderings")
+
+    @property
+    def data(self) -> str:
+        return os.path.join(self.paths, "data")
+
+    def initialize(self):
+        for directory in (self.paths, self.simulation, self.renderings, self.data):
+            os.makedirs(directory, exist_ok=True)
+
+
+@dataclass
+class TerminalInfo:
+    """Outcome of ``Environment.run``.  ``<x>_nan_status`` / ``<x>_steady_state_status`` attributes are
+    attached only when the corresponding check was requested, as in the reference (:72-131)."""
+
+    end_status: bool = False
+
+    def _status_names(self):
+        return [name for name in self.__dir__() if name.endswith("status")]
+
+    def __str__(self):
+        return "\n".join("%s = %s" % (name, getattr(self, name)) for name in self._status_names())
+
+    @property
+    def combined_nan_status(self) -> bool:
+        # reference semantics (:113): all() over the individual NaN flags
+        return all(getattr(self, n) for n in self._status_names() if "_nan_" in n and "combined_" not in n)
+
+    @property
+    def combined_steady_state_status(self) -> bool:
+        # reference semantics (:131): any() over the individual steady-state flags
+        return any(getattr(self, n) for n in self._status_names() if "_steady_state_" in n and "combined_" not in n)
+
+
+def _capture_plan(collection, start_time, n_steps, dt):
+    """Ordinals (1-based, within this run) of the steps after which some callback fires, using the
+    reference's own step index ``round(time / dt)`` on the fp64-accumulated time."""
+    if not collection._callback_ops:
+        return []
+    plan = []
+    time = start_time
+    half = 0.5 * dt
+    for ordinal in range(1, n_steps + 1):
+        time += half
+        time += half
+        if collection.callbacks_due(round(time / dt)):
+            plan.append((ordinal, time))
+    return plan
+
+
+class Environment:
+    def __init__(self, run_tag: str, rendering_fps: int = 25, time_step: float = 2.0e-5,
+                 final_time: Optional[float] = None, *, batch: int = 1, device=None, create_dirs: bool = True):
+        self.StatefulStepper = PositionVerlet()
+        self.paths = DataPaths(run_tag)
+        if create_dirs:
+            self.paths.initialize()
+        self.final_time = final_time
+        self.time_step = time_step
+        self.rendering_fps = rendering_fps
+        self.step_skip = int(1.0 / (self.rendering_fps * self.time_step))
+        self.capture_interval = None
+        self.shearable_rods = {}
+        self.batch = int(batch)
+        self.device = device
+        # steady-state thresholds (reference :176-181)
+        self.position_threshold = 1.0e-7
+        self.director_threshold = 1.0e-5
+        self.velocity_threshold = 1.0e-4
+        self.omega_threshold = 1.0e-3
+        self.acceleration_threshold = 10 ** (0)
+        self.alpha_threshold = 1.0e1
+
+    # ------------------------------------------------------------------ reset (reference :183-224)
+    def reset(self, rod_database_path: str, assembly_config_path: str, start_time: float = 0.0, **kwargs) -> None:
+        assert os.path.exists(rod_database_path), "Rod database path does not exists."
+        assert os.path.exists(assembly_config_path), "Assembly configuration does not exists."
+        verbose = kwargs.pop("verbose", False)
+        self.assy = FreeAssembly(self, **kwargs)
+        self.shearable_rods = self.assy.build(rod_database_path, assembly_config_path, verbose=verbose)
+        self.simulator = self.assy.simulator
+        self.data_rods = self.assy.generate_callbacks(self.step_skip, time_interval=self.capture_interval)
+        self.simulator.batch = self.batch
+        self.simulator.device = self.device
+        self.simulator.finalize()
+        self.engine = self.simulator.engine
+        self.do_step, self.stages_and_updates = extend_stepper_interface(self.StatefulStepper, self.simulator)
+        self.time = start_time
+
+    # ------------------------------------------------------------------ run (reference :226-352)
+    def _push_actuation(self):
+        program = self.simulator.program
+        self.engine.set_pressures([shared[0] for shared in program.action_lists])
+
+    def _state_stack(self, short):
+        """[batch, 3 (or 3,3), total] device tensor: one field concatenated over rods (reference :259-265)."""
+        torch = self.engine.torch
+        return torch.cat([self.engine.view(r, short) for r in range(len(self.simulator))], dim=-1)
+
+    def run(self, action: dict, duration: Optional[float] = None, disable_progress_bar: bool = False,
+            check_nan: bool = False, check_steady_state: Optional[int] = None) -> TerminalInfo:
+        status = TerminalInfo()
+        self.assy.set_actuation(action)
+        self._push_actuation()
+        engine, dt = self.engine, self.time_step
+
+        previous = None
+        if check_steady_state == 2:
+            previous = {short: self._state_stack(short).clone() for short in ("x", "v", "a", "Q", "w", "alpha")}
+
+        if not duration:
+            duration = dt
+        n_steps, _ = _native.count_steps(self.time, duration, dt)
+        plan = _capture_plan(self.simulator, self.time, n_steps, dt)
+
+        progress = None
+        if not disable_progress_bar:
+            from tqdm import tqdm
+
+            progress = tqdm(total=self.time + duration, mininterval=0.5,
+                            bar_format="{desc}: {percentage:.3f}%|{bar}| {n:.5f}/{total_fmt} [{elapsed}<{remaining}")
+        time, done = self.time, 0
+        stops = [ordinal for ordinal, _ in plan]
+        if not stops or stops[-1] != n_steps:
+            stops.append(n_steps)
+        for stop in stops:
+            chunk = stop - done
+            if chunk > 0:
+                time = self.do_step(self.StatefulStepper, self.stages_and_updates, self.simulator, time, dt,
+                                    n_steps=chunk, callbacks=True)
+                done = stop
+                if progress is not None:
+                    progress.update(chunk * dt)
+        if progress is not None:
+            progress.close()
+        self.time = time
+
+        torch = engine.torch
+        if check_steady_state == 1:
+            # the reference measures node POSITIONS here although it calls them velocities (:292-298)
+            per_instance = torch.linalg.vector_norm(self._state_stack("x"), dim=1).amax(dim=-1)
+            max_velocity = float(per_instance.max())
+            status.velocity_steady_state_status = max_velocity < self.velocity_threshold
+            status.max_velocity = max_velocity
+            status.max_velocity_per_instance = per_instance.cpu().numpy()
+        elif check_steady_state == 2:
+            # the reference computes these six deltas and discards them (:300-338); they are exposed
+            # under a name its combined_* properties do not pick up.
+            deltas = {}
+            for short in previous:
+                diff = previous[short] - self._state_stack(short)
+                dims = (1, 2) if short == "Q" else (1,)
+                norms = torch.linalg.vector_norm(diff, dim=dims)
+                deltas[short] = torch.nan_to_num(norms, nan=-np.inf).amax(dim=-1).cpu().numpy()
+            status.steady_state_deltas = deltas
+        if check_nan:
+            flags = {}
+            for label, short in (("position", "x"), ("velocity", "v"), ("director", "Q"), ("omega", "w")):
+                per_instance = torch.isnan(self._state_stack(short)).flatten(1).any(dim=1)
+                flags[label] = per_instance.cpu().numpy()
+                setattr(status, "%s_nan_status" % label, bool(per_instance.any()))
+            status.nan_per_instance = flags
+        status.end_status = True
+        return status
+
+    # ------------------------------------------------------------------ checkpoint (reference :354-392)
+    def save_state(self, directory: Optional[str] = None, verbose: bool = False) -> None:
+        self.assy.save_state(directory=directory or self.paths.simulation, time=self.time, verbose=verbose)
+
+    def load_state(self, directory: str = "", clear_callback: bool = False, verbose: bool = False) -> None:
+        self.assy.load_state(directory=directory or self.paths.simulation, verbose=verbose)
+        if clear_callback:
+            for sink in self.data_rods:
+                sink.clear()
+            if verbose:
+                print("callback cleared")
+
+    # ------------------------------------------------------------------ export (reference :394-464)
+    def render_video(self, visualize_twist_angle: bool = False, **kwargs) -> None:
+        save_folder = self.paths.renderings
+        if os.path.exists(save_folder):
+            logging.warning("The folder already exists. The data will be overwritten.")
+        os.makedirs(save_folder, exist_ok=True)
+        from .visualize import plot_video_with_surface, visual_twist_with_surface
+
+        plot_video_with_surface(self.data_rods, video_name="br2_simulation", fps=self.rendering_fps, step=1,
+                                save_folder=save_folder, **kwargs)
+        if visualize_twist_angle:
+            visual_twist_with_surface(self.data_rods, video_name="br2_simulation", fps=self.rendering_fps, step=1,
+                                      save_folder=save_folder, **kwargs)
+        self.save_data("position")
+
+    def save_data(self, tag: Optional[str] = None) -> None:
+        """``time``, element-centre ``positions [rod, T, (batch,) 3, n]`` and ``directors
+        [rod, T, (batch,) 3, 3, n]`` to ``result_<tag>/data/br2_data[_tag].npz`` (reference :431-464)."""
+        filename = "br2_data_%s.npz" % tag if tag else "br2_data.npz"
+        os.makedirs(self.paths.data, exist_ok=True)
+        positions, directors = [], []
+        for sink in self.data_rods:
+            nodes = np.array(sink["position"])
+            positions.append(0.5 * (nodes[..., 1:] + nodes[..., :-1]))
+            directors.append(np.array(sink["director"]))
+        np.savez(os.path.join(self.paths.data, filename), time=np.array(self.data_rods[0]["time"]),
+                 positions=np.asarray(positions), directors=np.asarray(directors))
+
+    def close(self):
+        engine = getattr(self, "engine", None)
+        if engine is not None:
+            engine.close()

@@ -1,0 +1,37 @@
+"""Stepper seam: ``do_step, stages = extend_stepper_interface(PositionVerlet(), simulator)`` and
+``time = do_step(stepper, stages, simulator, time, dt)`` exactly as the reference calls them
+(/root/reference/br2/environment.py:155, :221-223, :279-285).
+
+One call advances one PositionVerlet step of every batch instance on the GPU; pass ``n_steps=K`` to
+advance K steps in a single kernel launch (state stays in registers between the steps).  Diagnostics
+callbacks are the caller's business when K > 1 (``Environment.run`` splits launches at capture steps).
+"""
+
+
+class PositionVerlet:
+    """Marker for the only integrator of the path (half kinematic / dynamic / half kinematic)."""
+
+
+class _DeviceStages:
+    def __init__(self, stepper, collection):
+        if not isinstance(stepper, PositionVerlet):
+            raise TypeError("only PositionVerlet is implemented on the device")
+        self.collection = collection
+
+
+def _do_step(stepper, stages_and_updates, collection, time, dt, n_steps=1, callbacks=True):
+    engine = collection.engine
+    if engine is None:
+        raise RuntimeError("finalize() the collection before stepping")
+    end = engine.step(n_steps, time, dt)
+    if callbacks and collection._callback_ops:
+        current_step = round(end / dt)
+        if collection.callbacks_due(current_step):
+            snap = collection.snapshot_views()
+            for rod_index, op in collection._callback_ops:
+                op.make_callback(snap[rod_index], end, current_step)
+    return end
+
+
+def extend_stepper_interface(stepper, system_collection):
+    return _do_step, _DeviceStages(stepper, system_collection)

@@ -1,0 +1,179 @@
+/*
+ * br2cuda.h -- C ABI of libbr2cuda.so: the B200 (sm_100a) replacement for the rod-integration hot
+ * path of BR2-simulator.
+ *
+ * What it replaces.  In the reference the path is entered from exactly one place, the loop
+ *     while time < self.time + duration:
+ *         time = self.do_step(self.StatefulStepper, self.stages_and_updates, self.simulator, time, dt)
+ * (/root/reference/br2/environment.py:278-285), where `do_step` comes from PyElastica's
+ * `extend_stepper_interface(PositionVerlet(), simulator)` (environment.py:221-223) and `simulator`
+ * is the system collection filled by `FreeAssembly.build` (/root/reference/br2/free_simulator.py:101-268)
+ * through the hooks append / dampen / constrain / add_forcing_to / connect / collect_diagnostics /
+ * finalize.  There is no FFI in the reference: the seam is the Python callable above.  The drop-in
+ * therefore is (1) a `br2` Python package with the same classes and hooks whose `finalize()` lowers
+ * the registered operators to the flat tables below, and (2) this library, which a maintainer binds
+ * with ctypes (INTEGRATION.md shows the stub) -- or from any language with a C FFI.
+ *
+ * Conventions: every entry point returns 0 on success or a negative BR2_E* code; the message is
+ * available from br2_last_error() (thread-local).  No exceptions or C++ types cross the boundary.
+ * Device pointers are BORROWED (typically PyTorch-owned); the library never frees them.  One host
+ * thread drives one handle; handles on different GPUs are independent.
+ */
+#ifndef BR2CUDA_H
+#define BR2CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BR2_ABI_VERSION 1
+
+enum {
+    BR2_OK = 0,
+    BR2_EINVAL = -1,   /* malformed program / argument */
+    BR2_ECUDA = -2,    /* CUDA runtime error (message holds cudaGetErrorString) */
+    BR2_ELIMIT = -3,   /* assembly does not fit the kernel's resource limits */
+    BR2_ESTATE = -4    /* call order error (e.g. step before bind) */
+};
+
+/* ---- table layout (what finalize() lowers the registered operators to) ---------------------
+ *
+ * A "slot" is one CUDA thread's share of an assembly: node k and (for k < n) element k and
+ * (for k < n-1) Voronoi cell k of one rod.  Rod r with n elements owns slots slot0 .. slot0+n.
+ * All tables are host arrays; br2_create copies them to the device.
+ */
+
+/* rod_i: [n_rods][BR2_ROD_NI] int32 */
+enum {
+    BR2_ROD_N = 0,        /* elements */
+    BR2_ROD_SLOT0 = 1,    /* first slot */
+    BR2_ROD_WOFF = 2,     /* offset (doubles) of the rod's block inside one instance's state */
+    BR2_ROD_FLAGS = 3,    /* BR2_ROD_HAS_DAMPER */
+    BR2_ROD_F_BEGIN = 4,  /* forcing rows [begin, end) of this rod, in execution order */
+    BR2_ROD_F_END = 5,
+    BR2_ROD_C_BEGIN = 6,  /* constraint rows [begin, end) of this rod, in execution order */
+    BR2_ROD_C_END = 7,
+    BR2_ROD_NI = 8
+};
+enum { BR2_ROD_HAS_DAMPER = 1 };
+/* rod_d: [n_rods][BR2_ROD_ND] double : translational damping factor exp(-nu dt) */
+enum { BR2_ROD_CT = 0, BR2_ROD_ND = 2 };
+
+/* slot_c: [BR2_SC_COUNT][n_slots] double, per-slot constants (PyElastica CosseratRod arrays,
+ * SURVEY.md Appendix A.2; only the diagonals of the constitutive matrices are supported) */
+enum {
+    BR2_SC_MASS = 0,       /* node */
+    BR2_SC_REST_LEN = 1,   /* element */
+    BR2_SC_VOLUME = 2,
+    BR2_SC_SHEAR = 3,      /* 3: diag(shear_matrix) */
+    BR2_SC_J = 6,          /* 3: diag(mass_second_moment_of_inertia) */
+    BR2_SC_JINV = 9,       /* 3: diag(inv_mass_second_moment_of_inertia) */
+    BR2_SC_LN_CR = 12,     /* 3: ln(rotational_damping_coefficient) of AnalyticalLinearDamper */
+    BR2_SC_REST_SIGMA = 15,/* 3 */
+    BR2_SC_REST_VLEN = 18, /* Voronoi */
+    BR2_SC_BEND = 19,      /* 3: diag(bend_matrix) */
+    BR2_SC_REST_KAPPA = 22,/* 3 */
+    BR2_SC_COUNT = 25
+};
+
+/* forcing_i: [n_forcing][BR2_F_NI] int32 ; forcing_d: [n_forcing][BR2_F_ND] double */
+enum { BR2_F_TYPE = 0, BR2_F_ACTION = 1, BR2_F_NODE = 2, BR2_F_NI = 4, BR2_F_ND = 6 };
+enum {
+    BR2_FORCE_GRAVITY = 0, /* d = {g[3]}                       elastica GravityForces (free_simulator.py:334-338) */
+    BR2_FORCE_TWIST = 1,   /* d = {scale, ramp_up_time}        FreeTwistActuation (free_custom_systems.py:96-101) */
+    BR2_FORCE_BEND = 2,    /* d = {scale, ramp_up_time, cos z, sin z}  FreeBendActuation (free_custom_systems.py:49-57) */
+    BR2_FORCE_POINT = 3    /* d = {F[3], ramp_up_time}, node   PointForces (custom_activation.py:46-81) */
+};
+
+/* cons_i: [n_constraints][BR2_C_NI] int32 ; cons_d: [n_constraints][BR2_C_ND] double
+ * d = {fixed_position[3], fixed_directors[9] row-major, k, nu} */
+enum { BR2_C_TYPE = 0, BR2_C_NI = 2, BR2_C_ND = 14 };
+enum {
+    BR2_CONS_SOFT_FIXED_BASE = 0, /* FreeBaseEndSoftFixed (free_custom_systems.py:104-185) */
+    BR2_CONS_LAST_END_FIXED = 1   /* LastEndFixedRod (custom_constraint.py:9-88) */
+};
+
+/* joint_i: [n_joints][BR2_J_NI] int32 ; joint_d: [n_joints][BR2_J_ND] double, registration order.
+ * S1/S2: element slots of rod one / rod two; Q1/Q2: element slots whose (start-of-synchronize)
+ * directors the joint sees -- differ from S1/S2 only downstream of a tip-to-base joint's
+ * director overwrite (legacy_surface_connection_parallel_rod_numba.py:474-478). */
+enum { BR2_J_TYPE = 0, BR2_J_S1 = 1, BR2_J_S2 = 2, BR2_J_Q1 = 3, BR2_J_Q2 = 4, BR2_J_NI = 8, BR2_J_ND = 10 };
+enum {
+    BR2_JOINT_SURFACE = 0,    /* d = {k, nu, k_repulsive, dv1[3], dv2[3], offset}  elastica SurfaceJointSideBySide */
+    BR2_JOINT_TIP_TO_BASE = 1 /* d = {k, nu, 0, l1[3], l2[3], 0}                   TipToTipStraightJoint (legacy...:346-478) */
+};
+
+typedef struct br2_program {
+    int32_t abi_version;          /* BR2_ABI_VERSION */
+    int32_t n_slots, n_rods, n_forcing, n_constraints, n_joints, n_actions;
+    int64_t words_per_instance;   /* doubles of state + derived per instance */
+    const int32_t *slot_rod;      /* [n_slots] rod of each slot */
+    const int32_t *rod_i;
+    const double *rod_d;
+    const double *slot_c;
+    const int32_t *forcing_i;
+    const double *forcing_d;
+    const int32_t *cons_i;
+    const double *cons_d;
+    const int32_t *joint_i;
+    const double *joint_d;
+    /* CSR gather lists, per slot, in joint registration order.  item = (joint << 1) | bit.
+     * node list: bit 0 -> rod one (+F/2), bit 1 -> rod two (-F/2).  elem list: bit = which side's torque. */
+    const int32_t *node_ptr;      /* [n_slots + 1] */
+    const int32_t *node_items;
+    const int32_t *elem_ptr;      /* [n_slots + 1] */
+    const int32_t *elem_items;
+    const int32_t *overwrite_src; /* [n_slots] element slot whose director/omega replace this slot's during
+                                     synchronize (tip-to-base joint), or -1 */
+} br2_program;
+
+/* Instance state layout (doubles), per rod at BR2_ROD_WOFF, component-major like numpy [3, n]:
+ *   position 3(n+1) | velocity 3(n+1) | director 9n | omega 3n            <- read at launch, written back
+ *   acceleration 3(n+1) | alpha 3n | internal_forces 3(n+1) | internal_torques 3n |
+ *   external_forces 3(n+1) | external_torques 3n | lengths n | dilatation n | radius n   <- written only
+ * (exactly the 12 arrays FreeCallback copies, /root/reference/br2/free_simulator.py:56-72, plus alpha). */
+
+typedef struct br2_handle_s *br2_handle;
+
+const char *br2_last_error(void);
+int br2_abi_version(void);
+
+/* Lower-level life cycle ------------------------------------------------------------------- */
+int br2_create(const br2_program *program, int device, br2_handle *out);
+int br2_destroy(br2_handle h);
+int64_t br2_words_per_instance(br2_handle h);
+
+/* Borrow a device buffer of batch * words_per_instance doubles (instance-major). */
+int br2_bind_state(br2_handle h, double *dev_state, int64_t batch);
+/* Borrow per-instance actuation pressures, device, [n_actions][batch] doubles
+ * (replaces FreeAssembly.set_actuation's shared python lists, free_simulator.py:276-289). */
+int br2_set_actuation(br2_handle h, const double *dev_pressures);
+
+/* Advance every bound instance n_steps PositionVerlet steps starting at time t0 (replaces n_steps
+ * calls of do_step, environment.py:279-285).  Asynchronous on `stream` (a cudaStream_t, e.g.
+ * torch.cuda.current_stream().cuda_stream).  *t_end receives the fp64-accumulated end time. */
+int br2_step(br2_handle h, int64_t n_steps, double t0, double dt, void *stream, double *t_end);
+
+/* Same through HOST buffers: H2D of state and pressures, step, D2H of the state; synchronous. */
+int br2_step_host(br2_handle h, double *host_state, const double *host_pressures, int64_t batch,
+                  int64_t n_steps, double t0, double dt, double *t_end);
+
+/* Number of do_step calls `while time < t0 + duration` makes, and the time it ends at
+ * (environment.py:278: the count comes from fp64 accumulation, two +dt/2 per step). */
+int br2_count_steps(double t0, double duration, double dt, int64_t *n_steps, double *t_end);
+
+/* Kernel facts for measurement: registers per thread, dynamic shared memory per block, threads per
+ * block, resident blocks per SM as reported by the occupancy API, SM count of the device. */
+int br2_kernel_info(br2_handle h, int32_t *regs, int32_t *smem_bytes, int32_t *threads,
+                    int32_t *blocks_per_sm, int32_t *sm_count);
+
+/* fp64 roofline denominator: runs a register-resident DFMA chain kernel on `device` and returns the
+ * best-of-`repeats` rate in TFLOP/s (FMA = 2 flop). */
+int br2_fp64_peak_tflops(int device, int32_t repeats, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BR2CUDA_H */

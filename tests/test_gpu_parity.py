@@ -1,0 +1,201 @@
+"""GPU parity: the CUDA path (through the br2 package and the C ABI) against the oracle.
+
+Tolerances (BASELINE.json north_star): positions max|dx|/max|x| <= 1e-9 and directors max|dQ| <= 1e-9
+after 10^4 steps, fp64.  Velocities / omegas sit on the rounding-noise floor of the dynamics
+(tests/test_oracle_fused.py measures ~1e-9 / ~3e-8 between two CPU builds that differ in one ulp of
+``pow``), so they get looser, stated bounds."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import DATA, GOLDEN
+from golden.cases import CALLBACK_KEYS, TRAJECTORIES
+
+pytestmark = pytest.mark.gpu
+
+ROD_DB = os.path.join(DATA, "rod_library.json")
+ASSEMBLY = {k: os.path.join(DATA, "assembly_%s.json" % k) for k in ("single", "double", "triple")}
+PSI = 6895.0
+NAMES = ["action1", "action2", "action3"]
+POS_TOL, DIR_TOL, VEL_TOL, OMEGA_TOL = 1e-9, 1e-9, 1e-7, 1e-5
+
+SHORT = {"position_collection": "x", "velocity_collection": "v", "director_collection": "Q",
+         "omega_collection": "w", "acceleration_collection": "a"}
+
+
+def make_env(assembly, batch, fps=25, **kwargs):
+    from br2.environment import Environment
+
+    env = Environment("gpu_test", rendering_fps=fps, batch=batch, create_dirs=False)
+    env.reset(ROD_DB, ASSEMBLY[assembly], **kwargs)
+    return env
+
+
+@pytest.mark.parametrize("case", TRAJECTORIES, ids=[c[0] for c in TRAJECTORIES])
+def test_golden_trajectories(case):
+    """Same assembly JSON, action, dt and duration as the golden runs of the reference's real br2 code."""
+    name, assembly, kwargs, action, duration, fps = case
+    g = np.load(os.path.join(GOLDEN, "traj_%s.npz" % name))
+    env = make_env(assembly, 1, fps=fps, **kwargs)
+    status = env.run(action, duration=duration, disable_progress_bar=True, check_nan=True, check_steady_state=1)
+    assert env.time == float(g["final_time"]) and env.step_skip == int(g["step_skip"])
+    assert list(env.shearable_rods.keys()) == list(g["rod_names"])
+    assert not (status.position_nan_status or status.director_nan_status)
+    assert abs(status.max_velocity - float(g["max_velocity"])) <= POS_TOL * float(g["max_velocity"])
+    x_scale = max(np.abs(g["rod%d_position_collection" % i]).max() for i in range(len(env.simulator)))
+    for idx, rod in enumerate(env.shearable_rods.values()):
+        assert np.abs(rod.position_collection - g["rod%d_position_collection" % idx]).max() <= POS_TOL * x_scale
+        assert np.abs(rod.director_collection - g["rod%d_director_collection" % idx]).max() <= DIR_TOL
+        assert np.abs(rod.velocity_collection - g["rod%d_velocity_collection" % idx]).max() <= VEL_TOL
+        assert np.abs(rod.omega_collection - g["rod%d_omega_collection" % idx]).max() <= OMEGA_TOL
+        # callback history: same cadence, keys and shapes as FreeCallback in the reference
+        sink = env.data_rods[idx]
+        np.testing.assert_array_equal(np.array(sink["step"]), g["rod%d_cb_step" % idx])
+        np.testing.assert_array_equal(np.array(sink["time"]), g["rod%d_cb_time" % idx])
+        for key in CALLBACK_KEYS:
+            got, want = np.array(sink[key]), g["rod%d_cb_%s" % (idx, key)]
+            assert got.shape == want.shape, key
+        for key, tol in (("position", POS_TOL * x_scale), ("director", DIR_TOL), ("com", POS_TOL * x_scale),
+                         ("lengths", 1e-12), ("radius", 1e-12), ("dilatation", 1e-9)):
+            assert np.abs(np.array(sink[key]) - g["rod%d_cb_%s" % (idx, key)]).max() <= tol, key
+        for key in ("internal_forces", "external_forces", "internal_torques", "external_torques", "acceleration"):
+            want = g["rod%d_cb_%s" % (idx, key)]
+            assert np.abs(np.array(sink[key]) - want).max() <= 1e-6 * max(np.abs(want).max(), 1.0), key
+    env.close()
+
+
+def fused_reference(assembly, kwargs, pressures, n_steps, dt=2.0e-5):
+    from oracle import br2_port
+    from oracle.fused import FusedOracle
+
+    ref = br2_port.OracleEnvironment(time_step=dt)
+    ref.reset(ROD_DB, ASSEMBLY[assembly], **kwargs)
+    fused = FusedOracle.from_simulator(ref.simulator, NAMES)
+    W = fused.pack(pressures.shape[1])
+    fused.run(W, pressures, n_steps, 0.0, dt)
+    return fused, W
+
+
+BATCH_CASES = [
+    # BASELINE.json configs 2 / 3 (and the sample triple assembly at n=41), sampled: 64 random instances
+    ("single", {"gravity": True}, 0, 10000),
+    ("double", {}, 1, 10000),
+    ("triple", {"gravity": True}, 2, 4000),
+]
+
+
+@pytest.mark.parametrize("assembly,kwargs,seed,n_steps", BATCH_CASES, ids=[c[0] for c in BATCH_CASES])
+def test_batched_random_pressures_match_oracle(assembly, kwargs, seed, n_steps):
+    batch, dt = 64, 2.0e-5
+    rng = np.random.default_rng(seed)
+    pressures = rng.uniform(0.0, 40.0, size=(3, batch)) * PSI
+    env = make_env(assembly, batch, **kwargs)
+    env.simulator._callback_ops = []
+    action = {name: pressures[i] for i, name in enumerate(NAMES)}
+    status = env.run(action, duration=n_steps * dt - 0.5 * dt, disable_progress_bar=True, check_nan=True)
+    assert round(env.time / dt) == n_steps
+    assert not any(status.nan_per_instance[k].any() for k in status.nan_per_instance)
+    fused, W = fused_reference(assembly, kwargs, pressures, n_steps, dt)
+    x_scale = max(np.abs(fused.view(W, r, "x")).max() for r in range(len(env.simulator)))
+    worst = {"x": 0.0, "Q": 0.0, "v": 0.0, "w": 0.0}
+    for r, rod in enumerate(env.simulator):
+        for attr, short in SHORT.items():
+            if short == "a":
+                continue
+            err = np.abs(getattr(rod, attr) - fused.view(W, r, short)).max()
+            worst[short] = max(worst[short], err / x_scale if short == "x" else err)
+    print(assembly, "worst errors", worst)
+    assert worst["x"] <= POS_TOL and worst["Q"] <= DIR_TOL
+    assert worst["v"] <= VEL_TOL and worst["w"] <= OMEGA_TOL
+    # instances really are independent: instance 5 alone reproduces its batch result bit for bit
+    solo = make_env(assembly, 1, **kwargs)
+    solo.simulator._callback_ops = []
+    solo.run({name: pressures[i, 5] for i, name in enumerate(NAMES)}, duration=n_steps * dt - 0.5 * dt,
+             disable_progress_bar=True)
+    for r, rod in enumerate(env.simulator):
+        np.testing.assert_array_equal(solo.simulator[r].position_collection, rod.position_collection[5])
+        np.testing.assert_array_equal(solo.simulator[r].director_collection, rod.director_collection[5])
+    # directors stay orthonormal
+    for rod in env.simulator:
+        Q = rod.director_collection
+        gram = np.einsum("bijk,bljk->bilk", Q, Q)
+        assert np.abs(gram - np.eye(3)[None, :, :, None]).max() < 1e-10
+    env.close()
+    solo.close()
+
+
+def test_chunked_launches_equal_one_launch():
+    """State round-trips through HBM between launches must not change a single bit."""
+    dt = 2.0e-5
+    action = {"action1": 30 * PSI, "action2": 12 * PSI, "action3": 3 * PSI}
+    a = make_env("single", 2, gravity=True)
+    a.simulator._callback_ops = []
+    a.run(action, duration=600 * dt - 0.5 * dt, disable_progress_bar=True)
+    b = make_env("single", 2, gravity=True)
+    b.simulator._callback_ops = []
+    for _ in range(6):
+        b.run(action, duration=100 * dt - 0.5 * dt, disable_progress_bar=True)
+    assert a.time == b.time
+    for ra, rb in zip(a.simulator, b.simulator):
+        for attr in SHORT:
+            np.testing.assert_array_equal(getattr(ra, attr), getattr(rb, attr), err_msg=attr)
+    a.close()
+    b.close()
+
+
+def test_optional_ops_point_force_and_last_end_fixed():
+    """PointForces / LastEndFixedRod on a lone rod, through the hooks, vs the faithful oracle."""
+    from br2.custom_activation import PointForces
+    from br2.custom_constraint import LastEndFixedRod
+    from br2.free_simulator import BR2Simulator
+    from br2.hooks import AnalyticalLinearDamper, CosseratRod, PositionVerlet, extend_stepper_interface
+    from oracle import br2_port, mini_elastica
+
+    spec = dict(n_elements=20, start=np.zeros(3), direction=np.array([0.0, 1.0, 0.0]), normal=np.array([0.0, 0.0, 1.0]),
+                base_length=0.2, base_radius=0.005, density=1200.0, youngs_modulus=2e6, shear_modulus=1.2e6)
+    dt, n_steps, force = 1.0e-5, 3000, np.array([0.02, 0.0, -0.01])
+
+    def build(sim_cls, rod_cls, damper, point, pin, stepper_mod):
+        sim = sim_cls()
+        rod = rod_cls.straight_rod(**spec)
+        sim.append(rod)
+        sim.dampen(rod).using(damper, damping_constant=2.0, time_step=dt)
+        sim.add_forcing_to(rod).using(point, force, 0.4, ramp_up_time=5e-3)
+        sim.constrain(rod).using(pin, constrained_position_idx=(-1,), constrained_director_idx=(-1,))
+        sim.finalize()
+        return sim, rod
+
+    sim, rod = build(BR2Simulator, CosseratRod, AnalyticalLinearDamper, PointForces, LastEndFixedRod, None)
+    do_step, stages = extend_stepper_interface(PositionVerlet(), sim)
+    t = do_step(PositionVerlet(), stages, sim, 0.0, dt, n_steps=n_steps)
+    osim, orod = build(br2_port.BR2Simulator, mini_elastica.CosseratRod, mini_elastica.AnalyticalLinearDamper,
+                       br2_port.PointForces, br2_port.LastEndFixedRod, None)
+    ot = mini_elastica.timestepper.integrate(mini_elastica.PositionVerlet(), osim, n_steps * dt, n_steps)
+    assert abs(t - ot) < 1e-15
+    assert np.abs(orod.position_collection[:, 8] - spec["start"][:, None][:, 0]).max() > 1e-6  # it moved
+    scale = np.abs(orod.position_collection).max()
+    assert np.abs(rod.position_collection - orod.position_collection).max() <= POS_TOL * scale
+    assert np.abs(rod.director_collection - orod.director_collection).max() <= DIR_TOL
+    np.testing.assert_array_equal(rod.position_collection[:, -1], orod.position_collection[:, -1])
+    np.testing.assert_array_equal(rod.velocity_collection[:, -1], 0.0)
+
+
+def test_step_host_entry_point_matches_device_path():
+    """br2_step_host (host buffers in, host buffers out) == bind + step on device buffers."""
+    import ctypes
+
+    from br2 import _native
+
+    env = make_env("single", 3, gravity=True)
+    env.simulator._callback_ops = []
+    pressures = np.random.default_rng(3).uniform(0, 40, size=(3, 3)) * PSI
+    host_state = env.engine.state.cpu().numpy().copy()
+    env.run({n: pressures[i] for i, n in enumerate(NAMES)}, duration=50 * 2e-5 - 1e-5, disable_progress_bar=True)
+    t_end = ctypes.c_double()
+    _native.check(env.engine.lib.br2_step_host(env.engine.handle, host_state.ctypes.data,
+                                               np.ascontiguousarray(pressures).ctypes.data, 3, 50, 0.0, 2e-5,
+                                               ctypes.byref(t_end)))
+    assert t_end.value == env.time
+    np.testing.assert_array_equal(host_state, env.engine.state.cpu().numpy())
+    env.close()
