@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Benchmark of the rod-integration hot path (BASELINE.json metric: rod-element-steps/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+One bench "step" = ONE launch of the fused kernel advancing the whole batch `--substeps`
+PositionVerlet steps (default 2000 = the reference's capture cadence `step_skip` at dt=2e-5, 25 fps).
+Workload at every N: BASELINE.json configs[1], single_br2 assembly (3 rods x 41 elements), 4096 instances
+PER GPU with per-instance random actuation pressures, gravity on, dt=2e-5 (weak scaling: the batch is
+partitioned, instances never interact, no collective on the step path).
+
+`value`   : element-steps/s with the state resident in HBM, CUDA-event timed per launch, L2 flushed
+            between launches, max over ranks.
+`e2e`     : same metric through the public API (`Environment.run` with HOST action arrays + a read-back
+            of the full batch state into pinned host memory), wall clock between device synchronisations.
+`roofline`: fp64 pipe -- 695 algorithmic flop per element-step against a DFMA
+            micro-benchmark measured in this process (MEASURED_PEAKS.json has no fp64 entry); the
+            `hbm` sub-object gives achieved algorithmic HBM GB/s against MEASURED_PEAKS.json.
+`cpu_baseline`: the faithful oracle port (one numba dispatch per operator, like the reference) on one
+            host core, on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "br2-simulator_b200"))
+os.environ.setdefault("NUMBA_CACHE_DIR", os.path.join(ROOT, ".numba_cache"))
+
+DATA = os.path.join(ROOT, "tests", "data")
+ROD_DB = os.path.join(DATA, "rod_library.json")
+PSI = 6895.0
+FLOP_PER_ELEMENT_STEP = 695.0  # SURVEY.md Appendix B (single-BR2-type assembly, gravity on)
+WORKLOADS = {
+    "single": dict(assembly="assembly_single.json", elements=123, gravity=True, seed=0,
+                   label="single_br2_v1 x4096/GPU, random pressures U[0,40] psi, gravity on, dt=2e-5 (BASELINE configs[1])"),
+    "double": dict(assembly="assembly_double.json", elements=246, gravity=False, seed=1,
+                   label="double_br2_v1 with serial joints, random pressures, gravity off, dt=2e-5 (BASELINE configs[2])"),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="single", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=4096, help="instances per GPU")
+    ap.add_argument("--substeps", type=int, default=2000, help="integration steps per launch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path)), "MEASURED_PEAKS.json"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        clocks, reasons, sm_max = [], set(), None
+        try:
+            for line in open(self.path):
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    clocks.append(float(parts[1]))
+                    sm_max = float(parts[2])
+                except ValueError:
+                    continue
+                for name, flag in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                    if flag.lower().startswith("active"):
+                        reasons.add(name)
+            os.remove(self.path)
+        except Exception:
+            pass
+        if clocks:
+            clocks.sort()
+            out.update(sm_mhz=clocks[len(clocks) // 2], sm_max_mhz=sm_max, reasons=sorted(reasons), samples=len(clocks))
+        return out
+
+
+def dist_setup(args):
+    import torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        backend = "nccl" if (args.impl == "ours" and torch.cuda.is_available()) else "gloo"
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return world, rank, local
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU legs (the only place bench.py touches oracle/)
+# ----------------------------------------------------------------------------------------------
+def _faithful_worker(payload):
+    assembly, gravity, pressures, n_steps = payload
+    from oracle import br2_port
+
+    env = br2_port.OracleEnvironment()
+    env.reset(ROD_DB, os.path.join(DATA, assembly), gravity=gravity)
+    action = {"action%d" % (i + 1): float(p) for i, p in enumerate(pressures)}
+    env.simulator._callback_list[:] = []
+    env.run(action, n_steps=20)  # JIT / cache warm-up, untimed
+    t0 = time.perf_counter()
+    env.run(action, n_steps=n_steps)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline_port(workload, n_steps=8000):
+    """Faithful oracle port, ONE core, one instance: the reference's execution pattern
+    (one Python->numba dispatch per operator / per joint element per step)."""
+    w = WORKLOADS[workload]
+    seconds = _faithful_worker((w["assembly"], w["gravity"], [30 * PSI, 30 * PSI, 0.0], n_steps))
+    return {"value": w["elements"] * n_steps / seconds, "unit": "rod-element-steps/s", "cores": 1, "kind": "port",
+            "sample": "1 instance x %d steps of the same assembly (faithful per-operator numba oracle; "
+                      "the reference's PyElastica cannot be installed here)" % n_steps}
+
+
+def run_reference_arm(args, world, rank):
+    """`--impl reference`: the reference's CPU path (oracle port; PyElastica itself is not
+    installable) on all host cores -- one independent instance per process, like a user of the
+    reference running a sweep would."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    w = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    sample_steps = 400
+    import numpy as np
+
+    rng = np.random.default_rng(w["seed"])
+    payloads = [(w["assembly"], w["gravity"], list(rng.uniform(0, 40, size=3) * PSI), sample_steps) for _ in range(cores)]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        for _ in range(max(args.warmup, 1)):
+            pool.map(_faithful_worker, payloads)
+        elapsed = 0.0  # stepping time only (slowest process per bench step); set-up / JIT is not charged
+        for _ in range(args.steps):
+            elapsed += max(pool.map(_faithful_worker, payloads))
+    value = cores * w["elements"] * sample_steps * args.steps / elapsed
+    line = {
+        "impl": "reference", "metric": "rod-element-steps/sec", "value": value, "unit": "rod-element-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["label"], "batch_per_gpu": args.batch, "substeps_per_step": args.substeps},
+        "cpu_baseline": {"value": value, "unit": "rod-element-steps/s", "cores": cores, "kind": "port",
+                         "sample": "%d processes x 1 instance x %d steps per bench step (+20 untimed warm-up steps each); "
+                                   "faithful per-operator numba oracle -- PyElastica 0.3.1 is not installable here" % (cores, sample_steps)},
+        "e2e": {"value": value, "unit": "rod-element-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args, world, rank, local):
+    import numpy as np
+    import torch
+
+    from br2 import _native
+    from br2.environment import Environment
+
+    w = WORKLOADS[args.workload]
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    B, M, dt = args.batch, args.substeps, 2.0e-5
+    rng = np.random.default_rng(w["seed"] + 1000 * rank)
+    pressures = rng.uniform(0.0, 40.0, size=(3, B)) * PSI
+
+    env = Environment("bench", batch=B, device=device, create_dirs=False)
+    env.reset(ROD_DB, os.path.join(DATA, w["assembly"]), gravity=w["gravity"])
+    env.simulator._callback_ops = []  # stepping only; capture is a separate (next-row) path
+    engine = env.engine
+    names = ["action1", "action2", "action3"]
+    action_host = {n: torch.from_numpy(pressures[i].copy()).pin_memory().numpy() for i, n in enumerate(names)}
+    env.assy.set_actuation(action_host)
+    env._push_actuation()
+
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=device)  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(device)
+
+    # ---- device-resident throughput ------------------------------------------------------
+    t_sim = 0.0
+    for _ in range(args.warmup):
+        t_sim = engine.step(M, t_sim, dt)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    launches0 = engine.launches
+    for i in range(args.steps):
+        flush.fill_(float(i))  # L2 flush between timed launches (outside the event pair)
+        starts[i].record()
+        t_sim = engine.step(M, t_sim, dt)
+        stops[i].record()
+    barrier()
+    clocks = sampler.stop()
+    launches = engine.launches - launches0
+    per_launch_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+    total_ms = torch.tensor([sum(per_launch_ms)], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(total_ms, op=torch.distributed.ReduceOp.MAX)
+    total_s = float(total_ms.item()) * 1e-3
+    element_steps = world * B * w["elements"] * M * args.steps
+    value = element_steps / total_s
+    state_ok = bool(torch.isfinite(engine.state).all().item())
+
+    # ---- end to end through the public API ---------------------------------------------------
+    pinned_state = torch.empty((B, engine.words), dtype=torch.float64).pin_memory()
+    e2e_steps = max(2, min(args.steps, 5))
+    duration = M * dt - 0.5 * dt
+
+    def e2e_once():
+        env.run(action_host, duration=duration, disable_progress_bar=True)  # H2D of the pressures inside
+        pinned_state.copy_(engine.state, non_blocking=True)                 # D2H of the batch state
+        torch.cuda.synchronize(device)
+
+    e2e_once()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_once()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(e2e_s, op=torch.distributed.ReduceOp.MAX)
+    e2e_value = world * B * w["elements"] * M * e2e_steps / float(e2e_s.item())
+
+    if rank != 0:
+        return
+    # ---- roofline denominators ---------------------------------------------------------------
+    pk, pk_src = peaks()
+    import ctypes
+
+    tf = ctypes.c_double(0.0)
+    _native.check(engine.lib.br2_fp64_peak_tflops(local, 3, ctypes.byref(tf)))
+    kernel_s = sum(per_launch_ms) * 1e-3 / args.steps          # this rank's average launch duration
+    el_steps_per_launch = B * w["elements"] * M
+    achieved_tf = FLOP_PER_ELEMENT_STEP * el_steps_per_launch / kernel_s / 1e12
+    io_words = sum(sum(sz for short, (off, sz) in fields.items() if short in ("x", "v", "Q", "w")) for fields in engine.program.layout)
+    hbm_bytes = B * 8.0 * (io_words + engine.words)            # state read + state/derived write per launch
+    info = engine.kernel_info()
+    line = {
+        "metric": "rod-element-steps/sec", "value": value, "unit": "rod-element-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["label"], "batch_per_gpu": B, "substeps_per_step": M, "dt": dt,
+                   "elements_per_instance": w["elements"], "l2": "flushed between timed launches (256 MB fill)",
+                   "parallelism": "batch partition x%d, no step-path collective" % world},
+        "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": tf.value, "unit": "TFLOP/s",
+                     "frac": achieved_tf / tf.value if tf.value else None, "traffic": None,
+                     "flop_per_element_step": FLOP_PER_ELEMENT_STEP,
+                     "peak_source": "DFMA micro-benchmark run in this process (br2_fp64_peak_tflops)",
+                     "hbm": {"achieved_gbs": hbm_bytes / kernel_s / 1e9, "peak_gbs": pk["hbm_gbs"], "peak_source": pk_src,
+                             "frac": hbm_bytes / kernel_s / 1e9 / pk["hbm_gbs"], "bytes_per_launch": hbm_bytes}},
+        "e2e": {"value": e2e_value, "unit": "rod-element-steps/s", "h2d_bytes_per_step": int(3 * B * 8),
+                "d2h_bytes_per_step": int(B * engine.words * 8), "steps": e2e_steps},
+        "gpu_launches": launches,
+        "kernel": dict(info, name="br2_step_kernel", launch_ms=per_launch_ms),
+        "clocks": clocks,
+        "state_finite": state_ok,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_port(args.workload)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    world, rank, local = dist_setup(args)
+    if args.impl == "reference":
+        run_reference_arm(args, world, rank)
+    else:
+        run_ours(args, world, rank, local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -113,16 +113,18 @@ class FreeTwistActuation(NoForces):
 # --------------------------------------------------------------------------------------
 @njit(cache=True)
 def _soft_pin_force(base_position, fixed_position, base_velocity, external_forces, k, nu):
-    """free_custom_systems.py:151-185."""
+    """free_custom_systems.py:151-185.  The reference's two ``np.dot`` calls are written out as
+    ordered sums (numba's ``np.dot`` needs SciPy's BLAS, which the GPU box lacks); the golden
+    vectors confirm the results are unchanged."""
     d = fixed_position - base_position
-    dist = np.sqrt(np.dot(d, d))
-    if dist <= 1e-8:
-        unit = np.array([0.0, 0.0, 0.0])
-    else:
-        unit = d / dist
+    dist = np.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2])
+    unit = np.zeros(3)
+    if not dist <= 1e-8:
+        unit[:] = d / dist
     elastic = k * d
     rel_v = -base_velocity
-    damping = -nu * (np.dot(rel_v, unit) * unit)
+    proj = rel_v[0] * unit[0] + rel_v[1] * unit[1] + rel_v[2] * unit[2]
+    damping = -nu * (proj * unit)
     external_forces[..., 0] += elastic + damping
 
 
@@ -160,24 +162,28 @@ class FreeBaseEndSoftFixed(ConstraintBase):
 # serial joint: /root/reference/br2/legacy_surface_connection_parallel_rod_numba.py:346-478
 # --------------------------------------------------------------------------------------
 @njit(cache=True)
-def _tip_to_base_force(
-    k, nu, l1, l2, x1, x2, r1, r2, v1, v2, Q1, Q2, f1, f2
-):
+def _tip_to_base_force(k, nu, l1, l2, x1, x2, r1, r2, v1, v2, Q1, Q2, f1, f2):
     """legacy...:386-464.  Spring between the surface points of rod-1's last and rod-2's first
-    element, un-projected relative-velocity damping, halves to the two end nodes."""
-    c1 = 0.5 * (x1[..., -1] + x1[..., -2])
-    c2 = 0.5 * (x2[..., 0] + x2[..., 1])
-    arm1 = Q1[..., -1].T @ (l1 * r1[..., -1])
-    arm2 = Q2[..., 0].T @ (l2 * r2[..., 0])
-    gap = (c2 + arm2) - (c1 + arm1)
-    spring = k * gap
-    u1 = 0.5 * (v1[..., -1] + v1[..., -2])
-    u2 = 0.5 * (v2[..., 0] + v2[..., 1])
-    total = spring + (-nu * (u2 - u1))
-    f1[..., -1] += 0.5 * total
-    f1[..., -2] += 0.5 * total
-    f2[..., 0] -= 0.5 * total
-    f2[..., 1] -= 0.5 * total
+    element, un-projected relative-velocity damping, halves to the two end nodes.  The reference's
+    ``Q[..., idx].T @ (l * r)`` is written out as an ordered j = 0,1,2 sum (no BLAS dependency)."""
+    n1, n2 = Q1.shape[2], Q2.shape[2]
+    arm1 = np.zeros(3)
+    arm2 = np.zeros(3)
+    total = np.zeros(3)
+    for i in range(3):
+        for j in range(3):
+            arm1[i] += Q1[j, i, n1 - 1] * (l1[j] * r1[0, n1 - 1])
+            arm2[i] += Q2[j, i, 0] * (l2[j] * r2[0, 0])
+        c1 = 0.5 * (x1[i, n1] + x1[i, n1 - 1])
+        c2 = 0.5 * (x2[i, 0] + x2[i, 1])
+        gap = (c2 + arm2[i]) - (c1 + arm1[i])
+        u1 = 0.5 * (v1[i, n1] + v1[i, n1 - 1])
+        u2 = 0.5 * (v2[i, 0] + v2[i, 1])
+        total[i] = k * gap + (-nu * (u2 - u1))
+        f1[i, n1] += 0.5 * total[i]
+        f1[i, n1 - 1] += 0.5 * total[i]
+        f2[i, 0] -= 0.5 * total[i]
+        f2[i, 1] -= 0.5 * total[i]
     return arm1, arm2, total
 
 

@@ -59,9 +59,12 @@ def test_golden_trajectories(case):
         for key, tol in (("position", POS_TOL * x_scale), ("director", DIR_TOL), ("com", POS_TOL * x_scale),
                          ("lengths", 1e-12), ("radius", 1e-12), ("dilatation", 1e-9)):
             assert np.abs(np.array(sink[key]) - g["rod%d_cb_%s" % (idx, key)]).max() <= tol, key
-        for key in ("internal_forces", "external_forces", "internal_torques", "external_torques", "acceleration"):
+        # loads and accelerations carry the joint's round-to-12-decimals noise (5.8e-9 N per flipped digit,
+        # over node masses of ~1e-3 kg): stated bounds, relative to the field's magnitude
+        for key, rtol in (("internal_forces", 1e-6), ("external_forces", 1e-6), ("internal_torques", 1e-6),
+                          ("external_torques", 1e-6), ("acceleration", 1e-4)):
             want = g["rod%d_cb_%s" % (idx, key)]
-            assert np.abs(np.array(sink[key]) - want).max() <= 1e-6 * max(np.abs(want).max(), 1.0), key
+            assert np.abs(np.array(sink[key]) - want).max() <= rtol * max(np.abs(want).max(), 1.0), key
     env.close()
 
 
