@@ -103,10 +103,16 @@ class Engine:
         return t_end.value
 
     def kernel_info(self):
-        vals = [ctypes.c_int32(0) for _ in range(5)]
+        vals = [ctypes.c_int32(0) for _ in range(6)]
         _native.check(self.lib.br2_kernel_info(self.handle, *[ctypes.byref(v) for v in vals]))
-        keys = ("registers", "smem_bytes", "threads", "blocks_per_sm", "sm_count")
-        return dict(zip(keys, (v.value for v in vals)))
+        keys = ("registers", "smem_bytes", "threads", "blocks_per_sm", "sm_count", "variant")
+        info = dict(zip(keys, (v.value for v in vals)))
+        info["variant_name"] = ("generic", "fast", "fast-uniform")[info["variant"]]
+        return info
+
+    def select_kernel(self, variant):
+        """0 generic, 1 fast (per-slot constants), 2 fast (uniform constants), -1 automatic."""
+        _native.check(self.lib.br2_select_kernel(self.handle, int(variant)))
 
     def close(self):
         if getattr(self, "handle", None) is not None and self.handle.value:

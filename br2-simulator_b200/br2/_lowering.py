@@ -19,7 +19,7 @@ import numpy as np
 from .hooks import ops as _ops
 from .hooks.rod import STATE_ORDER, field_sizes, rod_words
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 ROD_NI, ROD_ND = 8, 2
 SC_COUNT = 25
 SC_MASS, SC_REST_LEN, SC_VOLUME, SC_SHEAR, SC_J, SC_JINV, SC_LN_CR, SC_REST_SIGMA = 0, 1, 2, 3, 6, 9, 12, 15
@@ -29,6 +29,18 @@ C_NI, C_ND = 2, 14
 J_NI, J_ND = 8, 10
 ROD_HAS_DAMPER = 1
 MAX_SLOTS = 1024
+# fast-path tables (include/br2cuda.h)
+FAST_NI, FAST_NODE_ITEMS = 16, 8
+FAST_FLAGS, FAST_OWN_JOINT, FAST_EXTRA_JOINT, FAST_SOFTFIX_ROW, FAST_ACT_BEGIN, FAST_ACT_END = 0, 1, 2, 3, 4, 5
+FAST_ELEM_ITEM0, FAST_NODE_ITEM0 = 6, 8
+PIN_DIRECTOR, PIN_POSITION, ZERO_NODE_RATE, ZERO_ELEM_RATE, ZERO_REPORTED = 1, 2, 4, 8, 16
+FC_REST_LEN, FC_INV_REST_LEN, FC_VOL_OVER_PI, FC_SHEAR, FC_J, FC_JINV, FC_LN_CR, FC_CR = 0, 1, 2, 3, 6, 9, 12, 15
+FC_REST_VLEN, FC_INV_REST_VLEN, FC_BEND, FC_CT, FC_GRAVITY, FC_JK, FC_JNU, FC_JKREP, FC_PIN, FC_COUNT = (
+    18, 19, 20, 23, 24, 27, 28, 29, 30, 42)
+FORCE_GRAVITY, FORCE_TWIST, FORCE_BEND, FORCE_POINT = 0, 1, 2, 3
+CONS_SOFT_FIXED_BASE, CONS_LAST_END_FIXED = 0, 1
+JOINT_SURFACE, JOINT_TIP_TO_BASE = 0, 1
+UNIFORM_RTOL = 1e-13
 
 
 def _diagonal_only(matrix, what):
@@ -238,12 +250,164 @@ def lower_collection(collection):
         overwrite_src[ctx.slot(rod_index, elem)] = ctx.slot(*src)
 
     prog.action_lists = ctx.action_lists
+    fast = _lower_fast(ctx, rods, rod_i, slot_c, rod_d, forcing_rows, cons_rows, node_lists, elem_lists, overwrite_src)
     prog.tables = dict(
         slot_rod=slot_rod, rod_i=rod_i, rod_d=rod_d, slot_c=slot_c, forcing_i=forcing_i, forcing_d=forcing_d,
         cons_i=cons_i, cons_d=cons_d, joint_i=joint_i, joint_d=joint_d, node_ptr=node_ptr,
         node_items=node_items, elem_ptr=elem_ptr, elem_items=elem_items, overwrite_src=overwrite_src,
+        fast_i=fast["fast_i"], fast_c=fast["fast_c"], act_i=fast["act_i"], act_d=fast["act_d"],
     )
+    prog.fast = dict(ok=fast["ok"], uniform=fast["uniform"], why=fast["why"], ramp_up_time=fast["ramp_up_time"],
+                     n_act=len(fast["act_i"]))
     prog.tables = {k: np.ascontiguousarray(v) for k, v in prog.tables.items()}
     prog.counts = dict(n_slots=S, n_rods=len(rods), n_forcing=len(forcing_rows), n_constraints=len(cons_rows),
                        n_joints=NJ, n_actions=len(ctx.action_lists))
     return prog
+
+
+def _lower_fast(ctx, rods, rod_i, slot_c, rod_d, forcing_rows, cons_rows, node_lists, elem_lists, overwrite_src):
+    """Per-slot descriptors of the fast kernel (csrc/br2_fast.cuh), or ``ok = False`` with the reason
+    when the assembly needs the generic kernel."""
+    S = ctx.n_slots
+    fast_i = np.full((S, FAST_NI), -1, dtype=np.int32)
+    fast_i[:, FAST_FLAGS] = 0
+    fast_i[:, FAST_ACT_BEGIN] = 0
+    fast_i[:, FAST_ACT_END] = 0
+    fast_c = np.zeros((FC_COUNT, S))
+    act_i, act_d = [], []
+    out = dict(ok=False, uniform=False, why="", ramp_up_time=1.0, fast_i=fast_i, fast_c=fast_c,
+               act_i=np.zeros(0, dtype=np.int32), act_d=np.zeros((0, 3)))
+
+    def refuse(reason):
+        out["why"] = reason
+        return out
+
+    if slot_c[SC_REST_SIGMA:SC_REST_SIGMA + 3].any() or slot_c[SC_REST_KAPPA:SC_REST_KAPPA + 3].any():
+        return refuse("non-zero rest strains")
+    ramps = {float(row[1]) for kind, _, _, row in forcing_rows if kind in (FORCE_TWIST, FORCE_BEND)}
+    if any(kind == FORCE_POINT for kind, _, _, _ in forcing_rows):
+        return refuse("point forces")
+    if len(ramps) > 1:
+        return refuse("actuation rows with different ramp_up_time")
+    out["ramp_up_time"] = ramps.pop() if ramps else 1.0
+
+    # ---- per-slot constants (element values; undefined slots copy a defined neighbour so that a
+    #      uniform assembly stays uniform) ------------------------------------------------------
+    for r, rod in enumerate(rods):
+        n, s0 = rod.n_elems, int(rod_i[r, 1])
+        cols = slice(s0, s0 + n + 1)
+
+        def spread(values, count):  # [.., count] element/voronoi values -> all n + 1 slots of the rod
+            values = np.asarray(values, dtype=np.float64)
+            if count == 0:
+                return np.ones(values.shape[:-1] + (n + 1,))
+            pad = np.repeat(values[..., -1:], n + 1 - count, axis=-1)
+            return np.concatenate([values[..., :count], pad], axis=-1)
+
+        fast_c[FC_REST_LEN, cols] = spread(rod.rest_lengths, n)
+        fast_c[FC_INV_REST_LEN, cols] = 1.0 / fast_c[FC_REST_LEN, cols]
+        fast_c[FC_VOL_OVER_PI, cols] = spread(rod.volume, n) / np.pi
+        fast_c[FC_SHEAR:FC_SHEAR + 3, cols] = spread(slot_c[SC_SHEAR:SC_SHEAR + 3, s0:s0 + n], n)
+        fast_c[FC_J:FC_J + 3, cols] = spread(slot_c[SC_J:SC_J + 3, s0:s0 + n], n)
+        fast_c[FC_JINV:FC_JINV + 3, cols] = spread(slot_c[SC_JINV:SC_JINV + 3, s0:s0 + n], n)
+        ln_cr = spread(slot_c[SC_LN_CR:SC_LN_CR + 3, s0:s0 + n], n)
+        fast_c[FC_LN_CR:FC_LN_CR + 3, cols] = ln_cr
+        fast_c[FC_CR:FC_CR + 3, cols] = np.exp(ln_cr)
+        fast_c[FC_REST_VLEN, cols] = spread(rod.rest_voronoi_lengths, n - 1)
+        fast_c[FC_INV_REST_VLEN, cols] = 1.0 / fast_c[FC_REST_VLEN, cols]
+        fast_c[FC_BEND:FC_BEND + 3, cols] = spread(slot_c[SC_BEND:SC_BEND + 3, s0:s0 + n - 1], n - 1) if n > 1 else 0.0
+        fast_c[FC_CT, cols] = rod_d[r, 0]
+
+    # ---- forcing ----------------------------------------------------------------------------
+    row_cursor = 0
+    for r, rod in enumerate(rods):
+        n, s0 = rod.n_elems, int(rod_i[r, 1])
+        gravity = np.zeros(3)
+        twist_rows, bend_rows = [], []
+        for kind, action, node, row in ctx.forcing[r]:
+            if kind == FORCE_GRAVITY:
+                gravity += row[:3]
+            elif kind == FORCE_TWIST:   # (P * scale * ramp) / n about d3, every element
+                twist_rows.append((action, np.array([0.0, 0.0, row[0] / n])))
+            elif kind == FORCE_BEND:    # P * scale * ramp * [cos, sin, 0], last element only
+                bend_rows.append((action, np.array([row[0] * row[2], row[0] * row[3], 0.0])))
+        fast_c[FC_GRAVITY:FC_GRAVITY + 3, s0:s0 + n + 1] = gravity[:, None]
+        if twist_rows:
+            begin = len(act_i)
+            for action, coeff in twist_rows:
+                act_i.append(action)
+                act_d.append(coeff)
+            fast_i[s0:s0 + n - 1, FAST_ACT_BEGIN] = begin
+            fast_i[s0:s0 + n - 1, FAST_ACT_END] = len(act_i)
+        # the last element sees the twist rows followed by the bend rows (registration order is
+        # alpha, beta, gamma fibres -- free_simulator.py:371-374 -- but sums commute up to rounding)
+        begin = len(act_i)
+        for action, coeff in twist_rows + bend_rows:
+            act_i.append(action)
+            act_d.append(coeff)
+        fast_i[s0 + n - 1, FAST_ACT_BEGIN] = begin
+        fast_i[s0 + n - 1, FAST_ACT_END] = len(act_i)
+
+    # ---- constraints --------------------------------------------------------------------------
+    cons_cursor = 0
+    for r, rod in enumerate(rods):
+        n, s0 = rod.n_elems, int(rod_i[r, 1])
+        c_begin = int(rod_i[r, 6])
+        kinds = [kind for kind, _ in ctx.constraints[r]]
+        if len(kinds) != len(set(kinds)):
+            return refuse("two constraints of the same kind on one rod")
+        for offset, (kind, row) in enumerate(ctx.constraints[r]):
+            if kind == CONS_SOFT_FIXED_BASE:
+                fast_i[s0, FAST_FLAGS] |= PIN_DIRECTOR | ZERO_NODE_RATE | ZERO_ELEM_RATE | ZERO_REPORTED
+                fast_i[s0, FAST_SOFTFIX_ROW] = c_begin + offset
+                fast_c[FC_PIN + 3:FC_PIN + 12, s0] = row[3:12]
+            else:
+                fast_i[s0 + n, FAST_FLAGS] |= PIN_POSITION | ZERO_NODE_RATE
+                fast_c[FC_PIN:FC_PIN + 3, s0 + n] = row[0:3]
+                if fast_i[s0 + n - 1, FAST_FLAGS] & PIN_DIRECTOR:
+                    return refuse("two director pins on one element")
+                fast_i[s0 + n - 1, FAST_FLAGS] |= PIN_DIRECTOR | ZERO_ELEM_RATE
+                fast_c[FC_PIN + 3:FC_PIN + 12, s0 + n - 1] = row[3:12]
+
+    # ---- joints -------------------------------------------------------------------------------
+    NJ = len(ctx.joints)
+    extra = []
+    jparams = None
+    for j, (kind, s1, s2, q1, q2, row, torque) in enumerate(ctx.joints):
+        ownable = (kind == JOINT_SURFACE and q1 == s1 and q2 == s2 and fast_i[s2, FAST_OWN_JOINT] < 0 and s1 != s2)
+        if ownable:
+            fast_i[s2, FAST_OWN_JOINT] = j
+            fast_c[FC_JK, s2], fast_c[FC_JNU, s2], fast_c[FC_JKREP, s2] = row[0], row[1], row[2]
+            jparams = (row[0], row[1], row[2]) if jparams is None else jparams
+        else:
+            extra.append(j)
+    if jparams is not None:  # slots without an own joint copy the common parameters (keeps uniformity)
+        none = fast_i[:, FAST_OWN_JOINT] < 0
+        fast_c[FC_JK, none], fast_c[FC_JNU, none], fast_c[FC_JKREP, none] = jparams
+    # spread the remaining joints over threads that have no second joint yet, one warp after another
+    warps = (S + 31) // 32
+    candidates = [w * 32 + lane for lane in range(32) for w in range(warps) if w * 32 + lane < S]
+    if len(extra) > len(candidates):
+        return refuse("more joints than threads")
+    for j, slot in zip(extra, candidates):
+        fast_i[slot, FAST_EXTRA_JOINT] = j
+    for slot in range(S):
+        if len(node_lists[slot]) > FAST_NODE_ITEMS:
+            return refuse("a node receives more than %d joint forces" % FAST_NODE_ITEMS)
+        if len(elem_lists[slot]) > 2:
+            return refuse("an element receives more than 2 joint torques")
+        if any(item >= 0xFFFF for item in node_lists[slot]):
+            return refuse("too many joints for 16-bit gather items")
+        fast_i[slot, FAST_NODE_ITEM0:FAST_NODE_ITEM0 + len(node_lists[slot])] = node_lists[slot]
+        fast_i[slot, FAST_ELEM_ITEM0:FAST_ELEM_ITEM0 + len(elem_lists[slot])] = elem_lists[slot]
+    if NJ > S + 64:
+        return refuse("joint rows exceed the fast kernel's buffer")
+
+    # ---- uniformity: every slot's element constants equal slot 0's (kernel then uses the constant bank)
+    ref = fast_c[:FC_PIN, :1]
+    scale = np.maximum(np.abs(ref), 1e-300)
+    out["uniform"] = bool((np.abs(fast_c[:FC_PIN] - ref) <= UNIFORM_RTOL * scale).all())
+    out["ok"] = True
+    out["act_i"] = np.array(act_i, dtype=np.int32).reshape(-1)
+    out["act_d"] = np.array(act_d, dtype=np.float64).reshape(-1, 3)
+    return out

@@ -11,7 +11,7 @@ import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(PKG_DIR, "lib", "libbr2cuda.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _i32p = ctypes.POINTER(ctypes.c_int32)
 _f64p = ctypes.POINTER(ctypes.c_double)
@@ -30,6 +30,9 @@ class Br2Program(ctypes.Structure):
         ("cons_i", ctypes.c_void_p), ("cons_d", ctypes.c_void_p), ("joint_i", ctypes.c_void_p),
         ("joint_d", ctypes.c_void_p), ("node_ptr", ctypes.c_void_p), ("node_items", ctypes.c_void_p),
         ("elem_ptr", ctypes.c_void_p), ("elem_items", ctypes.c_void_p), ("overwrite_src", ctypes.c_void_p),
+        ("fast_ok", ctypes.c_int32), ("fast_uniform", ctypes.c_int32), ("n_act", ctypes.c_int32),
+        ("reserved", ctypes.c_int32), ("act_ramp_up_time", ctypes.c_double),
+        ("fast_i", ctypes.c_void_p), ("fast_c", ctypes.c_void_p), ("act_i", ctypes.c_void_p), ("act_d", ctypes.c_void_p),
     ]
 
 
@@ -42,7 +45,7 @@ _lib = None
 EXPORTS = (
     "br2_last_error", "br2_abi_version", "br2_create", "br2_destroy", "br2_words_per_instance",
     "br2_bind_state", "br2_set_actuation", "br2_step", "br2_step_host", "br2_count_steps",
-    "br2_kernel_info", "br2_fp64_peak_tflops",
+    "br2_kernel_info", "br2_fp64_peak_tflops", "br2_select_kernel", "br2_selftest_math",
 )
 
 
@@ -69,7 +72,9 @@ def load():
                                   ctypes.c_int64, ctypes.c_double, ctypes.c_double, _f64p]
     lib.br2_count_steps.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                     ctypes.POINTER(ctypes.c_int64), _f64p]
-    lib.br2_kernel_info.argtypes = [ctypes.c_void_p] + [_i32p] * 5
+    lib.br2_kernel_info.argtypes = [ctypes.c_void_p] + [_i32p] * 6
+    lib.br2_select_kernel.argtypes = [ctypes.c_void_p, ctypes.c_int32]
+    lib.br2_selftest_math.argtypes = [ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
     lib.br2_fp64_peak_tflops.argtypes = [ctypes.c_int, ctypes.c_int32, _f64p]
     if lib.br2_abi_version() != ABI_VERSION:
         raise Br2Error("libbr2cuda.so ABI %d != expected %d; rebuild" % (lib.br2_abi_version(), ABI_VERSION))
@@ -90,7 +95,9 @@ def make_program(prog):
         prog.words,
         *[t[name].ctypes.data for name in (
             "slot_rod", "rod_i", "rod_d", "slot_c", "forcing_i", "forcing_d", "cons_i", "cons_d", "joint_i",
-            "joint_d", "node_ptr", "node_items", "elem_ptr", "elem_items", "overwrite_src")])
+            "joint_d", "node_ptr", "node_items", "elem_ptr", "elem_items", "overwrite_src")],
+        int(prog.fast["ok"]), int(prog.fast["uniform"]), int(prog.fast["n_act"]), 0, float(prog.fast["ramp_up_time"]),
+        *[t[name].ctypes.data for name in ("fast_i", "fast_c", "act_i", "act_d")])
 
 
 def count_steps(t0, duration, dt):

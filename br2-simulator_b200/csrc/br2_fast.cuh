@@ -1,0 +1,532 @@
+// br2_fast.cuh -- the performance kernel: one fused PositionVerlet step loop for BR2-structured
+// assemblies (rods with damper / gravity / fibre actuation / base constraints, ring of surface joints
+// between parallel rods, tip-to-base joints between segments).
+//
+// Same phase structure and semantics as the generic kernel (br2_generic.cuh), but
+//   * no table walking inside the step loop: each thread's share of the operator tables (its joint, its
+//     gather lists, its actuation torque, its constraint flags) is decoded once per launch into
+//     registers / shared memory;
+//   * shared-memory exchange arrays have compile-time strides (no address arithmetic);
+//   * reciprocals instead of divisions, hardware-seeded rsqrt, short series for the tiny-angle
+//     transcendentals (br2_math.cuh), each with a libm slow path behind a never-taken-in-practice branch;
+//   * per-element constants come from the constant bank when every element of the assembly shares them
+//     (kUniform; the case for all BR2 sample assemblies), else from L1-cached global memory.
+#pragma once
+
+#include "br2_math.cuh"
+#include "br2_tables.cuh"
+
+namespace br2 {
+
+template <int kThreads, int kMinBlocks, bool kUniform>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(const __grid_constant__ StepParams p) {
+    constexpr int T = kThreads;
+    constexpr int TJ = kThreads + 64;  // joint rows (ring joints <= element slots, plus tip-to-base joints)
+    extern __shared__ double sm[];
+    double *X = sm;               // [3][T] node position
+    double *Vs = X + 3 * T;       // [3][T] node velocity
+    double *Qs = Vs + 3 * T;      // [9][T] element director
+    double *Ws = Qs + 9 * T;      // [3][T] element omega (only published when a joint overwrites directors)
+    double *Ls = Ws + 3 * T;      // [T] length
+    double *Rs = Ls + T;          // [T] radius
+    double *RSE = Rs + T;         // [T] 1/sqrt(dilatation)
+    double *Sk = RSE + T;         // [3][T] Q^T n_L / e
+    double *Av = Sk + 3 * T;      // [3][T] tau_L / E^3
+    double *Cv = Av + 3 * T;      // [3][T] (kappa x tau_L) D / E^3
+    double *JD = Cv + 3 * T;      // [7][T] own joint: dv1[3], dv2[3], offset
+    double *TA = JD + 7 * T;      // [3][T] actuation torque at full ramp
+    double *JF = TA + 3 * T;      // [3][TJ] half of the joint force
+    double *JT = JF + 3 * TJ;     // [2][3][TJ] joint torque on rod one / rod two (material frame)
+
+    const DevTables &tb = p.t;
+    const int S = tb.n_slots;
+    const int s = threadIdx.x;
+    const long long b = blockIdx.x;
+    const bool valid = s < S;
+    const int sc = valid ? s : S - 1;
+
+    const int rod = tb.slot_rod[sc];
+    const int *ri = tb.rod_i + rod * BR2_ROD_NI;
+    const int n = ri[BR2_ROD_N];
+    const int k = sc - ri[BR2_ROD_SLOT0];
+    const bool is_elem = valid && (k < n);
+    const bool is_vor = valid && (k < n - 1);
+
+    const int *fi = tb.fast_i + sc * BR2_FAST_NI;
+    const int flags = valid ? fi[BR2_FAST_FLAGS] : 0;
+    const int own_joint = valid ? fi[BR2_FAST_OWN_JOINT] : -1;
+    const int extra_joint = valid ? fi[BR2_FAST_EXTRA_JOINT] : -1;
+    const int softfix_row = valid ? fi[BR2_FAST_SOFTFIX_ROW] : -1;
+    const int elem_item0 = fi[BR2_FAST_ELEM_ITEM0], elem_item1 = fi[BR2_FAST_ELEM_ITEM0 + 1];
+    unsigned node_items[BR2_FAST_NODE_ITEMS / 2];
+    int node_count = 0;
+#pragma unroll
+    for (int q = 0; q < BR2_FAST_NODE_ITEMS; q += 2) {
+        const int i0 = fi[BR2_FAST_NODE_ITEM0 + q], i1 = fi[BR2_FAST_NODE_ITEM0 + q + 1];
+        node_items[q / 2] = (unsigned)(i0 & 0xFFFF) | ((unsigned)(i1 & 0xFFFF) << 16);
+        node_count += (i0 >= 0) + (i1 >= 0);
+    }
+    if (!valid) node_count = 0;
+    const int ow_src = valid ? tb.overwrite_src[sc] : -1;
+    const int own_partner = (own_joint >= 0) ? tb.joint_i[own_joint * BR2_J_NI + BR2_J_S1] : 0;
+
+    // ---- per-slot constants ---------------------------------------------------------------
+    const double *FCg = tb.fast_c + sc;
+#define FC(idx) (kUniform ? p.uni[(idx)] : __ldg(FCg + (long long)(idx) * S))
+    const double mass = tb.slot_c[(long long)BR2_SC_MASS * S + sc];
+    const double inv_mass = 1.0 / mass;
+
+    // own joint descriptor and actuation torque -> shared memory (read every step, written once)
+    {
+        const double *jd = tb.joint_d + (own_joint >= 0 ? own_joint : 0) * BR2_J_ND;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) JD[i * T + s] = (own_joint >= 0) ? jd[3 + i] : 0.0;
+        double ta[3] = {0.0, 0.0, 0.0};
+        if (valid) {
+            for (int r = fi[BR2_FAST_ACT_BEGIN]; r < fi[BR2_FAST_ACT_END]; ++r) {
+                const double P = p.pressures[(long long)tb.act_i[r] * p.batch + b];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) ta[i] = fma(P, tb.act_d[r * 3 + i], ta[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) TA[i * T + s] = ta[i];
+    }
+    const bool has_overwrite = (tb.n_joints > 0) && (__syncthreads_or(ow_src >= 0) != 0);
+
+    // ---- state in registers -------------------------------------------------------------
+    double *inst = p.state + b * tb.words + ri[BR2_ROD_WOFF];
+    const int np1 = n + 1;
+    double *g_x = inst, *g_v = g_x + 3 * np1, *g_Q = g_v + 3 * np1, *g_w = g_Q + 9 * n;
+    double *g_a = g_w + 3 * n, *g_alpha = g_a + 3 * np1, *g_fint = g_alpha + 3 * n, *g_tint = g_fint + 3 * np1;
+    double *g_fext = g_tint + 3 * n, *g_text = g_fext + 3 * np1, *g_len = g_text + 3 * n, *g_dil = g_len + n,
+           *g_rad = g_dil + n;
+
+    double x[3], v[3], Q[9], w[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        x[i] = valid ? g_x[i * np1 + k] : 0.0;
+        v[i] = valid ? g_v[i * np1 + k] : 0.0;
+        w[i] = is_elem ? g_w[i * n + k] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Q[i] = is_elem ? g_Q[i * n + k] : ((i % 4 == 0) ? 1.0 : 0.0);
+    // pinned values are constants of the launch: set once, never updated
+    if (flags & BR2_FAST_PIN_POSITION) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) x[i] = FCg[(long long)(BR2_FC_PIN + i) * S];
+    }
+    if (flags & BR2_FAST_PIN_DIRECTOR) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Q[i] = FCg[(long long)(BR2_FC_PIN + 3 + i) * S];
+    }
+    const bool move_x = !(flags & BR2_FAST_PIN_POSITION);
+    const bool spin_Q = is_elem && !(flags & BR2_FAST_PIN_DIRECTOR);
+
+    const double dt = p.dt, hdt = 0.5 * p.dt;
+    double time = p.t0;
+    const long long last_step = p.n_steps - 1;
+
+    for (long long step = 0; step < p.n_steps; ++step) {
+        const bool last = (step == last_step);
+        // =============================== P1: kinematic half step ===========================
+        if (move_x) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) x[i] = fma(hdt, v[i], x[i]);
+        }
+        if (spin_Q) rotate_directors(Q, hdt * w[0], hdt * w[1], hdt * w[2]);
+        time += hdt;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            X[i * T + s] = x[i];
+            Vs[i * T + s] = v[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Qs[i * T + s] = Q[i];
+        if (has_overwrite) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) Ws[i * T + s] = w[i];
+        }
+        __syncthreads();
+
+        // =============================== P2: element quantities =============================
+        double len = 1.0, rad = 1.0, dil = 1.0, rs_e = 1.0;
+        double sk[3] = {0, 0, 0}, local_t[3] = {0, 0, 0};
+        if (is_elem) {
+            double d[3], dv[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                d[i] = X[i * T + s + 1] - x[i];
+                dv[i] = Vs[i * T + s + 1] - v[i];
+            }
+            const double d2 = fma(d[0], d[0], fma(d[1], d[1], d[2] * d[2]));
+            const double rs = fast_rsqrt(d2);
+            len = fma(d2, rs, 1e-14);
+            const double inv_len = rs * fma(-1e-14, rs, 1.0);  // 1/(|d| + 1e-14), second order 1e-23
+            const double rest_len = FC(BR2_FC_REST_LEN), inv_rest_len = FC(BR2_FC_INV_REST_LEN);
+            const double r2 = FC(BR2_FC_VOL_OVER_PI) * inv_len;
+            rad = r2 * fast_rsqrt(r2);
+            dil = len * inv_rest_len;
+            const double inv_dil = rest_len * inv_len;
+            rs_e = fast_rsqrt(dil);
+            double qt[3], nL[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                qt[i] = fma(Q[3 * i], d[0], fma(Q[3 * i + 1], d[1], Q[3 * i + 2] * d[2])) * inv_len;
+                const double sigma = fma(dil, qt[i], (i == 2) ? -1.0 : 0.0);
+                nL[i] = FC(BR2_FC_SHEAR + i) * sigma;
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) sk[i] = fma(Q[i], nL[0], fma(Q[3 + i], nL[1], Q[6 + i] * nL[2])) * inv_dil;
+            // d(e)/dt = (x_{k+1} - x_k).(v_{k+1} - v_k) / l / l_hat  (expanded form in the reference)
+            const double edot = fma(d[0], dv[0], fma(d[1], dv[1], d[2] * dv[2])) * inv_len * inv_rest_len;
+            double jw[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) jw[i] = FC(BR2_FC_J + i) * w[i] * inv_dil;
+            const double ue = edot * inv_dil;
+            local_t[0] = fma(fma(qt[1], nL[2], -qt[2] * nL[1]), rest_len, fma(jw[1], w[2], fma(-jw[2], w[1], jw[0] * ue)));
+            local_t[1] = fma(fma(qt[2], nL[0], -qt[0] * nL[2]), rest_len, fma(jw[2], w[0], fma(-jw[0], w[2], jw[1] * ue)));
+            local_t[2] = fma(fma(qt[0], nL[1], -qt[1] * nL[0]), rest_len, fma(jw[0], w[1], fma(-jw[1], w[0], jw[2] * ue)));
+        }
+        Ls[s] = len;
+        Rs[s] = rad;
+        RSE[s] = rs_e;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) Sk[i * T + s] = sk[i];
+        __syncthreads();
+
+        // =============================== P3: Voronoi couples and joints =====================
+        double Ak[3] = {0, 0, 0}, Ck[3] = {0, 0, 0};
+        if (is_vor) {
+            double Qn[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Qn[i] = Qs[i * T + s + 1];
+#define ROWDOT(a_, b_) fma(Qn[3 * (a_)], Q[3 * (b_)], fma(Qn[3 * (a_) + 1], Q[3 * (b_) + 1], Qn[3 * (a_) + 2] * Q[3 * (b_) + 2]))
+            const double w0 = ROWDOT(2, 1) - ROWDOT(1, 2);
+            const double w1 = ROWDOT(0, 2) - ROWDOT(2, 0);
+            const double w2 = ROWDOT(1, 0) - ROWDOT(0, 1);
+            const double tr = ROWDOT(0, 0) + ROWDOT(1, 1) + ROWDOT(2, 2);
+#undef ROWDOT
+            const double rest_vlen = FC(BR2_FC_REST_VLEN), inv_rest_vlen = FC(BR2_FC_INV_REST_VLEN);
+            const double ks = logmap_scale(fma(0.5, tr, -0.5 - 1e-10)) * inv_rest_vlen;
+            const double kap[3] = {w0 * ks, w1 * ks, w2 * ks};
+            const double tau[3] = {FC(BR2_FC_BEND) * kap[0], FC(BR2_FC_BEND + 1) * kap[1], FC(BR2_FC_BEND + 2) * kap[2]};
+            const double vdil = 0.5 * (Ls[s + 1] + len) * inv_rest_vlen;
+            const double iv = fast_rcp(vdil);
+            const double inv3 = iv * iv * iv;
+            const double dinv3 = rest_vlen * inv3;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) Ak[i] = tau[i] * inv3;
+            Ck[0] = fma(kap[1], tau[2], -kap[2] * tau[1]) * dinv3;
+            Ck[1] = fma(kap[2], tau[0], -kap[0] * tau[2]) * dinv3;
+            Ck[2] = fma(kap[0], tau[1], -kap[1] * tau[0]) * dinv3;
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            Av[i * T + s] = Ak[i];
+            Cv[i * T + s] = Ck[i];
+        }
+        // own joint: this element is rod two (own data in registers), rod one's element is in shared memory
+        if (own_joint >= 0) {
+            const int s1 = own_partner;
+            double Q1[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Q1[i] = Qs[i * T + s1];
+            double c1[3], c2[3], cd[3], vrel[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                c1[i] = 0.5 * (X[i * T + s1] + X[i * T + s1 + 1]);
+                c2[i] = 0.5 * (x[i] + X[i * T + s + 1]);
+                cd[i] = c2[i] - c1[i];
+                vrel[i] = 0.5 * (v[i] + Vs[i * T + s + 1]) - 0.5 * (Vs[i * T + s1] + Vs[i * T + s1 + 1]);
+            }
+            const double off = JD[6 * T + s];
+            const double ra1 = fma(0.5 * off, RSE[s1], Rs[s1]);   // r1 + o1
+            const double ra2 = fma(0.5 * off, rs_e, rad);         // r2 + o2
+            const double jk = FC(BR2_FC_JK), jnu = FC(BR2_FC_JNU);
+            double rd1[3], rd2[3], dvec[3], Fs[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const double g1 = fma(Q1[i], JD[0 * T + s], fma(Q1[3 + i], JD[1 * T + s], Q1[6 + i] * JD[2 * T + s]));
+                const double g2 = fma(Q[i], JD[3 * T + s], fma(Q[3 + i], JD[4 * T + s], Q[6 + i] * JD[5 * T + s]));
+                rd1[i] = g1 * ra1;
+                rd2[i] = g2 * ra2;
+                // (c2 + rd2) - (c1 + rd1), rounded to 12 decimals like np.round_(x, 12)
+                const double di = (c2[i] + rd2[i]) - (c1[i] + rd1[i]);
+                dvec[i] = rint(di * 1e12) * 1e-12;
+                Fs[i] = jk * dvec[i];
+            }
+            const double dist2 = fma(dvec[0], dvec[0], fma(dvec[1], dvec[1], dvec[2] * dvec[2]));
+            double F[3] = {Fs[0], Fs[1], Fs[2]};
+            if (dist2 >= 1e-24) {
+                const double rdist = fast_rsqrt(dist2);
+                const double proj = fma(vrel[0], dvec[0], fma(vrel[1], dvec[1], vrel[2] * dvec[2])) * rdist;
+                const double coef = -jnu * proj * rdist;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) F[i] = fma(coef, dvec[i], F[i]);
+            }
+            const double cn2 = fma(cd[0], cd[0], fma(cd[1], cd[1], cd[2] * cd[2]));
+            const double rcn = fast_rsqrt(cn2);
+            const double pen = fma(cn2, rcn, -(ra1 + ra2));
+            if (pen < 0.0) {
+                const double ap = -pen;
+                const double mag = -FC(BR2_FC_JKREP) * ap * (ap * fast_rsqrt(ap)) * rcn;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) F[i] = fma(mag, cd[i], F[i]);
+            }
+            const double t1[3] = {fma(rd1[1], Fs[2], -rd1[2] * Fs[1]), fma(rd1[2], Fs[0], -rd1[0] * Fs[2]),
+                                  fma(rd1[0], Fs[1], -rd1[1] * Fs[0])};
+            const double t2[3] = {fma(rd2[2], Fs[1], -rd2[1] * Fs[2]), fma(rd2[0], Fs[2], -rd2[2] * Fs[0]),
+                                  fma(rd2[1], Fs[0], -rd2[0] * Fs[1])};
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                JF[i * TJ + own_joint] = 0.5 * F[i];
+                JT[i * TJ + own_joint] = fma(Q1[3 * i], t1[0], fma(Q1[3 * i + 1], t1[1], Q1[3 * i + 2] * t1[2]));
+                JT[(3 + i) * TJ + own_joint] = fma(Q[3 * i], t2[0], fma(Q[3 * i + 1], t2[1], Q[3 * i + 2] * t2[2]));
+            }
+        }
+        // one further joint per thread (tip-to-base joints, or surface joints that did not fit the
+        // "own" pattern), both sides read from shared memory, descriptor from the generic tables
+        if (extra_joint >= 0) {
+            const int j = extra_joint;
+            const int *ji = tb.joint_i + j * BR2_J_NI;
+            const double *jd = tb.joint_d + j * BR2_J_ND;
+            const int type = ji[BR2_J_TYPE], s1 = ji[BR2_J_S1], s2 = ji[BR2_J_S2], q1 = ji[BR2_J_Q1], q2 = ji[BR2_J_Q2];
+            const double kj = jd[0], nuj = jd[1];
+            double Q1[9], Q2[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                Q1[i] = Qs[i * T + q1];
+                Q2[i] = Qs[i * T + q2];
+            }
+            double c1[3], c2[3], cd[3], vrel[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                c1[i] = 0.5 * (X[i * T + s1] + X[i * T + s1 + 1]);
+                c2[i] = 0.5 * (X[i * T + s2] + X[i * T + s2 + 1]);
+                cd[i] = c2[i] - c1[i];
+                vrel[i] = 0.5 * (Vs[i * T + s2] + Vs[i * T + s2 + 1]) - 0.5 * (Vs[i * T + s1] + Vs[i * T + s1 + 1]);
+            }
+            double F[3], T1[3] = {0, 0, 0}, T2[3] = {0, 0, 0};
+            if (type == BR2_JOINT_SURFACE) {
+                const double off = jd[9];
+                const double ra1 = fma(0.5 * off, RSE[s1], Rs[s1]);
+                const double ra2 = fma(0.5 * off, RSE[s2], Rs[s2]);
+                double rd1[3], rd2[3], dvec[3], Fs[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const double g1 = fma(Q1[i], jd[3], fma(Q1[3 + i], jd[4], Q1[6 + i] * jd[5]));
+                    const double g2 = fma(Q2[i], jd[6], fma(Q2[3 + i], jd[7], Q2[6 + i] * jd[8]));
+                    rd1[i] = g1 * ra1;
+                    rd2[i] = g2 * ra2;
+                    const double di = (c2[i] + rd2[i]) - (c1[i] + rd1[i]);
+                    dvec[i] = rint(di * 1e12) * 1e-12;
+                    Fs[i] = kj * dvec[i];
+                    F[i] = Fs[i];
+                }
+                const double dist2 = fma(dvec[0], dvec[0], fma(dvec[1], dvec[1], dvec[2] * dvec[2]));
+                if (dist2 >= 1e-24) {
+                    const double rdist = fast_rsqrt(dist2);
+                    const double proj = fma(vrel[0], dvec[0], fma(vrel[1], dvec[1], vrel[2] * dvec[2])) * rdist;
+                    const double coef = -nuj * proj * rdist;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) F[i] = fma(coef, dvec[i], F[i]);
+                }
+                const double cn2 = fma(cd[0], cd[0], fma(cd[1], cd[1], cd[2] * cd[2]));
+                const double rcn = fast_rsqrt(cn2);
+                const double pen = fma(cn2, rcn, -(ra1 + ra2));
+                if (pen < 0.0) {
+                    const double ap = -pen;
+                    const double mag = -jd[2] * ap * (ap * fast_rsqrt(ap)) * rcn;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) F[i] = fma(mag, cd[i], F[i]);
+                }
+                const double t1[3] = {fma(rd1[1], Fs[2], -rd1[2] * Fs[1]), fma(rd1[2], Fs[0], -rd1[0] * Fs[2]),
+                                      fma(rd1[0], Fs[1], -rd1[1] * Fs[0])};
+                const double t2[3] = {fma(rd2[2], Fs[1], -rd2[1] * Fs[2]), fma(rd2[0], Fs[2], -rd2[2] * Fs[0]),
+                                      fma(rd2[1], Fs[0], -rd2[0] * Fs[1])};
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    T1[i] = fma(Q1[3 * i], t1[0], fma(Q1[3 * i + 1], t1[1], Q1[3 * i + 2] * t1[2]));
+                    T2[i] = fma(Q2[3 * i], t2[0], fma(Q2[3 * i + 1], t2[1], Q2[3 * i + 2] * t2[2]));
+                }
+            } else {  // tip-to-base: un-rounded spring, un-projected damping, no torque
+                const double r1 = Rs[s1], r2 = Rs[s2];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const double a1 = fma(Q1[i], jd[3], fma(Q1[3 + i], jd[4], Q1[6 + i] * jd[5])) * r1;
+                    const double a2 = fma(Q2[i], jd[6], fma(Q2[3 + i], jd[7], Q2[6 + i] * jd[8])) * r2;
+                    const double gap = (c2[i] + a2) - (c1[i] + a1);
+                    F[i] = fma(kj, gap, -nuj * vrel[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                JF[i * TJ + j] = 0.5 * F[i];
+                JT[i * TJ + j] = T1[i];
+                JT[(3 + i) * TJ + j] = T2[i];
+            }
+        }
+        // tip-to-base joints overwrite the downstream base element's director / omega during
+        // synchronize; sources are start-of-synchronize values, still in Qs / Ws
+        if (ow_src >= 0) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Q[i] = Qs[i * T + ow_src];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) w[i] = Ws[i * T + ow_src];
+        }
+        __syncthreads();
+
+        // =============================== P4: assemble, dynamic step =========================
+        {
+            const bool first = (k == 0);
+            double f_int[3], t_int[3], f_ext[3], t_ext[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const double prev = first ? 0.0 : Sk[i * T + s - 1];
+                f_int[i] = sk[i] - prev;  // sk is 0 on the node-only slot k = n
+                const double Ap = first ? 0.0 : Av[i * T + s - 1];
+                const double Cp = first ? 0.0 : Cv[i * T + s - 1];
+                t_int[i] = (Ak[i] - Ap) + fma(0.5, Ck[i] + Cp, local_t[i]);  // Ak = Ck = 0 on k = n-1
+            }
+            // external loads: (soft-fix spring, reported only) -> forcing -> joints in registration order
+            double spring[3] = {0, 0, 0};
+            if (last && softfix_row >= 0) {
+                const double *cd = tb.cons_d + softfix_row * BR2_C_ND;
+                const double e0 = cd[0] - x[0], e1 = cd[1] - x[1], e2 = cd[2] - x[2];
+                const double dist = sqrt(e0 * e0 + e1 * e1 + e2 * e2);
+                double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+                if (!(dist <= 1e-8)) {
+                    u0 = e0 / dist;
+                    u1 = e1 / dist;
+                    u2 = e2 / dist;
+                }
+                const double proj = (-v[0]) * u0 + (-v[1]) * u1 + (-v[2]) * u2;
+                spring[0] = cd[12] * e0 + (-cd[13] * (proj * u0));
+                spring[1] = cd[12] * e1 + (-cd[13] * (proj * u1));
+                spring[2] = cd[12] * e2 + (-cd[13] * (proj * u2));
+            }
+            const double ramp = fmin(1.0, time * tb.act_inv_ramp);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                f_ext[i] = fma(FC(BR2_FC_GRAVITY + i), mass, spring[i]);
+                t_ext[i] = TA[i * T + s] * ramp;
+            }
+#pragma unroll
+            for (int q = 0; q < BR2_FAST_NODE_ITEMS; ++q) {
+                if (q < node_count) {
+                    const unsigned item = (node_items[q >> 1] >> ((q & 1) * 16)) & 0xFFFFu;
+                    const double sgn = (item & 1u) ? -1.0 : 1.0;
+                    const int j = (int)(item >> 1);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) f_ext[i] = fma(sgn, JF[i * TJ + j], f_ext[i]);
+                }
+            }
+            if (elem_item0 >= 0) {
+                const int base = (elem_item0 & 1) * 3 * TJ + (elem_item0 >> 1);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) t_ext[i] += JT[base + i * TJ];
+            }
+            if (elem_item1 >= 0) {
+                const int base = (elem_item1 & 1) * 3 * TJ + (elem_item1 >> 1);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) t_ext[i] += JT[base + i * TJ];
+            }
+            // dynamic step, damper, rate constraints
+            double a[3], alpha[3];
+            const double c_t = FC(BR2_FC_CT);
+            const double strain = dil - 1.0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                a[i] = (f_int[i] + f_ext[i]) * inv_mass;
+                v[i] = fma(dt, a[i], v[i]) * c_t;
+                alpha[i] = FC(BR2_FC_JINV + i) * (t_int[i] + t_ext[i]) * dil;
+                w[i] = fma(dt, alpha[i], w[i]) * (FC(BR2_FC_CR + i) * exp_near_zero(strain * FC(BR2_FC_LN_CR + i)));
+            }
+            if (flags & BR2_FAST_ZERO_NODE_RATE) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) v[i] = 0.0;
+            }
+            if (flags & BR2_FAST_ZERO_ELEM_RATE) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) w[i] = 0.0;
+            }
+            if (last && valid) {
+                if (flags & BR2_FAST_ZERO_REPORTED) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) a[i] = alpha[i] = 0.0;
+                }
+                if (softfix_row >= 0) {
+                    // second constrain_values of the step: node 0 has not moved and its velocity is now zero
+                    const double *cd = tb.cons_d + softfix_row * BR2_C_ND;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) f_ext[i] += cd[12] * (cd[i] - x[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    g_a[i * np1 + k] = a[i];
+                    g_fint[i * np1 + k] = f_int[i];
+                    g_fext[i * np1 + k] = f_ext[i];
+                }
+                if (is_elem) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        g_alpha[i * n + k] = alpha[i];
+                        g_tint[i * n + k] = t_int[i];
+                        g_text[i * n + k] = t_ext[i];
+                    }
+                    g_len[k] = len;
+                    g_dil[k] = dil;
+                    g_rad[k] = rad;
+                }
+            }
+        }
+        // second kinematic half step (value constraints = the pins, which never move)
+        if (move_x) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) x[i] = fma(hdt, v[i], x[i]);
+        }
+        if (spin_Q) rotate_directors(Q, hdt * w[0], hdt * w[1], hdt * w[2]);
+        time += hdt;
+    }
+
+    if (valid) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            g_x[i * np1 + k] = x[i];
+            g_v[i * np1 + k] = v[i];
+        }
+        if (is_elem) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) g_Q[i * n + k] = Q[i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) g_w[i * n + k] = w[i];
+        }
+    }
+#undef FC
+}
+
+// evaluation of the math helpers on arrays (tests only)
+__global__ void selftest_math_kernel(int which, const double *in, double *out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = in[i];
+    double y = 0.0, sinc, cosc;
+    switch (which) {
+    case 0: y = fast_rcp(x); break;
+    case 1: y = fast_rsqrt(x); break;
+    case 2:
+        if (x <= 0.01) sinc_cosc_small(x, sinc, cosc); else sinc_cosc_large(x, sinc, cosc);
+        y = sinc;
+        break;
+    case 3:
+        if (x <= 0.01) sinc_cosc_small(x, sinc, cosc); else sinc_cosc_large(x, sinc, cosc);
+        y = cosc;
+        break;
+    case 4: y = logmap_scale(x); break;
+    default: y = exp_near_zero(x); break;
+    }
+    out[i] = y;
+}
+
+}  // namespace br2

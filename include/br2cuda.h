@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define BR2_ABI_VERSION 1
+#define BR2_ABI_VERSION 2
 
 enum {
     BR2_OK = 0,
@@ -105,6 +105,48 @@ enum {
     BR2_JOINT_TIP_TO_BASE = 1 /* d = {k, nu, 0, l1[3], l2[3], 0}                   TipToTipStraightJoint (legacy...:346-478) */
 };
 
+/* ---- fast-path tables -------------------------------------------------------------------------
+ * The BR2 assembly structure (every operator of SURVEY.md section 8a rows A5-A12) is served by a
+ * specialised kernel that keeps per-slot descriptors in registers / shared memory instead of walking
+ * the generic tables every step.  finalize() fills these when the assembly qualifies (fast_ok = 1):
+ *   - forcing rows are gravity / twist / bend only, all with the same ramp_up_time;
+ *   - rest_sigma and rest_kappa are zero;
+ *   - every element owns at most one surface joint as "rod two" and at most one further joint,
+ *     every node receives at most BR2_FAST_NODE_ITEMS half-forces and every element at most two torques.
+ * Otherwise the generic table-interpreting kernel runs.  Same results either way (tests compare them).
+ */
+/* fast_i: [n_slots][BR2_FAST_NI] int32 */
+enum {
+    BR2_FAST_FLAGS = 0,
+    BR2_FAST_OWN_JOINT = 1,    /* joint row this slot's element evaluates as rod two, or -1 */
+    BR2_FAST_EXTRA_JOINT = 2,  /* one more joint row evaluated by this thread from shared memory, or -1 */
+    BR2_FAST_SOFTFIX_ROW = 3,  /* constraint row of a soft-fixed base on this slot (node 0), or -1 */
+    BR2_FAST_ACT_BEGIN = 4,    /* actuation rows [begin, end) acting on this slot's element */
+    BR2_FAST_ACT_END = 5,
+    BR2_FAST_ELEM_ITEM0 = 6,   /* 2 torque gather items ((joint << 1) | side), -1 = none */
+    BR2_FAST_NODE_ITEM0 = 8,   /* BR2_FAST_NODE_ITEMS force gather items ((joint << 1) | sign), -1 = none */
+    BR2_FAST_NI = 16
+};
+enum { BR2_FAST_NODE_ITEMS = 8 };
+enum {
+    BR2_FAST_PIN_DIRECTOR = 1,  /* element director is reset to a constant every half step */
+    BR2_FAST_PIN_POSITION = 2,  /* node position is reset to a constant every half step */
+    BR2_FAST_ZERO_NODE_RATE = 4,/* node velocity (and reported acceleration) zeroed in constrain_rates */
+    BR2_FAST_ZERO_ELEM_RATE = 8,/* element omega (and reported alpha) zeroed in constrain_rates */
+    BR2_FAST_ZERO_REPORTED = 16 /* soft-fixed base also zeroes the reported a / alpha of slot 0 */
+};
+/* fast_c: [BR2_FC_COUNT][n_slots] double.  Element / Voronoi constants with reciprocals precomputed. */
+enum {
+    BR2_FC_REST_LEN = 0, BR2_FC_INV_REST_LEN = 1, BR2_FC_VOL_OVER_PI = 2,
+    BR2_FC_SHEAR = 3, BR2_FC_J = 6, BR2_FC_JINV = 9, BR2_FC_LN_CR = 12, BR2_FC_CR = 15,
+    BR2_FC_REST_VLEN = 18, BR2_FC_INV_REST_VLEN = 19, BR2_FC_BEND = 20,
+    BR2_FC_CT = 23,          /* translational damping factor of the slot's rod (1 if none) */
+    BR2_FC_GRAVITY = 24,     /* 3: summed gravity acceleration on the slot's rod */
+    BR2_FC_JK = 27, BR2_FC_JNU = 28, BR2_FC_JKREP = 29,  /* parameters of the slot's own joint */
+    BR2_FC_PIN = 30,         /* 12: pinned position (3) and director (9) for BR2_FAST_PIN_* slots */
+    BR2_FC_COUNT = 42
+};
+
 typedef struct br2_program {
     int32_t abi_version;          /* BR2_ABI_VERSION */
     int32_t n_slots, n_rods, n_forcing, n_constraints, n_joints, n_actions;
@@ -127,6 +169,17 @@ typedef struct br2_program {
     const int32_t *elem_items;
     const int32_t *overwrite_src; /* [n_slots] element slot whose director/omega replace this slot's during
                                      synchronize (tip-to-base joint), or -1 */
+    /* fast path */
+    int32_t fast_ok;              /* 1: the fast tables below are valid */
+    int32_t fast_uniform;         /* 1: every element slot has identical fast_c constants (up to 1e-13
+                                     relative; kernel then reads them from the constant bank) */
+    int32_t n_act;                /* actuation rows */
+    int32_t reserved;
+    double act_ramp_up_time;
+    const int32_t *fast_i;
+    const double *fast_c;
+    const int32_t *act_i;         /* [n_act] action index */
+    const double *act_d;          /* [n_act][3] material-frame torque per unit pressure at full ramp */
 } br2_program;
 
 /* Instance state layout (doubles), per rod at BR2_ROD_WOFF, component-major like numpy [3, n]:
@@ -165,9 +218,16 @@ int br2_step_host(br2_handle h, double *host_state, const double *host_pressures
 int br2_count_steps(double t0, double duration, double dt, int64_t *n_steps, double *t_end);
 
 /* Kernel facts for measurement: registers per thread, dynamic shared memory per block, threads per
- * block, resident blocks per SM as reported by the occupancy API, SM count of the device. */
+ * block, resident blocks per SM as reported by the occupancy API, SM count of the device, and which
+ * kernel br2_step launches (0 generic, 1 fast per-slot constants, 2 fast uniform constants). */
 int br2_kernel_info(br2_handle h, int32_t *regs, int32_t *smem_bytes, int32_t *threads,
-                    int32_t *blocks_per_sm, int32_t *sm_count);
+                    int32_t *blocks_per_sm, int32_t *sm_count, int32_t *variant);
+/* Force the kernel variant (0 generic, 1 fast, 2 fast uniform, -1 automatic); for cross-checks. */
+int br2_select_kernel(br2_handle h, int32_t variant);
+/* Evaluate the fast kernel's fp64 helpers on device arrays of n doubles (tests only):
+ * which = 0 rcp, 1 rsqrt, 2 sinc(theta) [in: theta^2], 3 cosc(theta) [in: theta^2],
+ *         4 log-map scale [in: cos theta], 5 exp near zero. */
+int br2_selftest_math(int32_t which, const double *dev_in, double *dev_out, int64_t n);
 
 /* fp64 roofline denominator: runs a register-resident DFMA chain kernel on `device` and returns the
  * best-of-`repeats` rate in TFLOP/s (FMA = 2 flop). */

@@ -24,11 +24,17 @@ SHORT = {"position_collection": "x", "velocity_collection": "v", "director_colle
          "omega_collection": "w", "acceleration_collection": "a"}
 
 
-def make_env(assembly, batch, fps=25, **kwargs):
+VARIANTS = {"generic": 0, "fast": 1, "fast-uniform": 2}
+
+
+def make_env(assembly, batch, fps=25, variant=None, **kwargs):
     from br2.environment import Environment
 
     env = Environment("gpu_test", rendering_fps=fps, batch=batch, create_dirs=False)
     env.reset(ROD_DB, ASSEMBLY[assembly], **kwargs)
+    if variant is not None:
+        env.engine.select_kernel(VARIANTS[variant])
+        assert env.engine.kernel_info()["variant_name"] == variant
     return env
 
 
@@ -38,6 +44,7 @@ def test_golden_trajectories(case):
     name, assembly, kwargs, action, duration, fps = case
     g = np.load(os.path.join(GOLDEN, "traj_%s.npz" % name))
     env = make_env(assembly, 1, fps=fps, **kwargs)
+    assert env.engine.kernel_info()["variant_name"] == "fast-uniform"  # the sample assemblies take the fast path
     status = env.run(action, duration=duration, disable_progress_bar=True, check_nan=True, check_steady_state=1)
     assert env.time == float(g["final_time"]) and env.step_skip == int(g["step_skip"])
     assert list(env.shearable_rods.keys()) == list(g["rod_names"])
@@ -88,12 +95,13 @@ BATCH_CASES = [
 ]
 
 
+@pytest.mark.parametrize("variant", list(VARIANTS))
 @pytest.mark.parametrize("assembly,kwargs,seed,n_steps", BATCH_CASES, ids=[c[0] for c in BATCH_CASES])
-def test_batched_random_pressures_match_oracle(assembly, kwargs, seed, n_steps):
+def test_batched_random_pressures_match_oracle(assembly, kwargs, seed, n_steps, variant):
     batch, dt = 64, 2.0e-5
     rng = np.random.default_rng(seed)
     pressures = rng.uniform(0.0, 40.0, size=(3, batch)) * PSI
-    env = make_env(assembly, batch, **kwargs)
+    env = make_env(assembly, batch, variant=variant, **kwargs)
     env.simulator._callback_ops = []
     action = {name: pressures[i] for i, name in enumerate(NAMES)}
     status = env.run(action, duration=n_steps * dt - 0.5 * dt, disable_progress_bar=True, check_nan=True)
@@ -108,11 +116,11 @@ def test_batched_random_pressures_match_oracle(assembly, kwargs, seed, n_steps):
                 continue
             err = np.abs(getattr(rod, attr) - fused.view(W, r, short)).max()
             worst[short] = max(worst[short], err / x_scale if short == "x" else err)
-    print(assembly, "worst errors", worst)
+    print(assembly, variant, "worst errors", worst)
     assert worst["x"] <= POS_TOL and worst["Q"] <= DIR_TOL
     assert worst["v"] <= VEL_TOL and worst["w"] <= OMEGA_TOL
     # instances really are independent: instance 5 alone reproduces its batch result bit for bit
-    solo = make_env(assembly, 1, **kwargs)
+    solo = make_env(assembly, 1, variant=variant, **kwargs)
     solo.simulator._callback_ops = []
     solo.run({name: pressures[i, 5] for i, name in enumerate(NAMES)}, duration=n_steps * dt - 0.5 * dt,
              disable_progress_bar=True)
