@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(PKG_DIR, "lib", "libbr2cuda.so")
+LIB_PATH = os.environ.get("BR2_CUDA_LIB") or os.path.join(PKG_DIR, "lib", "libbr2cuda.so")
 ABI_VERSION = 2
 
 _i32p = ctypes.POINTER(ctypes.c_int32)

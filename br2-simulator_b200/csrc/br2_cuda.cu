@@ -20,6 +20,9 @@
 #define BR2_PI 3.141592653589793
 #endif
 
+#ifndef BR2_MB128
+#define BR2_MB128 3
+#endif
 #include "br2_fast.cuh"
 #include "br2_generic.cuh"
 #include "br2_tables.cuh"
@@ -79,10 +82,10 @@ const KernelChoice kKernels[3][6] = {
     {{128, br2::br2_step_generic_kernel<128, 4>}, {256, br2::br2_step_generic_kernel<256, 2>},
      {384, br2::br2_step_generic_kernel<384, 1>}, {512, br2::br2_step_generic_kernel<512, 1>},
      {768, br2::br2_step_generic_kernel<768, 1>}, {1024, br2::br2_step_generic_kernel<1024, 1>}},
-    {{128, br2::br2_step_fast_kernel<128, 4, false>}, {256, br2::br2_step_fast_kernel<256, 2, false>},
+    {{128, br2::br2_step_fast_kernel<128, BR2_MB128, false>}, {256, br2::br2_step_fast_kernel<256, 2, false>},
      {384, br2::br2_step_fast_kernel<384, 1, false>}, {512, br2::br2_step_fast_kernel<512, 1, false>},
      {768, br2::br2_step_fast_kernel<768, 1, false>}, {1024, br2::br2_step_fast_kernel<1024, 1, false>}},
-    {{128, br2::br2_step_fast_kernel<128, 4, true>}, {256, br2::br2_step_fast_kernel<256, 2, true>},
+    {{128, br2::br2_step_fast_kernel<128, BR2_MB128, true>}, {256, br2::br2_step_fast_kernel<256, 2, true>},
      {384, br2::br2_step_fast_kernel<384, 1, true>}, {512, br2::br2_step_fast_kernel<512, 1, true>},
      {768, br2::br2_step_fast_kernel<768, 1, true>}, {1024, br2::br2_step_fast_kernel<1024, 1, true>}},
 };

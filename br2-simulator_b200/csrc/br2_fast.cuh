@@ -95,22 +95,32 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
     const bool has_overwrite = (tb.n_joints > 0) && (__syncthreads_or(ow_src >= 0) != 0);
 
     // ---- state in registers -------------------------------------------------------------
-    double *inst = p.state + b * tb.words + ri[BR2_ROD_WOFF];
+    // field offsets inside the rod's block (include/br2cuda.h), derived where needed from n
+    double *const inst = p.state + b * tb.words + ri[BR2_ROD_WOFF];
     const int np1 = n + 1;
-    double *g_x = inst, *g_v = g_x + 3 * np1, *g_Q = g_v + 3 * np1, *g_w = g_Q + 9 * n;
-    double *g_a = g_w + 3 * n, *g_alpha = g_a + 3 * np1, *g_fint = g_alpha + 3 * n, *g_tint = g_fint + 3 * np1;
-    double *g_fext = g_tint + 3 * n, *g_text = g_fext + 3 * np1, *g_len = g_text + 3 * n, *g_dil = g_len + n,
-           *g_rad = g_dil + n;
+#define G_X (inst)
+#define G_V (inst + 3 * np1)
+#define G_Q (inst + 6 * np1)
+#define G_W (inst + 6 * np1 + 9 * n)
+#define G_A (inst + 6 * np1 + 12 * n)
+#define G_ALPHA (inst + 9 * np1 + 12 * n)
+#define G_FINT (inst + 9 * np1 + 15 * n)
+#define G_TINT (inst + 12 * np1 + 15 * n)
+#define G_FEXT (inst + 12 * np1 + 18 * n)
+#define G_TEXT (inst + 15 * np1 + 18 * n)
+#define G_LEN (inst + 15 * np1 + 21 * n)
+#define G_DIL (inst + 15 * np1 + 22 * n)
+#define G_RAD (inst + 15 * np1 + 23 * n)
 
     double x[3], v[3], Q[9], w[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        x[i] = valid ? g_x[i * np1 + k] : 0.0;
-        v[i] = valid ? g_v[i * np1 + k] : 0.0;
-        w[i] = is_elem ? g_w[i * n + k] : 0.0;
+        x[i] = valid ? G_X[i * np1 + k] : 0.0;
+        v[i] = valid ? G_V[i * np1 + k] : 0.0;
+        w[i] = is_elem ? G_W[i * n + k] : 0.0;
     }
 #pragma unroll
-    for (int i = 0; i < 9; ++i) Q[i] = is_elem ? g_Q[i * n + k] : ((i % 4 == 0) ? 1.0 : 0.0);
+    for (int i = 0; i < 9; ++i) Q[i] = is_elem ? G_Q[i * n + k] : ((i % 4 == 0) ? 1.0 : 0.0);
     // pinned values are constants of the launch: set once, never updated
     if (flags & BR2_FAST_PIN_POSITION) {
 #pragma unroll
@@ -124,18 +134,21 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
     const bool spin_Q = is_elem && !(flags & BR2_FAST_PIN_DIRECTOR);
 
     const double dt = p.dt, hdt = 0.5 * p.dt;
-    double time = p.t0;
+    double time = p.t0;  // time at the start of the current step
     const long long last_step = p.n_steps - 1;
+
+    // leading kinematic half step of the first step; every later one is fused with the trailing half
+    // step of the step before it (same velocities, same omega)
+    if (move_x) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) x[i] = fma(hdt, v[i], x[i]);
+    }
+    if (spin_Q) rotate_directors(Q, hdt * w[0], hdt * w[1], hdt * w[2], 1.0);
 
     for (long long step = 0; step < p.n_steps; ++step) {
         const bool last = (step == last_step);
-        // =============================== P1: kinematic half step ===========================
-        if (move_x) {
-#pragma unroll
-            for (int i = 0; i < 3; ++i) x[i] = fma(hdt, v[i], x[i]);
-        }
-        if (spin_Q) rotate_directors(Q, hdt * w[0], hdt * w[1], hdt * w[2]);
-        time += hdt;
+        // =============================== P1: publish the half-stepped state ================
+        const double time_mid = time + hdt;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             X[i * T + s] = x[i];
@@ -161,14 +174,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
             }
             const double d2 = fma(d[0], d[0], fma(d[1], d[1], d[2] * d[2]));
             const double rs = fast_rsqrt(d2);
-            len = fma(d2, rs, 1e-14);
-            const double inv_len = rs * fma(-1e-14, rs, 1.0);  // 1/(|d| + 1e-14), second order 1e-23
+            len = fma(d2, rs, BR2_EPS14);
+            const double inv_len = rs * fma(-BR2_EPS14, rs, 1.0);  // 1/(|d| + 1e-14), second order 1e-23
             const double rest_len = FC(BR2_FC_REST_LEN), inv_rest_len = FC(BR2_FC_INV_REST_LEN);
             const double r2 = FC(BR2_FC_VOL_OVER_PI) * inv_len;
             rad = r2 * fast_rsqrt(r2);
             dil = len * inv_rest_len;
             const double inv_dil = rest_len * inv_len;
-            rs_e = fast_rsqrt(dil);
+            rs_e = seed_rsqrt(dil);  // only thins the ~1e-8 m rest gap of a joint: 2^-20 relative is ample
             double qt[3], nL[3];
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
@@ -208,7 +221,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
             const double tr = ROWDOT(0, 0) + ROWDOT(1, 1) + ROWDOT(2, 2);
 #undef ROWDOT
             const double rest_vlen = FC(BR2_FC_REST_VLEN), inv_rest_vlen = FC(BR2_FC_INV_REST_VLEN);
-            const double ks = logmap_scale(fma(0.5, tr, -0.5 - 1e-10)) * inv_rest_vlen;
+            const double ks = logmap_scale(fma(0.5, tr, kMisc[6])) * inv_rest_vlen;
             const double kap[3] = {w0 * ks, w1 * ks, w2 * ks};
             const double tau[3] = {FC(BR2_FC_BEND) * kap[0], FC(BR2_FC_BEND + 1) * kap[1], FC(BR2_FC_BEND + 2) * kap[2]};
             const double vdil = 0.5 * (Ls[s + 1] + len) * inv_rest_vlen;
@@ -229,42 +242,41 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
         // own joint: this element is rod two (own data in registers), rod one's element is in shared memory
         if (own_joint >= 0) {
             const int s1 = own_partner;
-            double Q1[9];
-#pragma unroll
-            for (int i = 0; i < 9; ++i) Q1[i] = Qs[i * T + s1];
-            double c1[3], c2[3], cd[3], vrel[3];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                c1[i] = 0.5 * (X[i * T + s1] + X[i * T + s1 + 1]);
-                c2[i] = 0.5 * (x[i] + X[i * T + s + 1]);
-                cd[i] = c2[i] - c1[i];
-                vrel[i] = 0.5 * (v[i] + Vs[i * T + s + 1]) - 0.5 * (Vs[i * T + s1] + Vs[i * T + s1 + 1]);
-            }
             const double off = JD[6 * T + s];
             const double ra1 = fma(0.5 * off, RSE[s1], Rs[s1]);   // r1 + o1
             const double ra2 = fma(0.5 * off, rs_e, rad);         // r2 + o2
-            const double jk = FC(BR2_FC_JK), jnu = FC(BR2_FC_JNU);
-            double rd1[3], rd2[3], dvec[3], Fs[3];
+            double rd1[3], rd2[3];
+            {
+                const double a0 = JD[0 * T + s] * ra1, a1 = JD[1 * T + s] * ra1, a2 = JD[2 * T + s] * ra1;
+                const double b0 = JD[3 * T + s] * ra2, b1 = JD[4 * T + s] * ra2, b2 = JD[5 * T + s] * ra2;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    rd1[i] = fma(Qs[i * T + s1], a0, fma(Qs[(3 + i) * T + s1], a1, Qs[(6 + i) * T + s1] * a2));  // Q1^T dv1 (r1 + o1)
+                    rd2[i] = fma(Q[i], b0, fma(Q[3 + i], b1, Q[6 + i] * b2));                                  // Q2^T dv2 (r2 + o2)
+                }
+            }
+            const double jk = FC(BR2_FC_JK);
+            double cd[3], dvec[3];
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                const double g1 = fma(Q1[i], JD[0 * T + s], fma(Q1[3 + i], JD[1 * T + s], Q1[6 + i] * JD[2 * T + s]));
-                const double g2 = fma(Q[i], JD[3 * T + s], fma(Q[3 + i], JD[4 * T + s], Q[6 + i] * JD[5 * T + s]));
-                rd1[i] = g1 * ra1;
-                rd2[i] = g2 * ra2;
+                const double c1 = 0.5 * (X[i * T + s1] + X[i * T + s1 + 1]);
+                const double c2 = 0.5 * (x[i] + X[i * T + s + 1]);
+                cd[i] = c2 - c1;
                 // (c2 + rd2) - (c1 + rd1), rounded to 12 decimals like np.round_(x, 12)
-                const double di = (c2[i] + rd2[i]) - (c1[i] + rd1[i]);
-                dvec[i] = rint(di * 1e12) * 1e-12;
-                Fs[i] = jk * dvec[i];
+                dvec[i] = rint(((c2 + rd2[i]) - (c1 + rd1[i])) * BR2_1E12) * BR2_1EM12;
             }
             const double dist2 = fma(dvec[0], dvec[0], fma(dvec[1], dvec[1], dvec[2] * dvec[2]));
-            double F[3] = {Fs[0], Fs[1], Fs[2]};
-            if (dist2 >= 1e-24) {
-                const double rdist = fast_rsqrt(dist2);
-                const double proj = fma(vrel[0], dvec[0], fma(vrel[1], dvec[1], vrel[2] * dvec[2])) * rdist;
-                const double coef = -jnu * proj * rdist;
+            double coef = jk;  // F = k d - nu (v_rel . d_hat) d_hat = (k - nu (v_rel . d) / |d|^2) d
+            if (dist2 >= BR2_1EM24) {
+                double proj = 0.0;
 #pragma unroll
-                for (int i = 0; i < 3; ++i) F[i] = fma(coef, dvec[i], F[i]);
+                for (int i = 0; i < 3; ++i) {
+                    const double vr = 0.5 * (v[i] + Vs[i * T + s + 1]) - 0.5 * (Vs[i * T + s1] + Vs[i * T + s1 + 1]);
+                    proj = fma(vr, dvec[i], proj);
+                }
+                coef = fma(-FC(BR2_FC_JNU) * proj, seed_rcp(dist2), jk);  // damping term ~1e-8 N: seed accuracy is ample
             }
+            double F[3] = {coef * dvec[0], coef * dvec[1], coef * dvec[2]};
             const double cn2 = fma(cd[0], cd[0], fma(cd[1], cd[1], cd[2] * cd[2]));
             const double rcn = fast_rsqrt(cn2);
             const double pen = fma(cn2, rcn, -(ra1 + ra2));
@@ -274,14 +286,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
 #pragma unroll
                 for (int i = 0; i < 3; ++i) F[i] = fma(mag, cd[i], F[i]);
             }
-            const double t1[3] = {fma(rd1[1], Fs[2], -rd1[2] * Fs[1]), fma(rd1[2], Fs[0], -rd1[0] * Fs[2]),
-                                  fma(rd1[0], Fs[1], -rd1[1] * Fs[0])};
-            const double t2[3] = {fma(rd2[2], Fs[1], -rd2[1] * Fs[2]), fma(rd2[0], Fs[2], -rd2[2] * Fs[0]),
-                                  fma(rd2[1], Fs[0], -rd2[0] * Fs[1])};
+            // torques use the spring part only: t = rd x (k d); rotate into each material frame
+            const double t1[3] = {jk * fma(rd1[1], dvec[2], -rd1[2] * dvec[1]), jk * fma(rd1[2], dvec[0], -rd1[0] * dvec[2]),
+                                  jk * fma(rd1[0], dvec[1], -rd1[1] * dvec[0])};
+            const double t2[3] = {jk * fma(rd2[2], dvec[1], -rd2[1] * dvec[2]), jk * fma(rd2[0], dvec[2], -rd2[2] * dvec[0]),
+                                  jk * fma(rd2[1], dvec[0], -rd2[0] * dvec[1])};
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 JF[i * TJ + own_joint] = 0.5 * F[i];
-                JT[i * TJ + own_joint] = fma(Q1[3 * i], t1[0], fma(Q1[3 * i + 1], t1[1], Q1[3 * i + 2] * t1[2]));
+                JT[i * TJ + own_joint] = fma(Qs[(3 * i) * T + s1], t1[0], fma(Qs[(3 * i + 1) * T + s1], t1[1], Qs[(3 * i + 2) * T + s1] * t1[2]));
                 JT[(3 + i) * TJ + own_joint] = fma(Q[3 * i], t2[0], fma(Q[3 * i + 1], t2[1], Q[3 * i + 2] * t2[2]));
             }
         }
@@ -320,12 +333,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
                     rd1[i] = g1 * ra1;
                     rd2[i] = g2 * ra2;
                     const double di = (c2[i] + rd2[i]) - (c1[i] + rd1[i]);
-                    dvec[i] = rint(di * 1e12) * 1e-12;
+                    dvec[i] = rint(di * BR2_1E12) * BR2_1EM12;
                     Fs[i] = kj * dvec[i];
                     F[i] = Fs[i];
                 }
                 const double dist2 = fma(dvec[0], dvec[0], fma(dvec[1], dvec[1], dvec[2] * dvec[2]));
-                if (dist2 >= 1e-24) {
+                if (dist2 >= BR2_1EM24) {
                     const double rdist = fast_rsqrt(dist2);
                     const double proj = fma(vrel[0], dvec[0], fma(vrel[1], dvec[1], vrel[2] * dvec[2])) * rdist;
                     const double coef = -nuj * proj * rdist;
@@ -406,7 +419,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
                 spring[1] = cd[12] * e1 + (-cd[13] * (proj * u1));
                 spring[2] = cd[12] * e2 + (-cd[13] * (proj * u2));
             }
-            const double ramp = fmin(1.0, time * tb.act_inv_ramp);
+            const double ramp = fmin(1.0, time_mid * tb.act_inv_ramp);
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 f_ext[i] = fma(FC(BR2_FC_GRAVITY + i), mass, spring[i]);
@@ -436,12 +449,17 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
             double a[3], alpha[3];
             const double c_t = FC(BR2_FC_CT);
             const double strain = dil - 1.0;
+            double damp[3];
+            damp[0] = FC(BR2_FC_CR) * exp_near_zero(strain * FC(BR2_FC_LN_CR));
+            const bool isotropic = FC(BR2_FC_LN_CR + 1) == FC(BR2_FC_LN_CR);  // I1 == I2 (round cross-section)
+            damp[1] = isotropic ? damp[0] : FC(BR2_FC_CR + 1) * exp_near_zero(strain * FC(BR2_FC_LN_CR + 1));
+            damp[2] = FC(BR2_FC_CR + 2) * exp_near_zero(strain * FC(BR2_FC_LN_CR + 2));
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 a[i] = (f_int[i] + f_ext[i]) * inv_mass;
                 v[i] = fma(dt, a[i], v[i]) * c_t;
                 alpha[i] = FC(BR2_FC_JINV + i) * (t_int[i] + t_ext[i]) * dil;
-                w[i] = fma(dt, alpha[i], w[i]) * (FC(BR2_FC_CR + i) * exp_near_zero(strain * FC(BR2_FC_LN_CR + i)));
+                w[i] = fma(dt, alpha[i], w[i]) * damp[i];
             }
             if (flags & BR2_FAST_ZERO_NODE_RATE) {
 #pragma unroll
@@ -464,43 +482,47 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
                 }
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
-                    g_a[i * np1 + k] = a[i];
-                    g_fint[i * np1 + k] = f_int[i];
-                    g_fext[i * np1 + k] = f_ext[i];
+                    G_A[i * np1 + k] = a[i];
+                    G_FINT[i * np1 + k] = f_int[i];
+                    G_FEXT[i * np1 + k] = f_ext[i];
                 }
                 if (is_elem) {
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
-                        g_alpha[i * n + k] = alpha[i];
-                        g_tint[i * n + k] = t_int[i];
-                        g_text[i * n + k] = t_ext[i];
+                        G_ALPHA[i * n + k] = alpha[i];
+                        G_TINT[i * n + k] = t_int[i];
+                        G_TEXT[i * n + k] = t_ext[i];
                     }
-                    g_len[k] = len;
-                    g_dil[k] = dil;
-                    g_rad[k] = rad;
+                    G_LEN[k] = len;
+                    G_DIL[k] = dil;
+                    G_RAD[k] = rad;
                 }
             }
         }
-        // second kinematic half step (value constraints = the pins, which never move)
+        // trailing kinematic half step of this step + (unless this is the last step of the launch)
+        // the leading half step of the next one; value constraints = the pins, which never move
         if (move_x) {
 #pragma unroll
-            for (int i = 0; i < 3; ++i) x[i] = fma(hdt, v[i], x[i]);
+            for (int i = 0; i < 3; ++i) {
+                x[i] = fma(hdt, v[i], x[i]);
+                if (!last) x[i] = fma(hdt, v[i], x[i]);
+            }
         }
-        if (spin_Q) rotate_directors(Q, hdt * w[0], hdt * w[1], hdt * w[2]);
-        time += hdt;
+        if (spin_Q) rotate_directors(Q, hdt * w[0], hdt * w[1], hdt * w[2], last ? 1.0 : 2.0);
+        time = time_mid + hdt;
     }
 
     if (valid) {
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            g_x[i * np1 + k] = x[i];
-            g_v[i * np1 + k] = v[i];
+            G_X[i * np1 + k] = x[i];
+            G_V[i * np1 + k] = v[i];
         }
         if (is_elem) {
 #pragma unroll
-            for (int i = 0; i < 9; ++i) g_Q[i * n + k] = Q[i];
+            for (int i = 0; i < 9; ++i) G_Q[i * n + k] = Q[i];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) g_w[i * n + k] = w[i];
+            for (int i = 0; i < 3; ++i) G_W[i * n + k] = w[i];
         }
     }
 #undef FC

@@ -13,48 +13,65 @@
 
 namespace br2 {
 
-// 1/x: hardware seed (MUFU.RCP64H, ~2^-20 relative) + one cubic step: err -> err^3.
-__device__ __forceinline__ double fast_rcp(double x) {
+// Literal fp64 constants live in the constant bank: a DFMA can take c[bank][offset] as an operand
+// directly, whereas a 64-bit immediate costs two extra instructions to materialise in registers.
+__constant__ double kSincC[6] = {-1.0 / 39916800.0, 1.0 / 362880.0, -1.0 / 5040.0, 1.0 / 120.0, -1.0 / 6.0, 1.0};
+__constant__ double kCoscC[6] = {-1.0 / 479001600.0, 1.0 / 3628800.0, -1.0 / 40320.0, 1.0 / 720.0, -1.0 / 24.0, 0.5};
+// theta / sin(theta) = sum_n kLogC[n] z^n with z = sin^2(theta/2):  4^n (n!)^2 / (2n+1)!
+__constant__ double kLogC[16] = {
+    1.0, 2.0 / 3.0, 8.0 / 15.0, 16.0 / 35.0, 128.0 / 315.0, 256.0 / 693.0, 1024.0 / 3003.0, 2048.0 / 6435.0,
+    32768.0 / 109395.0, 65536.0 / 230945.0, 262144.0 / 969969.0, 524288.0 / 2028117.0, 4194304.0 / 16900975.0,
+    8388608.0 / 35102025.0, 33554432.0 / 145422675.0, 67108864.0 / 300540195.0};
+__constant__ double kExpC[7] = {1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0};
+__constant__ double kMisc[8] = {1e-14, 1e-300, 1e12, 1e-12, 1e-24, 0.375, -0.5 - 1e-10, 1e-10};
+#define BR2_EPS14 kMisc[0]
+#define BR2_TINY kMisc[1]
+#define BR2_1E12 kMisc[2]
+#define BR2_1EM12 kMisc[3]
+#define BR2_1EM24 kMisc[4]
+
+// Raw hardware seeds (MUFU.RCP64H / MUFU.RSQ64H): ~2^-20 relative accuracy, for quantities that
+// multiply something tiny (damping of a joint, thinning of a 1e-8 m gap).
+__device__ __forceinline__ double seed_rcp(double x) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double e = fma(-x, y, 1.0);
-    const double c = fma(e, e, e);            // e + e^2
-    y = fma(y, c, y);                         // y (1 + e + e^2)
-    // one more linear step for full double accuracy (seed accuracy is not architecturally guaranteed)
-    const double e2 = fma(-x, y, 1.0);
-    return fma(y, e2, y);
+    return y;
 }
-
-// 1/sqrt(x) for x > 0: hardware seed (MUFU.RSQ64H) + cubic step + linear step.
-__device__ __forceinline__ double fast_rsqrt(double x) {
+__device__ __forceinline__ double seed_rsqrt(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double t = x * y;
-    double e = fma(-t, y, 1.0);               // 1 - x y^2
-    const double c = fma(0.375, e, 0.5);      // 1/2 + 3/8 e
-    t = y * e;
-    y = fma(t, c, y);                         // y (1 + e/2 + 3 e^2/8)
-    t = x * y;
-    e = fma(-t, y, 1.0);
-    return fma(0.5 * y, e, y);
+    return y;
+}
+
+// 1/x: seed + one cubic step (err -> err^3 <= 2^-60).  tests/test_gpu_math.py holds it to 4 ulp.
+__device__ __forceinline__ double fast_rcp(double x) {
+    const double y = seed_rcp(x);
+    const double e = fma(-x, y, 1.0);
+    const double c = fma(e, e, e);            // e + e^2
+    return fma(y, c, y);                      // y (1 + e + e^2)
+}
+
+// 1/sqrt(x) for x > 0: seed + one cubic step.
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    const double y = seed_rsqrt(x);
+    const double t = x * y;
+    const double e = fma(-t, y, 1.0);         // 1 - x y^2
+    const double c = fma(kMisc[5], e, 0.5);   // 1/2 + 3/8 e
+    return fma(y * e, c, y);                  // y (1 + e/2 + 3 e^2/8)
 }
 
 // sinc(theta) = sin(theta)/theta and cosc(theta) = (1 - cos(theta))/theta^2 as functions of
-// t = theta^2, for t <= 0.01 (|theta| <= 0.1 rad per half step, i.e. |omega| <= 1e4 rad/s at dt=2e-5).
+// t = theta^2, for t <= 0.01 (|theta| <= 0.1 rad per step, i.e. |omega| <= 5e3 rad/s at dt=2e-5).
 // Truncation error < 3e-18.
 __device__ __forceinline__ void sinc_cosc_small(double t, double &sinc, double &cosc) {
-    double s = -1.0 / 39916800.0;
-    s = fma(s, t, 1.0 / 362880.0);
-    s = fma(s, t, -1.0 / 5040.0);
-    s = fma(s, t, 1.0 / 120.0);
-    s = fma(s, t, -1.0 / 6.0);
-    sinc = fma(s, t, 1.0);
-    double c = -1.0 / 479001600.0;
-    c = fma(c, t, 1.0 / 3628800.0);
-    c = fma(c, t, -1.0 / 40320.0);
-    c = fma(c, t, 1.0 / 720.0);
-    c = fma(c, t, -1.0 / 24.0);
-    cosc = fma(c, t, 0.5);
+    double s = kSincC[0], c = kCoscC[0];
+#pragma unroll
+    for (int i = 1; i < 6; ++i) {
+        s = fma(s, t, kSincC[i]);
+        c = fma(c, t, kCoscC[i]);
+    }
+    sinc = s;
+    cosc = c;
 }
 
 __device__ __noinline__ void sinc_cosc_large(double t, double &sinc, double &cosc) {
@@ -65,24 +82,29 @@ __device__ __noinline__ void sinc_cosc_large(double t, double &sinc, double &cos
     cosc = (1.0 - c) / t;
 }
 
-// Row-director Rodrigues update Q <- R(u) Q with the reference's guard: the unit axis is
-// u / (|u| + 1e-14), i.e. the effective rotation vector is g u with
-// g = |u| / (|u| + 1e-14).  R = I + a K + b K^2-like terms with a = sinc * g, b = cosc * g^2:
-//   R_ii = 1 - b (u_j^2 + u_k^2),  R_ij = +-a u_k + b u_i u_j.
-__device__ __forceinline__ void rotate_directors(double (&Q)[9], double u0, double u1, double u2) {
+// Row-director Rodrigues update for `mult` consecutive kinematic half steps with the same rotation
+// vector u = (dt/2) omega (mult = 1 or 2).  One half step of the reference uses
+// the unit axis u / (|u| + 1e-14), i.e. rotates by g |u| with g = |u| / (|u| + 1e-14); omega does not
+// change between the trailing half step of one step and the leading half step of the next, so the two
+// rotations share their axis and compose to one rotation by phi = 2 g |u| (applied as ONE matrix).
+//   R = I + (sin phi / |u|) K(u) + ((1 - cos phi) / |u|^2) (u u^T - |u|^2 I)
+//   sin phi / |u| = sinc(phi) m,   (1 - cos phi) / |u|^2 = cosc(phi) m^2,   m = mult * g.
+__device__ __forceinline__ void rotate_directors(double (&Q)[9], double u0, double u1, double u2, double mult) {
     const double t = fma(u0, u0, fma(u1, u1, u2 * u2));
-    const double tt = t + 1e-300;                 // keeps rsqrt finite for a resting element
+    const double tt = t + BR2_TINY;                 // keeps rsqrt finite for a resting element
     const double rs = fast_rsqrt(tt);
     const double theta = tt * rs;
-    const double g = theta * fast_rcp(theta + 1e-14);
+    const double m = mult * theta * fast_rcp(theta + BR2_EPS14);
+    const double m2 = m * m;
+    const double tphi = m2 * t;                   // phi^2
     double sinc, cosc;
-    if (t <= 0.01) {
-        sinc_cosc_small(t, sinc, cosc);
+    if (tphi <= 0.01) {
+        sinc_cosc_small(tphi, sinc, cosc);
     } else {
-        sinc_cosc_large(t, sinc, cosc);
+        sinc_cosc_large(tphi, sinc, cosc);
     }
-    const double a = sinc * g;
-    const double b = cosc * g * g;
+    const double a = sinc * m;
+    const double b = cosc * m2;
     const double a0 = a * u0, a1 = a * u1, a2 = a * u2;
     const double b0 = b * u0, b1 = b * u1, b2 = b * u2;
     const double R00 = fma(-b1, u1, fma(-b2, u2, 1.0));
@@ -92,41 +114,33 @@ __device__ __forceinline__ void rotate_directors(double (&Q)[9], double u0, doub
     const double R02 = fma(b0, u2, -a1), R20 = fma(b0, u2, a1);
     const double R12 = fma(b1, u2, a0), R21 = fma(b1, u2, -a0);
 #pragma unroll
-    for (int m = 0; m < 3; ++m) {
-        const double q0 = Q[m], q1 = Q[3 + m], q2 = Q[6 + m];
-        Q[m] = fma(R00, q0, fma(R01, q1, R02 * q2));
-        Q[3 + m] = fma(R10, q0, fma(R11, q1, R12 * q2));
-        Q[6 + m] = fma(R20, q0, fma(R21, q1, R22 * q2));
+    for (int c = 0; c < 3; ++c) {
+        const double q0 = Q[c], q1 = Q[3 + c], q2 = Q[6 + c];
+        Q[c] = fma(R00, q0, fma(R01, q1, R02 * q2));
+        Q[3 + c] = fma(R10, q0, fma(R11, q1, R12 * q2));
+        Q[6 + c] = fma(R20, q0, fma(R21, q1, R22 * q2));
     }
 }
 
 // Log-map scale of the rod curvature:
 //     theta = arccos(c),  scale = -0.5 * theta / sin(theta + 1e-14),   c = 0.5 tr - 0.5 - 1e-10.
-// With y = 1 - c = 2 sin^2(theta/2) and z = y/2:
-//     theta / sin(theta) = P(z) / sqrt(1 - z),   P(z) = asin(sqrt z)/sqrt z = sum_n c_n z^n,
-// and the +1e-14 guard enters to first order as 1 / (1 + 1e-14 cos/sin).  Valid for z <= 1/16
-// (relative rotation of neighbouring elements <= 0.505 rad); truncation error < 3e-17.
+// With y = 1 - c = 2 sin^2(theta/2) and z = y/2:  theta / sin(theta) = sum_n kLogC[n] z^n (Estrin scheme,
+// degree 15, truncation < 2e-18 for z <= 1/16, i.e. neighbouring elements rotated by <= 0.505 rad), and the
+// +1e-14 guard enters to first order as the factor 1 - 1e-14 cos(theta)/sin(theta); 1/sin(theta) =
+// 1/(2 sqrt(z (1 - z))) only needs the hardware seed's accuracy there (the factor differs from 1 by < 1e-9).
 __device__ __forceinline__ double logmap_scale_small(double y) {
     const double z = 0.5 * y;
-    double p = 0.0073125258735988454;
-    p = fma(p, z, 0.008390335809616815);
-    p = fma(p, z, 0.009761609529194078);
-    p = fma(p, z, 0.011551800896139705);
-    p = fma(p, z, 0.01396484375);
-    p = fma(p, z, 0.017352764423076924);
-    p = fma(p, z, 0.022372159090909092);
-    p = fma(p, z, 0.030381944444444444);
-    p = fma(p, z, 0.044642857142857144);
-    p = fma(p, z, 0.075);
-    p = fma(p, z, 1.0 / 6.0);
-    p = fma(p, z, 1.0);
-    const double omz = 1.0 - z;
-    const double r1 = fast_rsqrt(omz);             // 1/sqrt(1-z) = 1/cos(theta/2)
-    const double rz = fast_rsqrt(z);               // 1/sin(theta/2)
-    const double inv_sin = 0.5 * r1 * rz;          // 1/sin(theta)
-    const double cosv = 1.0 - y;
-    const double guard = fma(-1e-14 * cosv, inv_sin, 1.0);   // 1/(1 + eps cot) to first order
-    return -0.5 * p * r1 * guard;
+    const double z2 = z * z, z4 = z2 * z2, z8 = z4 * z4;
+    const double p01 = fma(kLogC[1], z, kLogC[0]), p23 = fma(kLogC[3], z, kLogC[2]);
+    const double p45 = fma(kLogC[5], z, kLogC[4]), p67 = fma(kLogC[7], z, kLogC[6]);
+    const double p89 = fma(kLogC[9], z, kLogC[8]), pab = fma(kLogC[11], z, kLogC[10]);
+    const double pcd = fma(kLogC[13], z, kLogC[12]), pef = fma(kLogC[15], z, kLogC[14]);
+    const double q0 = fma(p23, z2, p01), q1 = fma(p67, z2, p45), q2 = fma(pab, z2, p89), q3 = fma(pef, z2, pcd);
+    const double r0 = fma(q1, z4, q0), r1 = fma(q3, z4, q2);
+    const double f = fma(r1, z8, r0);                          // theta / sin(theta)
+    const double inv_sin = 0.5 * seed_rsqrt(z * (1.0 - z));    // 1 / sin(theta), ~2^-20 relative
+    const double guard = fma(-BR2_EPS14 * (1.0 - y), inv_sin, 1.0);
+    return -0.5 * f * guard;
 }
 
 __device__ __noinline__ double logmap_scale_large(double c) {
@@ -140,15 +154,11 @@ __device__ __forceinline__ double logmap_scale(double c) {
     return logmap_scale_large(c);
 }
 
-// exp(d) for |d| <= 0.02 (damper: exp(e ln c) = c * exp((e - 1) ln c)); truncation error < 3e-16 * 1e-0.
+// exp(d) for |d| <= 0.02 (damper: exp(e ln c) = c * exp((e - 1) ln c)); degree-7 Taylor, truncation < 1e-18.
 __device__ __forceinline__ double exp_small(double d) {
-    double p = 1.0 / 5040.0;
-    p = fma(p, d, 1.0 / 720.0);
-    p = fma(p, d, 1.0 / 120.0);
-    p = fma(p, d, 1.0 / 24.0);
-    p = fma(p, d, 1.0 / 6.0);
-    p = fma(p, d, 0.5);
-    p = fma(p, d, 1.0);
+    double p = kExpC[0];
+#pragma unroll
+    for (int i = 1; i < 7; ++i) p = fma(p, d, kExpC[i]);
     return fma(p, d, 1.0);
 }
 
