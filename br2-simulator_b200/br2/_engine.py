@@ -110,6 +110,12 @@ class Engine:
         info["variant_name"] = ("generic", "fast", "fast-uniform")[info["variant"]]
         return info
 
+    def replay_count(self):
+        """Instance-launches redone by the exact-path kernel behind the fast one (synchronises)."""
+        count = ctypes.c_int64(0)
+        _native.check(self.lib.br2_replay_count(self.handle, ctypes.byref(count)))
+        return count.value
+
     def select_kernel(self, variant):
         """0 generic, 1 fast (per-slot constants), 2 fast (uniform constants), -1 automatic."""
         _native.check(self.lib.br2_select_kernel(self.handle, int(variant)))

@@ -30,7 +30,7 @@ J_NI, J_ND = 8, 10
 ROD_HAS_DAMPER = 1
 MAX_SLOTS = 1024
 # fast-path tables (include/br2cuda.h)
-FAST_NI, FAST_NODE_ITEMS = 16, 8
+FAST_NI, FAST_NODE_ITEMS, FAST_MAX_EXTRA, FAST_EXTRA_ID = 18, 8, 64, 16
 FAST_FLAGS, FAST_OWN_JOINT, FAST_EXTRA_JOINT, FAST_SOFTFIX_ROW, FAST_ACT_BEGIN, FAST_ACT_END = 0, 1, 2, 3, 4, 5
 FAST_ELEM_ITEM0, FAST_NODE_ITEM0 = 6, 8
 PIN_DIRECTOR, PIN_POSITION, ZERO_NODE_RATE, ZERO_ELEM_RATE, ZERO_REPORTED = 1, 2, 4, 8, 16
@@ -370,13 +370,19 @@ def _lower_fast(ctx, rods, rod_i, slot_c, rod_d, forcing_rows, cons_rows, node_l
                 fast_c[FC_PIN + 3:FC_PIN + 12, s0 + n - 1] = row[3:12]
 
     # ---- joints -------------------------------------------------------------------------------
-    NJ = len(ctx.joints)
+    # "own" joints: surface joints whose rod-two element evaluates them; each element may be rod two of
+    # one and rod one of one such joint (the BR2 ring) -- their forces / torques are gathered implicitly.
+    # Everything else (tip-to-base joints, surface joints outside that pattern) is an "extra" joint with
+    # a compact id, spread over the threads, gathered through short per-slot lists.
     extra = []
     jparams = None
+    is_rod_one = np.zeros(S, dtype=bool)
     for j, (kind, s1, s2, q1, q2, row, torque) in enumerate(ctx.joints):
-        ownable = (kind == JOINT_SURFACE and q1 == s1 and q2 == s2 and fast_i[s2, FAST_OWN_JOINT] < 0 and s1 != s2)
+        ownable = (kind == JOINT_SURFACE and q1 == s1 and q2 == s2 and s1 != s2
+                   and fast_i[s2, FAST_OWN_JOINT] < 0 and not is_rod_one[s1])
         if ownable:
             fast_i[s2, FAST_OWN_JOINT] = j
+            is_rod_one[s1] = True
             fast_c[FC_JK, s2], fast_c[FC_JNU, s2], fast_c[FC_JKREP, s2] = row[0], row[1], row[2]
             jparams = (row[0], row[1], row[2]) if jparams is None else jparams
         else:
@@ -384,24 +390,33 @@ def _lower_fast(ctx, rods, rod_i, slot_c, rod_d, forcing_rows, cons_rows, node_l
     if jparams is not None:  # slots without an own joint copy the common parameters (keeps uniformity)
         none = fast_i[:, FAST_OWN_JOINT] < 0
         fast_c[FC_JK, none], fast_c[FC_JNU, none], fast_c[FC_JKREP, none] = jparams
-    # spread the remaining joints over threads that have no second joint yet, one warp after another
+    if len(extra) > FAST_MAX_EXTRA:
+        return refuse("more than %d joints outside the ring pattern" % FAST_MAX_EXTRA)
+    # spread the extra joints over the threads, one warp after another
     warps = (S + 31) // 32
     candidates = [w * 32 + lane for lane in range(32) for w in range(warps) if w * 32 + lane < S]
-    if len(extra) > len(candidates):
-        return refuse("more joints than threads")
-    for j, slot in zip(extra, candidates):
+    extra_id = {}
+    for xid, (j, slot) in enumerate(zip(extra, candidates)):
         fast_i[slot, FAST_EXTRA_JOINT] = j
+        fast_i[slot, FAST_EXTRA_ID] = xid
+        extra_id[j] = xid
+    x_node = [[] for _ in range(S)]
+    x_elem = [[] for _ in range(S)]
+    for j in extra:
+        kind, s1, s2, q1, q2, row, torque = ctx.joints[j]
+        xid = extra_id[j]
+        for slot, sign in ((s1, 0), (s1 + 1, 0), (s2, 1), (s2 + 1, 1)):
+            x_node[slot].append((xid << 1) | sign)
+        if torque:
+            x_elem[s1].append((xid << 1) | 0)
+            x_elem[s2].append((xid << 1) | 1)
     for slot in range(S):
-        if len(node_lists[slot]) > FAST_NODE_ITEMS:
-            return refuse("a node receives more than %d joint forces" % FAST_NODE_ITEMS)
-        if len(elem_lists[slot]) > 2:
-            return refuse("an element receives more than 2 joint torques")
-        if any(item >= 0xFFFF for item in node_lists[slot]):
-            return refuse("too many joints for 16-bit gather items")
-        fast_i[slot, FAST_NODE_ITEM0:FAST_NODE_ITEM0 + len(node_lists[slot])] = node_lists[slot]
-        fast_i[slot, FAST_ELEM_ITEM0:FAST_ELEM_ITEM0 + len(elem_lists[slot])] = elem_lists[slot]
-    if NJ > S + 64:
-        return refuse("joint rows exceed the fast kernel's buffer")
+        if len(x_node[slot]) > FAST_NODE_ITEMS:
+            return refuse("a node receives more than %d extra joint forces" % FAST_NODE_ITEMS)
+        if len(x_elem[slot]) > 2:
+            return refuse("an element receives more than 2 extra joint torques")
+        fast_i[slot, FAST_NODE_ITEM0:FAST_NODE_ITEM0 + len(x_node[slot])] = x_node[slot]
+        fast_i[slot, FAST_ELEM_ITEM0:FAST_ELEM_ITEM0 + len(x_elem[slot])] = x_elem[slot]
 
     # ---- uniformity: every slot's element constants equal slot 0's (kernel then uses the constant bank)
     ref = fast_c[:FC_PIN, :1]

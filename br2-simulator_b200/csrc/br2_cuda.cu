@@ -101,10 +101,15 @@ struct br2_handle_s {
     long long batch = 0;
     KernelChoice kernel{};
     size_t smem_bytes = 0;
+    KernelChoice replay{};  // generic kernel used behind the fast one
+    size_t replay_smem = 0;
     int variant = 0;        // 0 generic, 1 fast, 2 fast uniform
     int auto_variant = 0;   // what br2_create picked
     bool fast_ok = false, fast_uniform = false;
     double uni[BR2_FC_COUNT] = {0};
+    int *status = nullptr;            // [batch] fast-kernel validity flags (library-owned)
+    long long status_batch = 0;
+    unsigned long long *replays = nullptr;  // device counter
     double *scratch_state = nullptr;  // br2_step_host
     double *scratch_pressures = nullptr;
     long long scratch_batch = 0;
@@ -208,7 +213,7 @@ int br2_create(const br2_program *p, int device, br2_handle *out) {
     UP(elem_ptr, S + 1);
     UP(elem_items, (size_t)p->elem_ptr[S]);
     UP(overwrite_src, S);
-    h->fast_ok = p->fast_ok != 0 && p->fast_i && p->fast_c && p->n_joints <= p->n_slots + 64;
+    h->fast_ok = p->fast_ok != 0 && p->fast_i && p->fast_c;
     h->fast_uniform = h->fast_ok && p->fast_uniform != 0;
     if (h->fast_ok) {
         UP(fast_i, S * BR2_FAST_NI);
@@ -219,6 +224,14 @@ int br2_create(const br2_program *p, int device, br2_handle *out) {
         for (int i = 0; i < BR2_FC_COUNT; ++i) h->uni[i] = p->fast_c[(size_t)i * S];  // slot 0's column
     }
 #undef UP
+    {
+        cudaError_t e = cudaMalloc((void **)&h->replays, sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMemset(h->replays, 0, sizeof(unsigned long long));
+        if (e != cudaSuccess) {
+            br2_destroy(h);
+            return fail(BR2_ECUDA, std::string("replay counter: ") + cudaGetErrorString(e));
+        }
+    }
     h->auto_variant = h->fast_ok ? (h->fast_uniform ? 2 : 1) : 0;
     rc = br2_select_kernel(h, -1);
     if (rc != BR2_OK) {
@@ -248,13 +261,24 @@ int br2_select_kernel(br2_handle h, int32_t variant) {
     if (variant == 0)
         smem = sizeof(double) * (30 * S + 9 * (size_t)h->t.n_joints + 32);
     else
-        smem = sizeof(double) * (40 * (size_t)pick.threads + 9 * (size_t)(pick.threads + 64));
+        smem = sizeof(double) * (46 * (size_t)pick.threads + 9 * (size_t)(pick.threads + 8) + 9 * (size_t)BR2_FAST_MAX_EXTRA);
     if (smem > 227 * 1024)
         return fail(BR2_ELIMIT, "assembly needs " + std::to_string(smem) + " B of shared memory per CTA (max 232448)");
     CUDA_TRY(cudaFuncSetAttribute((const void *)pick.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     h->kernel = pick;
     h->smem_bytes = smem;
     h->variant = variant;
+    if (variant != 0) {
+        for (const KernelChoice &kc : kKernels[0])
+            if (kc.threads >= h->t.n_slots) {
+                h->replay = kc;
+                break;
+            }
+        h->replay_smem = sizeof(double) * (30 * S + 9 * (size_t)h->t.n_joints + 32);
+        if (h->replay_smem > 227 * 1024) return fail(BR2_ELIMIT, "assembly too large for the replay kernel");
+        CUDA_TRY(cudaFuncSetAttribute((const void *)h->replay.fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)h->replay_smem));
+    }
     return BR2_OK;
 }
 
@@ -262,6 +286,8 @@ int br2_destroy(br2_handle h) {
     if (!h) return BR2_OK;
     cudaSetDevice(h->device);
     for (void *d : h->owned) cudaFree(d);
+    if (h->status) cudaFree(h->status);
+    if (h->replays) cudaFree(h->replays);
     if (h->scratch_state) cudaFree(h->scratch_state);
     if (h->scratch_pressures) cudaFree(h->scratch_pressures);
     delete h;
@@ -274,6 +300,14 @@ int br2_bind_state(br2_handle h, double *dev_state, int64_t batch) {
     if (!h || !dev_state || batch <= 0) return fail(BR2_EINVAL, "br2_bind_state: bad argument");
     h->state = dev_state;
     h->batch = batch;
+    if (h->status_batch < batch) {
+        CUDA_TRY(cudaSetDevice(h->device));
+        if (h->status) cudaFree(h->status);
+        h->status = nullptr;
+        CUDA_TRY(cudaMalloc((void **)&h->status, sizeof(int) * (size_t)batch));
+        h->status_batch = batch;
+    }
+    CUDA_TRY(cudaMemset(h->status, 0, sizeof(int) * (size_t)batch));
     return BR2_OK;
 }
 
@@ -322,9 +356,18 @@ int br2_step(br2_handle h, int64_t n_steps, double t0, double dt, void *stream, 
     sp.t0 = t0;
     sp.dt = dt;
     memcpy(sp.uni, h->uni, sizeof(sp.uni));
+    sp.status = h->status;
+    sp.replays = h->replays;
+    sp.only_flagged = 0;
     void *args[] = {&sp};
     CUDA_TRY(cudaLaunchKernel((const void *)h->kernel.fn, dim3((unsigned)h->batch), dim3((unsigned)h->kernel.threads), args,
                               h->smem_bytes, (cudaStream_t)stream));
+    if (h->variant != 0) {
+        // exact-path replay, stream-ordered behind the fast kernel: CTAs of unflagged instances exit at once
+        sp.only_flagged = 1;
+        CUDA_TRY(cudaLaunchKernel((const void *)h->replay.fn, dim3((unsigned)h->batch), dim3((unsigned)h->replay.threads),
+                                  args, h->replay_smem, (cudaStream_t)stream));
+    }
     return BR2_OK;
 }
 
@@ -347,6 +390,13 @@ int br2_step_host(br2_handle h, double *host_state, const double *host_pressures
         if (!host_pressures) return fail(BR2_EINVAL, "br2_step_host: NULL pressures");
         CUDA_TRY(cudaMemcpy(h->scratch_pressures, host_pressures, sizeof(double) * (size_t)batch * (size_t)h->t.n_actions,
                             cudaMemcpyHostToDevice));
+    }
+    if (h->status_batch < batch) {
+        if (h->status) cudaFree(h->status);
+        h->status = nullptr;
+        CUDA_TRY(cudaMalloc((void **)&h->status, sizeof(int) * (size_t)batch));
+        h->status_batch = batch;
+        CUDA_TRY(cudaMemset(h->status, 0, sizeof(int) * (size_t)batch));
     }
     double *saved_state = h->state;
     const double *saved_p = h->pressures;
@@ -380,6 +430,15 @@ int br2_kernel_info(br2_handle h, int32_t *regs, int32_t *smem_bytes, int32_t *t
     if (blocks_per_sm) *blocks_per_sm = blocks;
     if (sm_count) *sm_count = sms;
     if (variant) *variant = h->variant;
+    return BR2_OK;
+}
+
+int br2_replay_count(br2_handle h, int64_t *count) {
+    if (!h || !count) return fail(BR2_EINVAL, "br2_replay_count: bad argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    unsigned long long v = 0;
+    CUDA_TRY(cudaMemcpy(&v, h->replays, sizeof(v), cudaMemcpyDeviceToHost));  // synchronises with prior work
+    *count = (int64_t)v;
     return BR2_OK;
 }
 

@@ -3,14 +3,19 @@
 // between parallel rods, tip-to-base joints between segments).
 //
 // Same phase structure and semantics as the generic kernel (br2_generic.cuh), but
-//   * no table walking inside the step loop: each thread's share of the operator tables (its joint, its
-//     gather lists, its actuation torque, its constraint flags) is decoded once per launch into
-//     registers / shared memory;
-//   * shared-memory exchange arrays have compile-time strides (no address arithmetic);
-//   * reciprocals instead of divisions, hardware-seeded rsqrt, short series for the tiny-angle
-//     transcendentals (br2_math.cuh), each with a libm slow path behind a never-taken-in-practice branch;
-//   * per-element constants come from the constant bank when every element of the assembly shares them
-//     (kUniform; the case for all BR2 sample assemblies), else from L1-cached global memory.
+//   * straight-line code: no table walking and (almost) no branches inside the step loop -- each thread's
+//     share of the operator tables is decoded once per launch, masks replace `if`s, so the compiler can
+//     interleave the many short dependent fp64 chains of a step;
+//   * optimistic math: reciprocals instead of divisions, hardware-seeded rsqrt, short series for the
+//     tiny-angle transcendentals (br2_math.cuh).  Every series has a validity range; a thread that leaves
+//     it raises the instance's flag in `status`, the CTA then does NOT write its state back, and the
+//     generic kernel -- launched right behind this one on the same stream in "flagged instances only"
+//     mode -- redoes the launch for that instance with libm.  Results are therefore always exact-path
+//     results; the flag costs nothing when it is not raised (never, for physically sensible motion);
+//   * shared-memory exchange arrays with compile-time strides; per-element constants from the constant
+//     bank when every element of the assembly shares them (kUniform), else from L1-cached global memory;
+//   * the trailing kinematic half step of one step and the leading one of the next share omega and are
+//     applied as ONE rotation.
 #pragma once
 
 #include "br2_math.cuh"
@@ -21,7 +26,8 @@ namespace br2 {
 template <int kThreads, int kMinBlocks, bool kUniform>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(const __grid_constant__ StepParams p) {
     constexpr int T = kThreads;
-    constexpr int TJ = kThreads + 64;  // joint rows (ring joints <= element slots, plus tip-to-base joints)
+    constexpr int TP = kThreads + 8;   // stride of the per-element joint accumulators; slot T is a trash row
+    constexpr int TJ = BR2_FAST_MAX_EXTRA;  // rows for "extra" joints (tip-to-base, or surface joints without an owner)
     extern __shared__ double sm[];
     double *X = sm;               // [3][T] node position
     double *Vs = X + 3 * T;       // [3][T] node velocity
@@ -35,13 +41,19 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
     double *Cv = Av + 3 * T;      // [3][T] (kappa x tau_L) D / E^3
     double *JD = Cv + 3 * T;      // [7][T] own joint: dv1[3], dv2[3], offset
     double *TA = JD + 7 * T;      // [3][T] actuation torque at full ramp
-    double *JF = TA + 3 * T;      // [3][TJ] half of the joint force
-    double *JT = JF + 3 * TJ;     // [2][3][TJ] joint torque on rod one / rod two (material frame)
+    double *LT = TA + 3 * T;      // [3][T] thread-private stash: shear couple + transport terms (P2 -> P4)
+    double *TO = LT + 3 * T;      // [3][T] thread-private stash: torque of my joint on my element (P3 -> P4)
+    double *EFo = TO + 3 * T;     // [3][TP] -F/2 of the joint this element owns (it is rod two)
+    double *EFp = EFo + 3 * TP;   // [3][TP] +F/2 of the joint in which this element is rod one
+    double *TQp = EFp + 3 * TP;   // [3][TP] torque of that joint on this element (rod one side)
+    double *JF = TQp + 3 * TP;    // [3][TJ] half force of extra joints
+    double *JT = JF + 3 * TJ;     // [2][3][TJ] torques of extra joints (rod one / rod two)
 
     const DevTables &tb = p.t;
     const int S = tb.n_slots;
     const int s = threadIdx.x;
     const long long b = blockIdx.x;
+    if (p.status[b] != 0) return;  // already waiting for the exact-path replay (whole CTA, before any barrier)
     const bool valid = s < S;
     const int sc = valid ? s : S - 1;
 
@@ -51,24 +63,20 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
     const int k = sc - ri[BR2_ROD_SLOT0];
     const bool is_elem = valid && (k < n);
     const bool is_vor = valid && (k < n - 1);
+    const bool first = (k == 0);
 
     const int *fi = tb.fast_i + sc * BR2_FAST_NI;
     const int flags = valid ? fi[BR2_FAST_FLAGS] : 0;
     const int own_joint = valid ? fi[BR2_FAST_OWN_JOINT] : -1;
     const int extra_joint = valid ? fi[BR2_FAST_EXTRA_JOINT] : -1;
+    const int extra_row = fi[BR2_FAST_EXTRA_ID];   // compact row of that joint in JF / JT
     const int softfix_row = valid ? fi[BR2_FAST_SOFTFIX_ROW] : -1;
-    const int elem_item0 = fi[BR2_FAST_ELEM_ITEM0], elem_item1 = fi[BR2_FAST_ELEM_ITEM0 + 1];
-    unsigned node_items[BR2_FAST_NODE_ITEMS / 2];
-    int node_count = 0;
-#pragma unroll
-    for (int q = 0; q < BR2_FAST_NODE_ITEMS; q += 2) {
-        const int i0 = fi[BR2_FAST_NODE_ITEM0 + q], i1 = fi[BR2_FAST_NODE_ITEM0 + q + 1];
-        node_items[q / 2] = (unsigned)(i0 & 0xFFFF) | ((unsigned)(i1 & 0xFFFF) << 16);
-        node_count += (i0 >= 0) + (i1 >= 0);
-    }
-    if (!valid) node_count = 0;
     const int ow_src = valid ? tb.overwrite_src[sc] : -1;
-    const int own_partner = (own_joint >= 0) ? tb.joint_i[own_joint * BR2_J_NI + BR2_J_S1] : 0;
+    // a thread without a joint evaluates a dummy one against itself and dumps the result in the trash row
+    const bool has_joint = own_joint >= 0;
+    const int s1 = has_joint ? tb.joint_i[own_joint * BR2_J_NI + BR2_J_S1] : ((s + 1 < T) ? s : s - 1);
+    const int jdst = has_joint ? s1 : T;   // where the rod-one side of my joint accumulates
+    const int odst = has_joint ? s : T;    // where my own (rod-two) side accumulates
 
     // ---- per-slot constants ---------------------------------------------------------------
     const double *FCg = tb.fast_c + sc;
@@ -76,11 +84,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
     const double mass = tb.slot_c[(long long)BR2_SC_MASS * S + sc];
     const double inv_mass = 1.0 / mass;
 
-    // own joint descriptor and actuation torque -> shared memory (read every step, written once)
+    // joint descriptor, actuation torque, accumulators -> shared memory (written once per launch)
     {
-        const double *jd = tb.joint_d + (own_joint >= 0 ? own_joint : 0) * BR2_J_ND;
+        const double *jd = tb.joint_d + (has_joint ? own_joint : 0) * BR2_J_ND;
 #pragma unroll
-        for (int i = 0; i < 7; ++i) JD[i * T + s] = (own_joint >= 0) ? jd[3 + i] : 0.0;
+        for (int i = 0; i < 7; ++i) JD[i * T + s] = has_joint ? jd[3 + i] : 0.0;
         double ta[3] = {0.0, 0.0, 0.0};
         if (valid) {
             for (int r = fi[BR2_FAST_ACT_BEGIN]; r < fi[BR2_FAST_ACT_END]; ++r) {
@@ -91,8 +99,21 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
         }
 #pragma unroll
         for (int i = 0; i < 3; ++i) TA[i * T + s] = ta[i];
+        for (int j = s; j < 9 * TP + 9 * TJ; j += T) EFo[j] = 0.0;  // EFo, EFp, TQp, JF, JT are contiguous
     }
-    const bool has_overwrite = (tb.n_joints > 0) && (__syncthreads_or(ow_src >= 0) != 0);
+    // extra-joint gather lists (tip-to-base joints etc.): rare, kept as (count, packed items)
+    unsigned x_node_items[BR2_FAST_NODE_ITEMS / 2];
+    int x_node_count = 0;
+#pragma unroll
+    for (int q = 0; q < BR2_FAST_NODE_ITEMS; q += 2) {
+        const int i0 = fi[BR2_FAST_NODE_ITEM0 + q], i1 = fi[BR2_FAST_NODE_ITEM0 + q + 1];
+        x_node_items[q / 2] = (unsigned)(i0 & 0xFFFF) | ((unsigned)(i1 & 0xFFFF) << 16);
+        x_node_count += (i0 >= 0) + (i1 >= 0);
+    }
+    if (!valid) x_node_count = 0;
+    const int x_elem_item0 = valid ? fi[BR2_FAST_ELEM_ITEM0] : -1, x_elem_item1 = valid ? fi[BR2_FAST_ELEM_ITEM0 + 1] : -1;
+    const bool any_extra =
+        __syncthreads_or((extra_joint >= 0) | (ow_src >= 0) | (x_node_count > 0) | (x_elem_item0 >= 0)) != 0;
 
     // ---- state in registers -------------------------------------------------------------
     // field offsets inside the rod's block (include/br2cuda.h), derived where needed from n
@@ -130,20 +151,26 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
 #pragma unroll
         for (int i = 0; i < 9; ++i) Q[i] = FCg[(long long)(BR2_FC_PIN + 3 + i) * S];
     }
-    const bool move_x = !(flags & BR2_FAST_PIN_POSITION);
-    const bool spin_Q = is_elem && !(flags & BR2_FAST_PIN_DIRECTOR);
-
     const double dt = p.dt, hdt = 0.5 * p.dt;
+    // masks instead of branches: a pinned node does not translate, a pinned / absent element does not rotate,
+    // constrained rates are multiplied by zero
+    const double hx = (flags & BR2_FAST_PIN_POSITION) ? 0.0 : hdt;
+    const double hq = (is_elem && !(flags & BR2_FAST_PIN_DIRECTOR)) ? hdt : 0.0;
+    const double keep_v = (flags & BR2_FAST_ZERO_NODE_RATE) ? 0.0 : 1.0;
+    const double keep_w = (flags & BR2_FAST_ZERO_ELEM_RATE) ? 0.0 : 1.0;
+    const double elem_mask = is_elem ? 1.0 : 0.0, vor_mask = is_vor ? 1.0 : 0.0, prev_mask = first ? 0.0 : 1.0;
+    const int sp = first ? s : s - 1;            // previous slot of the same rod (masked out on the first node)
+    const int sn = (s + 1 < T) ? s + 1 : s;      // next slot (the block's last thread reads itself; result masked)
+
     double time = p.t0;  // time at the start of the current step
     const long long last_step = p.n_steps - 1;
+    bool bad = false;    // some series left its validity range (or produced a NaN)
 
     // leading kinematic half step of the first step; every later one is fused with the trailing half
     // step of the step before it (same velocities, same omega)
-    if (move_x) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) x[i] = fma(hdt, v[i], x[i]);
-    }
-    if (spin_Q) rotate_directors(Q, hdt * w[0], hdt * w[1], hdt * w[2], 1.0);
+    for (int i = 0; i < 3; ++i) x[i] = fma(hx, v[i], x[i]);
+    bad |= rotate_directors(Q, hq * w[0], hq * w[1], hq * w[2], 1.0);
 
     for (long long step = 0; step < p.n_steps; ++step) {
         const bool last = (step == last_step);
@@ -156,41 +183,41 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
         }
 #pragma unroll
         for (int i = 0; i < 9; ++i) Qs[i * T + s] = Q[i];
-        if (has_overwrite) {
+        if (any_extra) {
 #pragma unroll
             for (int i = 0; i < 3; ++i) Ws[i * T + s] = w[i];
         }
         __syncthreads();
 
-        // =============================== P2: element quantities =============================
-        double len = 1.0, rad = 1.0, dil = 1.0, rs_e = 1.0;
-        double sk[3] = {0, 0, 0}, local_t[3] = {0, 0, 0};
-        if (is_elem) {
-            double d[3], dv[3];
+        // =============================== P2: element quantities (all threads; masked) =======
+        {
+        double d[3], dv[3];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                d[i] = X[i * T + s + 1] - x[i];
-                dv[i] = Vs[i * T + s + 1] - v[i];
-            }
-            const double d2 = fma(d[0], d[0], fma(d[1], d[1], d[2] * d[2]));
-            const double rs = fast_rsqrt(d2);
-            len = fma(d2, rs, BR2_EPS14);
-            const double inv_len = rs * fma(-BR2_EPS14, rs, 1.0);  // 1/(|d| + 1e-14), second order 1e-23
-            const double rest_len = FC(BR2_FC_REST_LEN), inv_rest_len = FC(BR2_FC_INV_REST_LEN);
-            const double r2 = FC(BR2_FC_VOL_OVER_PI) * inv_len;
-            rad = r2 * fast_rsqrt(r2);
-            dil = len * inv_rest_len;
-            const double inv_dil = rest_len * inv_len;
-            rs_e = seed_rsqrt(dil);  // only thins the ~1e-8 m rest gap of a joint: 2^-20 relative is ample
-            double qt[3], nL[3];
+        for (int i = 0; i < 3; ++i) {
+            d[i] = X[i * T + sn] - x[i];
+            dv[i] = Vs[i * T + sn] - v[i];
+        }
+        const double d2 = fma(d[0], d[0], fma(d[1], d[1], d[2] * d[2])) + (1.0 - elem_mask);  // keeps non-elements finite
+        const double rs = fast_rsqrt(d2);
+        const double len = fma(d2, rs, BR2_EPS14);
+        const double inv_len = rs * fma(-BR2_EPS14, rs, 1.0);  // 1/(|d| + 1e-14), second order 1e-23
+        const double rest_len = FC(BR2_FC_REST_LEN), inv_rest_len = FC(BR2_FC_INV_REST_LEN);
+        const double r2 = FC(BR2_FC_VOL_OVER_PI) * inv_len;
+        const double rad = r2 * fast_rsqrt(r2);
+        const double dil = len * inv_rest_len;
+        const double inv_dil = rest_len * inv_len;
+        const double rs_e = seed_rsqrt(dil);  // only thins the ~1e-8 m rest gap of a joint: 2^-20 relative is ample
+        double qt[3], nL[3], sk[3], local_t[3];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                qt[i] = fma(Q[3 * i], d[0], fma(Q[3 * i + 1], d[1], Q[3 * i + 2] * d[2])) * inv_len;
-                const double sigma = fma(dil, qt[i], (i == 2) ? -1.0 : 0.0);
-                nL[i] = FC(BR2_FC_SHEAR + i) * sigma;
-            }
+        for (int i = 0; i < 3; ++i) {
+            qt[i] = fma(Q[3 * i], d[0], fma(Q[3 * i + 1], d[1], Q[3 * i + 2] * d[2])) * inv_len;
+            const double sigma = fma(dil, qt[i], (i == 2) ? -1.0 : 0.0);
+            nL[i] = FC(BR2_FC_SHEAR + i) * sigma;
+        }
+        const double sk_scale = inv_dil * elem_mask;
 #pragma unroll
-            for (int i = 0; i < 3; ++i) sk[i] = fma(Q[i], nL[0], fma(Q[3 + i], nL[1], Q[6 + i] * nL[2])) * inv_dil;
+        for (int i = 0; i < 3; ++i) sk[i] = fma(Q[i], nL[0], fma(Q[3 + i], nL[1], Q[6 + i] * nL[2])) * sk_scale;
+        {
             // d(e)/dt = (x_{k+1} - x_k).(v_{k+1} - v_k) / l / l_hat  (expanded form in the reference)
             const double edot = fma(d[0], dv[0], fma(d[1], dv[1], d[2] * dv[2])) * inv_len * inv_rest_len;
             double jw[3];
@@ -205,15 +232,20 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
         Rs[s] = rad;
         RSE[s] = rs_e;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) Sk[i * T + s] = sk[i];
+        for (int i = 0; i < 3; ++i) {
+            Sk[i * T + s] = sk[i];
+            LT[i * T + s] = local_t[i];
+        }
+        }
         __syncthreads();
 
         // =============================== P3: Voronoi couples and joints =====================
-        double Ak[3] = {0, 0, 0}, Ck[3] = {0, 0, 0};
-        if (is_vor) {
+        const double len = Ls[s], rad = Rs[s], rs_e = RSE[s];
+        {
+            double Ak[3], Ck[3];
             double Qn[9];
 #pragma unroll
-            for (int i = 0; i < 9; ++i) Qn[i] = Qs[i * T + s + 1];
+            for (int i = 0; i < 9; ++i) Qn[i] = Qs[i * T + sn];
 #define ROWDOT(a_, b_) fma(Qn[3 * (a_)], Q[3 * (b_)], fma(Qn[3 * (a_) + 1], Q[3 * (b_) + 1], Qn[3 * (a_) + 2] * Q[3 * (b_) + 2]))
             const double w0 = ROWDOT(2, 1) - ROWDOT(1, 2);
             const double w1 = ROWDOT(0, 2) - ROWDOT(2, 0);
@@ -221,10 +253,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
             const double tr = ROWDOT(0, 0) + ROWDOT(1, 1) + ROWDOT(2, 2);
 #undef ROWDOT
             const double rest_vlen = FC(BR2_FC_REST_VLEN), inv_rest_vlen = FC(BR2_FC_INV_REST_VLEN);
-            const double ks = logmap_scale(fma(0.5, tr, kMisc[6])) * inv_rest_vlen;
+            // y = 1 - cos(theta) with the reference's -1e-10 guard; a benign value off the rod
+            const double y = is_vor ? fma(-0.5, tr, kMisc[7]) : 0.01;
+            bad |= !(y <= 0.125 && y > 0.0);
+            const double ks = logmap_scale_small(y) * inv_rest_vlen * vor_mask;
             const double kap[3] = {w0 * ks, w1 * ks, w2 * ks};
             const double tau[3] = {FC(BR2_FC_BEND) * kap[0], FC(BR2_FC_BEND + 1) * kap[1], FC(BR2_FC_BEND + 2) * kap[2]};
-            const double vdil = 0.5 * (Ls[s + 1] + len) * inv_rest_vlen;
+            const double vdil = 0.5 * (Ls[sn] + len) * inv_rest_vlen;
             const double iv = fast_rcp(vdil);
             const double inv3 = iv * iv * iv;
             const double dinv3 = rest_vlen * inv3;
@@ -233,15 +268,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
             Ck[0] = fma(kap[1], tau[2], -kap[2] * tau[1]) * dinv3;
             Ck[1] = fma(kap[2], tau[0], -kap[0] * tau[2]) * dinv3;
             Ck[2] = fma(kap[0], tau[1], -kap[1] * tau[0]) * dinv3;
-        }
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            Av[i * T + s] = Ak[i];
-            Cv[i * T + s] = Ck[i];
+            for (int i = 0; i < 3; ++i) {
+                Av[i * T + s] = Ak[i];
+                Cv[i * T + s] = Ck[i];
+            }
         }
-        // own joint: this element is rod two (own data in registers), rod one's element is in shared memory
-        if (own_joint >= 0) {
-            const int s1 = own_partner;
+        // own joint (Appendix A.7): this element is rod two (own data in registers), rod one's element s1 is in
+        // shared memory.  Threads without a joint run it against a neighbour with a zero descriptor.
+        {
             const double off = JD[6 * T + s];
             const double ra1 = fma(0.5 * off, RSE[s1], Rs[s1]);   // r1 + o1
             const double ra2 = fma(0.5 * off, rs_e, rad);         // r2 + o2
@@ -257,35 +292,27 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
             }
             const double jk = FC(BR2_FC_JK);
             double cd[3], dvec[3];
+            double proj = 0.0;
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 const double c1 = 0.5 * (X[i * T + s1] + X[i * T + s1 + 1]);
-                const double c2 = 0.5 * (x[i] + X[i * T + s + 1]);
+                const double c2 = 0.5 * (x[i] + X[i * T + sn]);
                 cd[i] = c2 - c1;
                 // (c2 + rd2) - (c1 + rd1), rounded to 12 decimals like np.round_(x, 12)
                 dvec[i] = rint(((c2 + rd2[i]) - (c1 + rd1[i])) * BR2_1E12) * BR2_1EM12;
+                const double vr = 0.5 * (v[i] + Vs[i * T + sn]) - 0.5 * (Vs[i * T + s1] + Vs[i * T + s1 + 1]);
+                proj = fma(vr, dvec[i], proj);
             }
             const double dist2 = fma(dvec[0], dvec[0], fma(dvec[1], dvec[1], dvec[2] * dvec[2]));
-            double coef = jk;  // F = k d - nu (v_rel . d_hat) d_hat = (k - nu (v_rel . d) / |d|^2) d
-            if (dist2 >= BR2_1EM24) {
-                double proj = 0.0;
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const double vr = 0.5 * (v[i] + Vs[i * T + s + 1]) - 0.5 * (Vs[i * T + s1] + Vs[i * T + s1 + 1]);
-                    proj = fma(vr, dvec[i], proj);
-                }
-                coef = fma(-FC(BR2_FC_JNU) * proj, seed_rcp(dist2), jk);  // damping term ~1e-8 N: seed accuracy is ample
-            }
-            double F[3] = {coef * dvec[0], coef * dvec[1], coef * dvec[2]};
-            const double cn2 = fma(cd[0], cd[0], fma(cd[1], cd[1], cd[2] * cd[2]));
+            // F = k d - nu (v_rel . d_hat) d_hat = (k - nu (v_rel . d) / |d|^2) d ; no damping below |d| = 1e-12
+            const double inv_d2 = (dist2 >= BR2_1EM24) ? seed_rcp(dist2) : 0.0;  // damping term ~1e-8 N: seed accuracy is ample
+            const double coef = fma(-FC(BR2_FC_JNU) * proj, inv_d2, jk);
+            // Hertz-like repulsion when the surfaces interpenetrate: -k_rep |pen|^1.5 along the centre line
+            const double cn2 = fma(cd[0], cd[0], fma(cd[1], cd[1], cd[2] * cd[2])) + (has_joint ? 0.0 : 1.0);
             const double rcn = fast_rsqrt(cn2);
-            const double pen = fma(cn2, rcn, -(ra1 + ra2));
-            if (pen < 0.0) {
-                const double ap = -pen;
-                const double mag = -FC(BR2_FC_JKREP) * ap * (ap * fast_rsqrt(ap)) * rcn;
-#pragma unroll
-                for (int i = 0; i < 3; ++i) F[i] = fma(mag, cd[i], F[i]);
-            }
+            const double ap = fmax(fma(-cn2, rcn, ra1 + ra2), 0.0);   // max(-pen, 0)
+            const double ap3 = ap * ap * ap;
+            const double mag = -FC(BR2_FC_JKREP) * (ap3 * fast_rsqrt(ap3 + BR2_TINY)) * rcn;  // ap^1.5 = ap^3 / sqrt(ap^3)
             // torques use the spring part only: t = rd x (k d); rotate into each material frame
             const double t1[3] = {jk * fma(rd1[1], dvec[2], -rd1[2] * dvec[1]), jk * fma(rd1[2], dvec[0], -rd1[0] * dvec[2]),
                                   jk * fma(rd1[0], dvec[1], -rd1[1] * dvec[0])};
@@ -293,9 +320,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
                                   jk * fma(rd2[1], dvec[0], -rd2[0] * dvec[1])};
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                JF[i * TJ + own_joint] = 0.5 * F[i];
-                JT[i * TJ + own_joint] = fma(Qs[(3 * i) * T + s1], t1[0], fma(Qs[(3 * i + 1) * T + s1], t1[1], Qs[(3 * i + 2) * T + s1] * t1[2]));
-                JT[(3 + i) * TJ + own_joint] = fma(Q[3 * i], t2[0], fma(Q[3 * i + 1], t2[1], Q[3 * i + 2] * t2[2]));
+                const double hF = 0.5 * fma(coef, dvec[i], mag * cd[i]);
+                EFp[i * TP + jdst] = hF;
+                EFo[i * TP + odst] = -hF;
+                TQp[i * TP + jdst] = fma(Qs[(3 * i) * T + s1], t1[0], fma(Qs[(3 * i + 1) * T + s1], t1[1], Qs[(3 * i + 2) * T + s1] * t1[2]));
+                TO[i * T + s] = fma(Q[3 * i], t2[0], fma(Q[3 * i + 1], t2[1], Q[3 * i + 2] * t2[2]));
             }
         }
         // one further joint per thread (tip-to-base joints, or surface joints that did not fit the
@@ -304,7 +333,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
             const int j = extra_joint;
             const int *ji = tb.joint_i + j * BR2_J_NI;
             const double *jd = tb.joint_d + j * BR2_J_ND;
-            const int type = ji[BR2_J_TYPE], s1 = ji[BR2_J_S1], s2 = ji[BR2_J_S2], q1 = ji[BR2_J_Q1], q2 = ji[BR2_J_Q2];
+            const int type = ji[BR2_J_TYPE], e1 = ji[BR2_J_S1], e2 = ji[BR2_J_S2], q1 = ji[BR2_J_Q1], q2 = ji[BR2_J_Q2];
             const double kj = jd[0], nuj = jd[1];
             double Q1[9], Q2[9];
 #pragma unroll
@@ -315,16 +344,16 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
             double c1[3], c2[3], cd[3], vrel[3];
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                c1[i] = 0.5 * (X[i * T + s1] + X[i * T + s1 + 1]);
-                c2[i] = 0.5 * (X[i * T + s2] + X[i * T + s2 + 1]);
+                c1[i] = 0.5 * (X[i * T + e1] + X[i * T + e1 + 1]);
+                c2[i] = 0.5 * (X[i * T + e2] + X[i * T + e2 + 1]);
                 cd[i] = c2[i] - c1[i];
-                vrel[i] = 0.5 * (Vs[i * T + s2] + Vs[i * T + s2 + 1]) - 0.5 * (Vs[i * T + s1] + Vs[i * T + s1 + 1]);
+                vrel[i] = 0.5 * (Vs[i * T + e2] + Vs[i * T + e2 + 1]) - 0.5 * (Vs[i * T + e1] + Vs[i * T + e1 + 1]);
             }
             double F[3], T1[3] = {0, 0, 0}, T2[3] = {0, 0, 0};
             if (type == BR2_JOINT_SURFACE) {
                 const double off = jd[9];
-                const double ra1 = fma(0.5 * off, RSE[s1], Rs[s1]);
-                const double ra2 = fma(0.5 * off, RSE[s2], Rs[s2]);
+                const double ra1 = fma(0.5 * off, RSE[e1], Rs[e1]);
+                const double ra2 = fma(0.5 * off, RSE[e2], Rs[e2]);
                 double rd1[3], rd2[3], dvec[3], Fs[3];
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
@@ -339,9 +368,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
                 }
                 const double dist2 = fma(dvec[0], dvec[0], fma(dvec[1], dvec[1], dvec[2] * dvec[2]));
                 if (dist2 >= BR2_1EM24) {
-                    const double rdist = fast_rsqrt(dist2);
-                    const double proj = fma(vrel[0], dvec[0], fma(vrel[1], dvec[1], vrel[2] * dvec[2])) * rdist;
-                    const double coef = -nuj * proj * rdist;
+                    const double proj = fma(vrel[0], dvec[0], fma(vrel[1], dvec[1], vrel[2] * dvec[2]));
+                    const double coef = -nuj * proj * seed_rcp(dist2);
 #pragma unroll
                     for (int i = 0; i < 3; ++i) F[i] = fma(coef, dvec[i], F[i]);
                 }
@@ -363,8 +391,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
                     T1[i] = fma(Q1[3 * i], t1[0], fma(Q1[3 * i + 1], t1[1], Q1[3 * i + 2] * t1[2]));
                     T2[i] = fma(Q2[3 * i], t2[0], fma(Q2[3 * i + 1], t2[1], Q2[3 * i + 2] * t2[2]));
                 }
-            } else {  // tip-to-base: un-rounded spring, un-projected damping, no torque
-                const double r1 = Rs[s1], r2 = Rs[s2];
+            } else {  // tip-to-base (Appendix A.8): un-rounded spring, un-projected damping, no torque
+                const double r1 = Rs[e1], r2 = Rs[e2];
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     const double a1 = fma(Q1[i], jd[3], fma(Q1[3 + i], jd[4], Q1[6 + i] * jd[5])) * r1;
@@ -375,9 +403,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
             }
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                JF[i * TJ + j] = 0.5 * F[i];
-                JT[i * TJ + j] = T1[i];
-                JT[(3 + i) * TJ + j] = T2[i];
+                JF[i * TJ + extra_row] = 0.5 * F[i];
+                JT[i * TJ + extra_row] = T1[i];
+                JT[(3 + i) * TJ + extra_row] = T2[i];
             }
         }
         // tip-to-base joints overwrite the downstream base element's director / omega during
@@ -392,93 +420,79 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
 
         // =============================== P4: assemble, dynamic step =========================
         {
-            const bool first = (k == 0);
             double f_int[3], t_int[3], f_ext[3], t_ext[3];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const double prev = first ? 0.0 : Sk[i * T + s - 1];
-                f_int[i] = sk[i] - prev;  // sk is 0 on the node-only slot k = n
-                const double Ap = first ? 0.0 : Av[i * T + s - 1];
-                const double Cp = first ? 0.0 : Cv[i * T + s - 1];
-                t_int[i] = (Ak[i] - Ap) + fma(0.5, Ck[i] + Cp, local_t[i]);  // Ak = Ck = 0 on k = n-1
-            }
-            // external loads: (soft-fix spring, reported only) -> forcing -> joints in registration order
-            double spring[3] = {0, 0, 0};
-            if (last && softfix_row >= 0) {
-                const double *cd = tb.cons_d + softfix_row * BR2_C_ND;
-                const double e0 = cd[0] - x[0], e1 = cd[1] - x[1], e2 = cd[2] - x[2];
-                const double dist = sqrt(e0 * e0 + e1 * e1 + e2 * e2);
-                double u0 = 0.0, u1 = 0.0, u2 = 0.0;
-                if (!(dist <= 1e-8)) {
-                    u0 = e0 / dist;
-                    u1 = e1 / dist;
-                    u2 = e2 / dist;
-                }
-                const double proj = (-v[0]) * u0 + (-v[1]) * u1 + (-v[2]) * u2;
-                spring[0] = cd[12] * e0 + (-cd[13] * (proj * u0));
-                spring[1] = cd[12] * e1 + (-cd[13] * (proj * u1));
-                spring[2] = cd[12] * e2 + (-cd[13] * (proj * u2));
-            }
             const double ramp = fmin(1.0, time_mid * tb.act_inv_ramp);
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                f_ext[i] = fma(FC(BR2_FC_GRAVITY + i), mass, spring[i]);
-                t_ext[i] = TA[i * T + s] * ramp;
+                // own values come back from shared memory rather than staying in registers across the barriers
+                f_int[i] = fma(-prev_mask, Sk[i * T + sp], Sk[i * T + s]);  // Sk is 0 on the node-only slot k = n
+                const double dA = fma(-prev_mask, Av[i * T + sp], Av[i * T + s]);  // Av = Cv = 0 on k >= n-1
+                const double sC = fma(prev_mask, Cv[i * T + sp], Cv[i * T + s]);
+                t_int[i] = dA + fma(0.5, sC, LT[i * T + s]);
+                // joints: node k collects the half forces of elements k and k-1 of its rod
+                const double fe = EFo[i * TP + s] + EFp[i * TP + s];
+                const double fp = EFo[i * TP + sp] + EFp[i * TP + sp];
+                f_ext[i] = fma(FC(BR2_FC_GRAVITY + i), mass, fma(prev_mask, fp, fe));
+                t_ext[i] = fma(TA[i * T + s], ramp, TO[i * T + s] + TQp[i * TP + s]);
             }
+            if (any_extra) {  // CTA-uniform: only assemblies with tip-to-base (or otherwise unowned) joints
 #pragma unroll
-            for (int q = 0; q < BR2_FAST_NODE_ITEMS; ++q) {
-                if (q < node_count) {
-                    const unsigned item = (node_items[q >> 1] >> ((q & 1) * 16)) & 0xFFFFu;
-                    const double sgn = (item & 1u) ? -1.0 : 1.0;
-                    const int j = (int)(item >> 1);
+                for (int q = 0; q < BR2_FAST_NODE_ITEMS; ++q) {
+                    if (q < x_node_count) {
+                        const unsigned item = (x_node_items[q >> 1] >> ((q & 1) * 16)) & 0xFFFFu;
+                        const double sgn = (item & 1u) ? -1.0 : 1.0;
+                        const int j = (int)(item >> 1);
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) f_ext[i] = fma(sgn, JF[i * TJ + j], f_ext[i]);
+                        for (int i = 0; i < 3; ++i) f_ext[i] = fma(sgn, JF[i * TJ + j], f_ext[i]);
+                    }
+                }
+                if (x_elem_item0 >= 0) {
+                    const int base = (x_elem_item0 & 1) * 3 * TJ + (x_elem_item0 >> 1);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) t_ext[i] += JT[base + i * TJ];
+                }
+                if (x_elem_item1 >= 0) {
+                    const int base = (x_elem_item1 & 1) * 3 * TJ + (x_elem_item1 >> 1);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) t_ext[i] += JT[base + i * TJ];
                 }
             }
-            if (elem_item0 >= 0) {
-                const int base = (elem_item0 & 1) * 3 * TJ + (elem_item0 >> 1);
-#pragma unroll
-                for (int i = 0; i < 3; ++i) t_ext[i] += JT[base + i * TJ];
-            }
-            if (elem_item1 >= 0) {
-                const int base = (elem_item1 & 1) * 3 * TJ + (elem_item1 >> 1);
-#pragma unroll
-                for (int i = 0; i < 3; ++i) t_ext[i] += JT[base + i * TJ];
-            }
             // dynamic step, damper, rate constraints
-            double a[3], alpha[3];
-            const double c_t = FC(BR2_FC_CT);
-            const double strain = dil - 1.0;
-            double damp[3];
-            damp[0] = FC(BR2_FC_CR) * exp_near_zero(strain * FC(BR2_FC_LN_CR));
-            const bool isotropic = FC(BR2_FC_LN_CR + 1) == FC(BR2_FC_LN_CR);  // I1 == I2 (round cross-section)
-            damp[1] = isotropic ? damp[0] : FC(BR2_FC_CR + 1) * exp_near_zero(strain * FC(BR2_FC_LN_CR + 1));
-            damp[2] = FC(BR2_FC_CR + 2) * exp_near_zero(strain * FC(BR2_FC_LN_CR + 2));
+            double a[3], alpha[3], damp[3];
+            const double c_t = FC(BR2_FC_CT) * keep_v;
+            const double len4 = Ls[s];
+            const double dil4 = len4 * FC(BR2_FC_INV_REST_LEN);
+            const double strain = (dil4 - 1.0) * elem_mask;
+            const double e0 = strain * FC(BR2_FC_LN_CR), e1 = strain * FC(BR2_FC_LN_CR + 1), e2 = strain * FC(BR2_FC_LN_CR + 2);
+            bad |= !(fmax(fabs(e0), fmax(fabs(e1), fabs(e2))) <= 0.02);
+            damp[0] = FC(BR2_FC_CR) * exp_small(e0) * keep_w;
+            damp[1] = (FC(BR2_FC_LN_CR + 1) == FC(BR2_FC_LN_CR))   // I1 == I2 (round cross-section)
+                          ? damp[0]
+                          : FC(BR2_FC_CR + 1) * exp_small(e1) * keep_w;
+            damp[2] = FC(BR2_FC_CR + 2) * exp_small(e2) * keep_w;
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 a[i] = (f_int[i] + f_ext[i]) * inv_mass;
                 v[i] = fma(dt, a[i], v[i]) * c_t;
-                alpha[i] = FC(BR2_FC_JINV + i) * (t_int[i] + t_ext[i]) * dil;
+                alpha[i] = FC(BR2_FC_JINV + i) * (t_int[i] + t_ext[i]) * dil4;
                 w[i] = fma(dt, alpha[i], w[i]) * damp[i];
             }
-            if (flags & BR2_FAST_ZERO_NODE_RATE) {
-#pragma unroll
-                for (int i = 0; i < 3; ++i) v[i] = 0.0;
-            }
-            if (flags & BR2_FAST_ZERO_ELEM_RATE) {
-#pragma unroll
-                for (int i = 0; i < 3; ++i) w[i] = 0.0;
-            }
             if (last && valid) {
+                // quantities the reference's callbacks report (free_simulator.py:56-72), as of this step
+                if (softfix_row >= 0) {
+                    // FreeBaseEndSoftFixed's spring acts on node 0 in both constrain_values calls of the step;
+                    // it never changes the motion (node 0's rates are zeroed) and is only visible here.
+                    // The velocity of node 0 is zero by construction, so the damping part vanishes.
+                    const double *cd = tb.cons_d + softfix_row * BR2_C_ND;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const double spring = cd[12] * (cd[i] - x[i]);
+                        f_ext[i] = (f_ext[i] + spring) + spring;
+                    }
+                }
                 if (flags & BR2_FAST_ZERO_REPORTED) {
 #pragma unroll
                     for (int i = 0; i < 3; ++i) a[i] = alpha[i] = 0.0;
-                }
-                if (softfix_row >= 0) {
-                    // second constrain_values of the step: node 0 has not moved and its velocity is now zero
-                    const double *cd = tb.cons_d + softfix_row * BR2_C_ND;
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) f_ext[i] += cd[12] * (cd[i] - x[i]);
                 }
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
@@ -493,25 +507,26 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
                         G_TINT[i * n + k] = t_int[i];
                         G_TEXT[i * n + k] = t_ext[i];
                     }
-                    G_LEN[k] = len;
-                    G_DIL[k] = dil;
-                    G_RAD[k] = rad;
+                    G_LEN[k] = len4;
+                    G_DIL[k] = dil4;
+                    G_RAD[k] = Rs[s];
                 }
             }
         }
         // trailing kinematic half step of this step + (unless this is the last step of the launch)
         // the leading half step of the next one; value constraints = the pins, which never move
-        if (move_x) {
+        const double hx2 = last ? 0.0 : hx;
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                x[i] = fma(hdt, v[i], x[i]);
-                if (!last) x[i] = fma(hdt, v[i], x[i]);
-            }
-        }
-        if (spin_Q) rotate_directors(Q, hdt * w[0], hdt * w[1], hdt * w[2], last ? 1.0 : 2.0);
+        for (int i = 0; i < 3; ++i) x[i] = fma(hx2, v[i], fma(hx, v[i], x[i]));
+        bad |= rotate_directors(Q, hq * w[0], hq * w[1], hq * w[2], last ? 1.0 : 2.0);
         time = time_mid + hdt;
     }
 
+    // a CTA that left the series' validity range keeps its launch-start state and asks for the exact path
+    if (__syncthreads_or(bad)) {
+        if (s == 0) p.status[b] = 1;
+        return;
+    }
     if (valid) {
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
@@ -538,15 +553,15 @@ __global__ void selftest_math_kernel(int which, const double *in, double *out, l
     case 0: y = fast_rcp(x); break;
     case 1: y = fast_rsqrt(x); break;
     case 2:
-        if (x <= 0.01) sinc_cosc_small(x, sinc, cosc); else sinc_cosc_large(x, sinc, cosc);
+        sinc_cosc_small(x, sinc, cosc);
         y = sinc;
         break;
     case 3:
-        if (x <= 0.01) sinc_cosc_small(x, sinc, cosc); else sinc_cosc_large(x, sinc, cosc);
+        sinc_cosc_small(x, sinc, cosc);
         y = cosc;
         break;
-    case 4: y = logmap_scale(x); break;
-    default: y = exp_near_zero(x); break;
+    case 4: y = logmap_scale_small(1.0 - x); break;
+    default: y = exp_small(x); break;
     }
     out[i] = y;
 }

@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_generic_kernel(
 
     const int s = threadIdx.x;
     const long long b = blockIdx.x;
+    if (p.only_flagged && p.status[b] == 0) return;  // replay pass: nothing to redo for this instance
     const bool valid = s < S;
     const int sc = valid ? s : S - 1;
 
@@ -529,6 +530,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_generic_kernel(
             g_dil[k] = dil;
             g_rad[k] = rad;
         }
+    }
+    if (p.only_flagged && s == 0) {
+        p.status[b] = 0;
+        atomicAdd(p.replays, 1ULL);
     }
 #undef SCONST
 }

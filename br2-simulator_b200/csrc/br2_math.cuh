@@ -23,7 +23,7 @@ __constant__ double kLogC[16] = {
     32768.0 / 109395.0, 65536.0 / 230945.0, 262144.0 / 969969.0, 524288.0 / 2028117.0, 4194304.0 / 16900975.0,
     8388608.0 / 35102025.0, 33554432.0 / 145422675.0, 67108864.0 / 300540195.0};
 __constant__ double kExpC[7] = {1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0};
-__constant__ double kMisc[8] = {1e-14, 1e-300, 1e12, 1e-12, 1e-24, 0.375, -0.5 - 1e-10, 1e-10};
+__constant__ double kMisc[8] = {1e-14, 1e-300, 1e12, 1e-12, 1e-24, 0.375, -0.5 - 1e-10, 1.5 + 1e-10};
 #define BR2_EPS14 kMisc[0]
 #define BR2_TINY kMisc[1]
 #define BR2_1E12 kMisc[2]
@@ -74,14 +74,6 @@ __device__ __forceinline__ void sinc_cosc_small(double t, double &sinc, double &
     cosc = c;
 }
 
-__device__ __noinline__ void sinc_cosc_large(double t, double &sinc, double &cosc) {
-    const double theta = sqrt(t);
-    double s, c;
-    sincos(theta, &s, &c);
-    sinc = s / theta;
-    cosc = (1.0 - c) / t;
-}
-
 // Row-director Rodrigues update for `mult` consecutive kinematic half steps with the same rotation
 // vector u = (dt/2) omega (mult = 1 or 2).  One half step of the reference uses
 // the unit axis u / (|u| + 1e-14), i.e. rotates by g |u| with g = |u| / (|u| + 1e-14); omega does not
@@ -89,7 +81,8 @@ __device__ __noinline__ void sinc_cosc_large(double t, double &sinc, double &cos
 // rotations share their axis and compose to one rotation by phi = 2 g |u| (applied as ONE matrix).
 //   R = I + (sin phi / |u|) K(u) + ((1 - cos phi) / |u|^2) (u u^T - |u|^2 I)
 //   sin phi / |u| = sinc(phi) m,   (1 - cos phi) / |u|^2 = cosc(phi) m^2,   m = mult * g.
-__device__ __forceinline__ void rotate_directors(double (&Q)[9], double u0, double u1, double u2, double mult) {
+// Returns true when phi^2 left the series' range (|phi| > 0.1 rad in one step) or is NaN.
+__device__ __forceinline__ bool rotate_directors(double (&Q)[9], double u0, double u1, double u2, double mult) {
     const double t = fma(u0, u0, fma(u1, u1, u2 * u2));
     const double tt = t + BR2_TINY;                 // keeps rsqrt finite for a resting element
     const double rs = fast_rsqrt(tt);
@@ -98,11 +91,7 @@ __device__ __forceinline__ void rotate_directors(double (&Q)[9], double u0, doub
     const double m2 = m * m;
     const double tphi = m2 * t;                   // phi^2
     double sinc, cosc;
-    if (tphi <= 0.01) {
-        sinc_cosc_small(tphi, sinc, cosc);
-    } else {
-        sinc_cosc_large(tphi, sinc, cosc);
-    }
+    sinc_cosc_small(tphi, sinc, cosc);
     const double a = sinc * m;
     const double b = cosc * m2;
     const double a0 = a * u0, a1 = a * u1, a2 = a * u2;
@@ -120,6 +109,7 @@ __device__ __forceinline__ void rotate_directors(double (&Q)[9], double u0, doub
         Q[3 + c] = fma(R10, q0, fma(R11, q1, R12 * q2));
         Q[6 + c] = fma(R20, q0, fma(R21, q1, R22 * q2));
     }
+    return !(tphi <= 0.01);
 }
 
 // Log-map scale of the rod curvature:
@@ -143,30 +133,12 @@ __device__ __forceinline__ double logmap_scale_small(double y) {
     return -0.5 * f * guard;
 }
 
-__device__ __noinline__ double logmap_scale_large(double c) {
-    const double theta = acos(c);
-    return -0.5 * theta / sin(theta + 1e-14);
-}
-
-__device__ __forceinline__ double logmap_scale(double c) {
-    const double y = 1.0 - c;
-    if (y <= 0.125 && y > 0.0) return logmap_scale_small(y);
-    return logmap_scale_large(c);
-}
-
 // exp(d) for |d| <= 0.02 (damper: exp(e ln c) = c * exp((e - 1) ln c)); degree-7 Taylor, truncation < 1e-18.
 __device__ __forceinline__ double exp_small(double d) {
     double p = kExpC[0];
 #pragma unroll
     for (int i = 1; i < 7; ++i) p = fma(p, d, kExpC[i]);
     return fma(p, d, 1.0);
-}
-
-__device__ __noinline__ double exp_large(double d) { return exp(d); }
-
-__device__ __forceinline__ double exp_near_zero(double d) {
-    if (fabs(d) <= 0.02) return exp_small(d);
-    return exp_large(d);
 }
 
 }  // namespace br2

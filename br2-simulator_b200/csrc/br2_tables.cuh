@@ -35,6 +35,9 @@ struct StepParams {
     long long batch;
     long long n_steps;
     double t0, dt;
+    int *status;        // [batch] 0 = ok, 1 = the fast kernel left its validity range on this instance
+    int only_flagged;   // generic kernel: integrate only instances whose status is set, then clear it
+    unsigned long long *replays;  // counts instance-launches redone by the exact path
     double uni[BR2_FC_COUNT];  // uniform copy of fast_c (all element slots identical), constant bank
 };
 

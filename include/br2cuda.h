@@ -111,8 +111,10 @@ enum {
  * the generic tables every step.  finalize() fills these when the assembly qualifies (fast_ok = 1):
  *   - forcing rows are gravity / twist / bend only, all with the same ramp_up_time;
  *   - rest_sigma and rest_kappa are zero;
- *   - every element owns at most one surface joint as "rod two" and at most one further joint,
- *     every node receives at most BR2_FAST_NODE_ITEMS half-forces and every element at most two torques.
+ *   - every element is "rod two" of at most one surface joint and "rod one" of at most one (those
+ *     contributions are gathered implicitly); at most BR2_FAST_MAX_EXTRA further joints (tip-to-base
+ *     joints, surface joints outside that pattern), of which a node receives at most
+ *     BR2_FAST_NODE_ITEMS half-forces and an element at most two torques.
  * Otherwise the generic table-interpreting kernel runs.  Same results either way (tests compare them).
  */
 /* fast_i: [n_slots][BR2_FAST_NI] int32 */
@@ -120,14 +122,15 @@ enum {
     BR2_FAST_FLAGS = 0,
     BR2_FAST_OWN_JOINT = 1,    /* joint row this slot's element evaluates as rod two, or -1 */
     BR2_FAST_EXTRA_JOINT = 2,  /* one more joint row evaluated by this thread from shared memory, or -1 */
+    BR2_FAST_EXTRA_ID = 16,    /* compact id (< BR2_FAST_MAX_EXTRA) of that joint; gather items refer to it */
     BR2_FAST_SOFTFIX_ROW = 3,  /* constraint row of a soft-fixed base on this slot (node 0), or -1 */
     BR2_FAST_ACT_BEGIN = 4,    /* actuation rows [begin, end) acting on this slot's element */
     BR2_FAST_ACT_END = 5,
-    BR2_FAST_ELEM_ITEM0 = 6,   /* 2 torque gather items ((joint << 1) | side), -1 = none */
-    BR2_FAST_NODE_ITEM0 = 8,   /* BR2_FAST_NODE_ITEMS force gather items ((joint << 1) | sign), -1 = none */
-    BR2_FAST_NI = 16
+    BR2_FAST_ELEM_ITEM0 = 6,   /* 2 torque gather items ((extra id << 1) | side) of extra joints, -1 = none */
+    BR2_FAST_NODE_ITEM0 = 8,   /* BR2_FAST_NODE_ITEMS force gather items ((extra id << 1) | sign) of extra joints */
+    BR2_FAST_NI = 18
 };
-enum { BR2_FAST_NODE_ITEMS = 8 };
+enum { BR2_FAST_NODE_ITEMS = 8, BR2_FAST_MAX_EXTRA = 64 };
 enum {
     BR2_FAST_PIN_DIRECTOR = 1,  /* element director is reset to a constant every half step */
     BR2_FAST_PIN_POSITION = 2,  /* node position is reset to a constant every half step */
@@ -224,9 +227,12 @@ int br2_kernel_info(br2_handle h, int32_t *regs, int32_t *smem_bytes, int32_t *t
                     int32_t *blocks_per_sm, int32_t *sm_count, int32_t *variant);
 /* Force the kernel variant (0 generic, 1 fast, 2 fast uniform, -1 automatic); for cross-checks. */
 int br2_select_kernel(br2_handle h, int32_t variant);
+/* Instance-launches the exact-path (generic) kernel had to redo because the fast kernel left the validity
+ * range of its series on them (normally 0).  Synchronises the device. */
+int br2_replay_count(br2_handle h, int64_t *count);
 /* Evaluate the fast kernel's fp64 helpers on device arrays of n doubles (tests only):
- * which = 0 rcp, 1 rsqrt, 2 sinc(theta) [in: theta^2], 3 cosc(theta) [in: theta^2],
- *         4 log-map scale [in: cos theta], 5 exp near zero. */
+ * which = 0 rcp, 1 rsqrt, 2 sinc(theta) [in: theta^2 <= 0.01], 3 cosc(theta) [in: theta^2 <= 0.01],
+ *         4 log-map scale [in: cos theta >= 0.875], 5 exp(d) [in: |d| <= 0.02]. */
 int br2_selftest_math(int32_t which, const double *dev_in, double *dev_out, int64_t n);
 
 /* fp64 roofline denominator: runs a register-resident DFMA chain kernel on `device` and returns the

@@ -1,4 +1,5 @@
-"""The fast kernel's fp64 helpers (csrc/br2_math.cuh) against libm / mpmath on the device.
+"""The fast kernel's fp64 helpers (csrc/br2_math.cuh) against libm / mpmath on the device, over the
+validity ranges inside which the fast kernel uses them (outside, the exact-path kernel takes over).
 Stated bound: 4 ulp (8.9e-16 relative) -- seven orders of magnitude inside the 1e-9 parity budget."""
 import numpy as np
 import pytest
@@ -35,35 +36,28 @@ def test_sinc_cosc():
     import mpmath as mp
 
     rng = np.random.default_rng(1)
-    t = np.concatenate([10.0 ** rng.uniform(-40, -2, 4000), rng.uniform(0.0, 0.01, 4000), rng.uniform(0.01, 9.0, 500), [0.0, 0.01]])
+    t = np.concatenate([10.0 ** rng.uniform(-40, -2, 4000), rng.uniform(0.0, 0.01, 4000), [0.0, 0.01]])
     mp.mp.dps = 120
     sinc = np.array([float(mp.sin(mp.sqrt(v)) / mp.sqrt(v)) if v > 0 else 1.0 for v in t])
     cosc = np.array([float((1 - mp.cos(mp.sqrt(v))) / mp.mpf(v)) if v > 0 else 0.5 for v in t])
-    small = t <= 0.01
-    assert relerr(run(2, t)[small], sinc[small]).max() <= ULP4
-    assert relerr(run(2, t)[~small], sinc[~small]).max() <= 1e-14  # libm slow path: sqrt, sin, divide
-    assert relerr(run(3, t)[small], cosc[small]).max() <= ULP4
-    # above the series range the libm slow path (1 - cos)/t loses digits to cancellation, like the reference
-    assert relerr(run(3, t)[~small], cosc[~small]).max() <= 1e-13
+    assert relerr(run(2, t), sinc).max() <= ULP4
+    assert relerr(run(3, t), cosc).max() <= ULP4
 
 
 def test_logmap_scale():
     import mpmath as mp
 
-    mp.mp.dps = 120
+    mp.mp.dps = 60
     rng = np.random.default_rng(2)
-    theta = np.concatenate([10.0 ** rng.uniform(-5, -0.3, 4000), rng.uniform(0.0, 0.5, 2000), rng.uniform(0.5, 3.0, 300)])
+    theta = np.concatenate([10.0 ** rng.uniform(-5, -0.3, 4000), rng.uniform(0.0, 0.5, 2000)])
     c = np.cos(theta)
-    c = c[c < 1.0 - 1e-11]  # the rod kernel always subtracts 1e-10 first
+    c = c[(c < 1.0 - 1e-11) & (1.0 - c <= 0.125)]  # the rod kernel always subtracts 1e-10 first
     want = np.array([float(-mp.mpf(0.5) * mp.acos(mp.mpf(v)) / mp.sin(mp.acos(mp.mpf(v)) + mp.mpf("1e-14"))) for v in c])
-    got = run(4, c)
-    # the conditioning of acos near 1 belongs to the input, not the method: compare as a function of c
-    series = (1.0 - c) <= 0.125
-    assert relerr(got[series], want[series]).max() <= 8 * 2.0 ** -52
-    assert relerr(got[~series], want[~series]).max() <= 1e-14
+    # compared as a function of c (the conditioning of acos near 1 belongs to the input, not the method)
+    assert relerr(run(4, c), want).max() <= 8 * 2.0 ** -52
 
 
 def test_exp_near_zero():
     rng = np.random.default_rng(3)
-    d = np.concatenate([rng.uniform(-0.02, 0.02, 100000), 10.0 ** rng.uniform(-20, -2, 1000), rng.uniform(-3, 3, 1000), [0.0]])
+    d = np.concatenate([rng.uniform(-0.02, 0.02, 100000), 10.0 ** rng.uniform(-20, -2, 1000), [0.0, 0.02, -0.02]])
     assert relerr(run(5, d), np.exp(d)).max() <= ULP4

@@ -146,6 +146,13 @@ def test_serial_joint_overwrite_chain_is_resolved():
             row = first[a, b]
             assert row[1] == S0[a] + n - 1 and row[2] == S0[3 + b] and row[3] == S0[a] + n - 1
             assert row[4] == (S0[3 + b] if a == 0 else S0[a - 1] + n - 1)
+    # fast path: the 18 tip joints are "extra" joints with compact ids, one per thread, spread over warps
+    fi = t["fast_i"]
+    assert program.fast["ok"] and program.fast["uniform"]
+    extra_rows = fi[fi[:, L.FAST_EXTRA_JOINT] >= 0]
+    assert sorted(extra_rows[:, L.FAST_EXTRA_ID]) == list(range(18))
+    assert set(t["joint_i"][extra_rows[:, L.FAST_EXTRA_JOINT], 0]) == {1}
+    assert (fi[:, L.FAST_OWN_JOINT] >= 0).sum() == 9 * n  # every element owns its ring joint
     # tip joints add no torque rows; unactuated rods of segment 3 have no fibre forcing
     assert np.diff(t["elem_ptr"]).max() == 2
     seg3 = t["rod_i"][6:9]
