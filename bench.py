@@ -213,7 +213,9 @@ def run_ours(args, world, rank, local):
     rng = np.random.default_rng(w["seed"] + 1000 * rank)
     pressures = rng.uniform(0.0, 40.0, size=(3, B)) * PSI
 
-    env = Environment("bench", batch=B, device=device, create_dirs=False)
+    # Environment's batch is the GLOBAL instance count; under torchrun it keeps this rank's contiguous share (B)
+    env = Environment("bench", batch=B * world, device=device, create_dirs=False)
+    assert env.batch == B
     env.reset(ROD_DB, os.path.join(DATA, w["assembly"]), gravity=w["gravity"])
     env.simulator._callback_ops = []  # stepping only; capture is a separate (next-row) path
     engine = env.engine
@@ -262,9 +264,15 @@ def run_ours(args, world, rank, local):
     e2e_steps = max(2, min(args.steps, 5))
     duration = M * dt - 0.5 * dt
 
+    from br2 import _dist
+
     def e2e_once():
         env.run(action_host, duration=duration, disable_progress_bar=True)  # H2D of the pressures inside
         pinned_state.copy_(engine.state, non_blocking=True)                 # D2H of the batch state
+        if world > 1:
+            # the only collective of the path: per-instance metrics of all ranks to rank 0 over NCCL
+            tip = engine.view(0, "x")[:, :, -1].contiguous()
+            _dist.gather_batch(tip, B * world, dst=0, device=device)
         torch.cuda.synchronize(device)
 
     e2e_once()

@@ -18,7 +18,7 @@ from typing import Optional
 
 import numpy as np
 
-from . import _native
+from . import _dist, _native
 from .free_simulator import FreeAssembly
 from .hooks import PositionVerlet, extend_stepper_interface
 
@@ -103,7 +103,23 @@ class Environment:
         self.step_skip = int(1.0 / (self.rendering_fps * self.time_step))
         self.capture_interval = None
         self.shearable_rods = {}
-        self.batch = int(batch)
+        # ``batch`` is the GLOBAL number of instances.  Under torch.distributed (one process per GPU) the
+        # batch is split contiguously over the ranks (br2._dist.partition); instances never interact, so
+        # stepping needs no collective and only results are gathered (gather_data / TerminalInfo).
+        self.global_batch = int(batch)
+        self.world_size, self.rank = 1, 0
+        try:
+            import torch.distributed as dist
+
+            if dist.is_available() and dist.is_initialized():
+                self.world_size, self.rank = dist.get_world_size(), dist.get_rank()
+        except ImportError:
+            pass
+        start, stop = _dist.partition(self.global_batch, self.world_size, self.rank)
+        self.batch_range = (start, stop)
+        self.batch = stop - start
+        if self.batch < 1:
+            raise ValueError("batch %d is smaller than the number of ranks %d" % (self.global_batch, self.world_size))
         self.device = device
         # steady-state thresholds (reference :176-181)
         self.position_threshold = 1.0e-7
@@ -142,6 +158,11 @@ class Environment:
     def run(self, action: dict, duration: Optional[float] = None, disable_progress_bar: bool = False,
             check_nan: bool = False, check_steady_state: Optional[int] = None) -> TerminalInfo:
         status = TerminalInfo()
+        if self.world_size > 1:
+            # global-length action arrays are sliced to this rank's share; local-length ones pass through
+            action = {k: (v if np.ndim(v) == 0 or len(v) == self.batch else
+                          _dist.shard_action({k: v}, self.global_batch, self.world_size, self.rank)[k])
+                      for k, v in action.items()}
         self.assy.set_actuation(action)
         self._push_actuation()
         engine, dt = self.engine, self.time_step
@@ -181,6 +202,7 @@ class Environment:
         if check_steady_state == 1:
             # the reference measures node POSITIONS here although it calls them velocities (:292-298)
             per_instance = torch.linalg.vector_norm(self._state_stack("x"), dim=1).amax(dim=-1)
+            per_instance = _dist.gather_batch(per_instance, self.global_batch, device=self.engine.device)
             max_velocity = float(per_instance.max())
             status.velocity_steady_state_status = max_velocity < self.velocity_threshold
             status.max_velocity = max_velocity
@@ -199,6 +221,8 @@ class Environment:
             flags = {}
             for label, short in (("position", "x"), ("velocity", "v"), ("director", "Q"), ("omega", "w")):
                 per_instance = torch.isnan(self._state_stack(short)).flatten(1).any(dim=1)
+                per_instance = _dist.gather_batch(per_instance.to(torch.int32), self.global_batch,
+                                                  device=self.engine.device).bool()
                 flags[label] = per_instance.cpu().numpy()
                 setattr(status, "%s_nan_status" % label, bool(per_instance.any()))
             status.nan_per_instance = flags
@@ -244,6 +268,21 @@ class Environment:
             directors.append(np.array(sink["director"]))
         np.savez(os.path.join(self.paths.data, filename), time=np.array(self.data_rods[0]["time"]),
                  positions=np.asarray(positions), directors=np.asarray(directors))
+
+    def gather_data(self, dst=0):
+        """Callback histories of ALL instances on rank ``dst`` (same layout as ``data_rods``, batch axis =
+        global batch); other ranks get ``None``.  One gather per recorded field, over NCCL / gloo."""
+        if self.world_size == 1:
+            return self.data_rods
+        gathered = [_dist.gather_history(sink, self.global_batch, dst=dst) for sink in self.data_rods]
+        return gathered if self.rank == dst else None
+
+    def gather_field(self, rod_index, attribute, dst=None):
+        """One rod attribute (e.g. ``"position_collection"``) of ALL instances, ``[global_batch, ...]``."""
+        local = np.asarray(getattr(self.simulator[rod_index], attribute))
+        if self.batch == 1:
+            local = local[None]
+        return _dist.gather_batch(local, self.global_batch, dst=dst)
 
     def close(self):
         engine = getattr(self, "engine", None)
