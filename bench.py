@@ -127,8 +127,11 @@ def dist_setup(args):
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        backend = "nccl" if (args.impl == "ours" and torch.cuda.is_available()) else "gloo"
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        if args.impl == "ours" and torch.cuda.is_available():
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend="nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend="gloo", rank=rank, world_size=world)
     return world, rank, local
 
 
@@ -316,7 +319,10 @@ def run_ours(args, world, rank, local):
         "e2e": {"value": e2e_value, "unit": "rod-element-steps/s", "h2d_bytes_per_step": int(3 * B * 8),
                 "d2h_bytes_per_step": int(B * engine.words * 8), "steps": e2e_steps},
         "gpu_launches": launches,
-        "kernel": dict(info, name="br2_step_kernel", launch_ms=per_launch_ms),
+        "kernel": dict(info, name="br2_step_fast_kernel" if info["variant"] else "br2_step_generic_kernel",
+                       launch_ms=per_launch_ms, exact_path_replays=engine.replay_count(),
+                       launches_per_step="fast kernel + exact-path replay pass (exits at once unless flagged)"
+                       if info["variant"] else "generic kernel"),
         "clocks": clocks,
         "state_finite": state_ok,
     }

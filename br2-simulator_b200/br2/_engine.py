@@ -42,6 +42,7 @@ class Engine:
         _native.check(self.lib.br2_bind_state(self.handle, self.state.data_ptr(), self.batch))
         _native.check(self.lib.br2_set_actuation(self.handle, self.pressures.data_ptr()))
         self.launches = 0
+        self._variant = self.kernel_info()["variant"]
 
     # ------------------------------------------------------------------ state access
     def load_template(self, rods):
@@ -99,7 +100,8 @@ class Engine:
             _native.check(self.lib.br2_step(self.handle, int(n_steps), float(t0), float(dt),
                                             ctypes.c_void_p(stream), ctypes.byref(t_end)))
         if n_steps > 0:
-            self.launches += 1
+            # the fast kernel is followed by the exact-path replay pass (br2_step launches both)
+            self.launches += 2 if self._variant else 1
         return t_end.value
 
     def kernel_info(self):
@@ -119,6 +121,7 @@ class Engine:
     def select_kernel(self, variant):
         """0 generic, 1 fast (per-slot constants), 2 fast (uniform constants), -1 automatic."""
         _native.check(self.lib.br2_select_kernel(self.handle, int(variant)))
+        self._variant = self.kernel_info()["variant"]
 
     def close(self):
         if getattr(self, "handle", None) is not None and self.handle.value:
