@@ -105,7 +105,7 @@ struct br2_handle_s {
     size_t replay_smem = 0;
     int variant = 0;        // 0 generic, 1 fast, 2 fast uniform
     int auto_variant = 0;   // what br2_create picked
-    bool fast_ok = false, fast_uniform = false;
+    bool fast_ok = false, fast_uniform = false, has_extra = false;
     double uni[BR2_FC_COUNT] = {0};
     int *status = nullptr;            // [batch] fast-kernel validity flags (library-owned)
     long long status_batch = 0;
@@ -222,6 +222,11 @@ int br2_create(const br2_program *p, int device, br2_handle *out) {
         UP(act_d, (size_t)p->n_act * 3);
         t.act_inv_ramp = 1.0 / p->act_ramp_up_time;
         for (int i = 0; i < BR2_FC_COUNT; ++i) h->uni[i] = p->fast_c[(size_t)i * S];  // slot 0's column
+        for (size_t sl = 0; sl < S; ++sl) {
+            const int32_t *fi = p->fast_i + sl * BR2_FAST_NI;
+            if (fi[BR2_FAST_EXTRA_JOINT] >= 0 || fi[BR2_FAST_NODE_ITEM0] >= 0 || fi[BR2_FAST_ELEM_ITEM0] >= 0 || p->overwrite_src[sl] >= 0)
+                h->has_extra = true;
+        }
     }
 #undef UP
     {
@@ -261,7 +266,13 @@ int br2_select_kernel(br2_handle h, int32_t variant) {
     if (variant == 0)
         smem = sizeof(double) * (30 * S + 9 * (size_t)h->t.n_joints + 32);
     else
-        smem = sizeof(double) * (46 * (size_t)pick.threads + 9 * (size_t)(pick.threads + 8) + 9 * (size_t)BR2_FAST_MAX_EXTRA);
+    {
+        // fixed part: 45 T doubles + two [3][T+8] accumulators + O1 (T ints); tail (omega, extra-joint rows,
+        // 14 T ints of bookkeeping) only for assemblies with extra joints / director overwrites
+        const size_t Tn = (size_t)pick.threads;
+        smem = sizeof(double) * (45 * Tn + 6 * (Tn + 8) + Tn / 2);
+        if (h->has_extra) smem += sizeof(double) * (3 * Tn + 9 * (size_t)BR2_FAST_MAX_EXTRA + 7 * Tn);
+    }
     if (smem > 227 * 1024)
         return fail(BR2_ELIMIT, "assembly needs " + std::to_string(smem) + " B of shared memory per CTA (max 232448)");
     CUDA_TRY(cudaFuncSetAttribute((const void *)pick.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -32,8 +32,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
     double *X = sm;               // [3][T] node position
     double *Vs = X + 3 * T;       // [3][T] node velocity
     double *Qs = Vs + 3 * T;      // [9][T] element director
-    double *Ws = Qs + 9 * T;      // [3][T] element omega (only published when a joint overwrites directors)
-    double *Ls = Ws + 3 * T;      // [T] length
+    double *Ls = Qs + 9 * T;      // [T] length
     double *Rs = Ls + T;          // [T] radius
     double *RSE = Rs + T;         // [T] 1/sqrt(dilatation)
     double *Sk = RSE + T;         // [3][T] Q^T n_L / e
@@ -43,11 +42,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
     double *TA = JD + 7 * T;      // [3][T] actuation torque at full ramp
     double *LT = TA + 3 * T;      // [3][T] thread-private stash: shear couple + transport terms (P2 -> P4)
     double *TO = LT + 3 * T;      // [3][T] thread-private stash: torque of my joint on my element (P3 -> P4)
-    double *EFo = TO + 3 * T;     // [3][TP] -F/2 of the joint this element owns (it is rod two)
-    double *EFp = EFo + 3 * TP;   // [3][TP] +F/2 of the joint in which this element is rod one
-    double *TQp = EFp + 3 * TP;   // [3][TP] torque of that joint on this element (rod one side)
-    double *JF = TQp + 3 * TP;    // [3][TJ] half force of extra joints
-    double *JT = JF + 3 * TJ;     // [2][3][TJ] torques of extra joints (rod one / rod two)
+    double *MS = TO + 3 * T;      // [2][T] node mass and its reciprocal
+    double *EFo = MS + 2 * T;     // [3][TP] -F/2 of the joint this element owns (it is rod two); row T = 0
+    double *TQp = EFo + 3 * TP;   // [3][TP] torque on this element of the joint in which it is rod one; row T = trash
+    int *O1 = (int *)(TQp + 3 * TP);  // [T] slot of the element that owns the joint in which this element is rod one (else T)
+    // tail, only allocated (by the host) for assemblies with "extra" joints / director overwrites
+    double *Ws = TQp + 3 * TP + T / 2;  // [3][T] element omega
+    double *JF = Ws + 3 * T;            // [3][TJ] half force of extra joints
+    double *JT = JF + 3 * TJ;           // [2][3][TJ] torques of extra joints (rod one / rod two)
+    int *XI = (int *)(JT + 6 * TJ);     // [14][T] per-thread extra-joint bookkeeping
 
     const DevTables &tb = p.t;
     const int S = tb.n_slots;
@@ -68,24 +71,21 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
     const int *fi = tb.fast_i + sc * BR2_FAST_NI;
     const int flags = valid ? fi[BR2_FAST_FLAGS] : 0;
     const int own_joint = valid ? fi[BR2_FAST_OWN_JOINT] : -1;
-    const int extra_joint = valid ? fi[BR2_FAST_EXTRA_JOINT] : -1;
-    const int extra_row = fi[BR2_FAST_EXTRA_ID];   // compact row of that joint in JF / JT
-    const int softfix_row = valid ? fi[BR2_FAST_SOFTFIX_ROW] : -1;
-    const int ow_src = valid ? tb.overwrite_src[sc] : -1;
-    // a thread without a joint evaluates a dummy one against itself and dumps the result in the trash row
+    // a thread without a joint evaluates a dummy one against a neighbour (zero descriptor, result masked / trashed)
     const bool has_joint = own_joint >= 0;
     const int s1 = has_joint ? tb.joint_i[own_joint * BR2_J_NI + BR2_J_S1] : ((s + 1 < T) ? s : s - 1);
-    const int jdst = has_joint ? s1 : T;   // where the rod-one side of my joint accumulates
-    const int odst = has_joint ? s : T;    // where my own (rod-two) side accumulates
+    const int jdst = has_joint ? s1 : T;   // TQp row the rod-one side of my joint goes to (row T = trash)
 
     // ---- per-slot constants ---------------------------------------------------------------
     const double *FCg = tb.fast_c + sc;
 #define FC(idx) (kUniform ? p.uni[(idx)] : __ldg(FCg + (long long)(idx) * S))
-    const double mass = tb.slot_c[(long long)BR2_SC_MASS * S + sc];
-    const double inv_mass = 1.0 / mass;
 
-    // joint descriptor, actuation torque, accumulators -> shared memory (written once per launch)
+    // joint descriptor, actuation torque, masses, accumulators -> shared memory (written once per launch)
+    int any_extra_local;
     {
+        const double mass = tb.slot_c[(long long)BR2_SC_MASS * S + sc];
+        MS[s] = mass;
+        MS[T + s] = 1.0 / mass;
         const double *jd = tb.joint_d + (has_joint ? own_joint : 0) * BR2_J_ND;
 #pragma unroll
         for (int i = 0; i < 7; ++i) JD[i * T + s] = has_joint ? jd[3 + i] : 0.0;
@@ -99,21 +99,34 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
         }
 #pragma unroll
         for (int i = 0; i < 3; ++i) TA[i * T + s] = ta[i];
-        for (int j = s; j < 9 * TP + 9 * TJ; j += T) EFo[j] = 0.0;  // EFo, EFp, TQp, JF, JT are contiguous
+        for (int j = s; j < 6 * TP; j += T) EFo[j] = 0.0;  // EFo and TQp are contiguous
+        O1[s] = T;
+        const int extra_joint = valid ? fi[BR2_FAST_EXTRA_JOINT] : -1;
+        const int ow = valid ? tb.overwrite_src[sc] : -1;
+        int cnt = 0;
+        if (valid)
+            for (int q = 0; q < BR2_FAST_NODE_ITEMS; ++q) cnt += fi[BR2_FAST_NODE_ITEM0 + q] >= 0;
+        any_extra_local = (extra_joint >= 0) | (ow >= 0) | (cnt > 0) | (valid && fi[BR2_FAST_ELEM_ITEM0] >= 0);
     }
-    // extra-joint gather lists (tip-to-base joints etc.): rare, kept as (count, packed items)
-    unsigned x_node_items[BR2_FAST_NODE_ITEMS / 2];
-    int x_node_count = 0;
+    const bool any_extra = __syncthreads_or(any_extra_local) != 0;  // CTA-uniform; also orders the O1 initialisation
+    if (has_joint) O1[s1] = s;
+    if (any_extra) {  // the tail of the shared-memory layout exists only then (host sizes it)
+        XI[0 * T + s] = valid ? fi[BR2_FAST_EXTRA_JOINT] : -1;
+        XI[1 * T + s] = fi[BR2_FAST_EXTRA_ID];
+        XI[2 * T + s] = valid ? tb.overwrite_src[sc] : -1;
+        int cnt = 0;
 #pragma unroll
-    for (int q = 0; q < BR2_FAST_NODE_ITEMS; q += 2) {
-        const int i0 = fi[BR2_FAST_NODE_ITEM0 + q], i1 = fi[BR2_FAST_NODE_ITEM0 + q + 1];
-        x_node_items[q / 2] = (unsigned)(i0 & 0xFFFF) | ((unsigned)(i1 & 0xFFFF) << 16);
-        x_node_count += (i0 >= 0) + (i1 >= 0);
+        for (int q = 0; q < BR2_FAST_NODE_ITEMS; ++q) {
+            const int item = valid ? fi[BR2_FAST_NODE_ITEM0 + q] : -1;
+            XI[(4 + q) * T + s] = item;
+            cnt += item >= 0;
+        }
+        XI[3 * T + s] = cnt;
+        XI[12 * T + s] = valid ? fi[BR2_FAST_ELEM_ITEM0] : -1;
+        XI[13 * T + s] = valid ? fi[BR2_FAST_ELEM_ITEM0 + 1] : -1;
+        for (int j = s; j < 9 * TJ; j += T) JF[j] = 0.0;  // JF and JT are contiguous
     }
-    if (!valid) x_node_count = 0;
-    const int x_elem_item0 = valid ? fi[BR2_FAST_ELEM_ITEM0] : -1, x_elem_item1 = valid ? fi[BR2_FAST_ELEM_ITEM0 + 1] : -1;
-    const bool any_extra =
-        __syncthreads_or((extra_joint >= 0) | (ow_src >= 0) | (x_node_count > 0) | (x_elem_item0 >= 0)) != 0;
+    __syncthreads();
 
     // ---- state in registers -------------------------------------------------------------
     // field offsets inside the rod's block (include/br2cuda.h), derived where needed from n
@@ -163,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
     const int sn = (s + 1 < T) ? s + 1 : s;      // next slot (the block's last thread reads itself; result masked)
 
     double time = p.t0;  // time at the start of the current step
-    const long long last_step = p.n_steps - 1;
+    const int n_steps = (int)p.n_steps;  // the host splits longer runs
     bool bad = false;    // some series left its validity range (or produced a NaN)
 
     // leading kinematic half step of the first step; every later one is fused with the trailing half
@@ -172,8 +185,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
     for (int i = 0; i < 3; ++i) x[i] = fma(hx, v[i], x[i]);
     bad |= rotate_directors(Q, hq * w[0], hq * w[1], hq * w[2], 1.0);
 
-    for (long long step = 0; step < p.n_steps; ++step) {
-        const bool last = (step == last_step);
+    for (int step = 0; step < n_steps; ++step) {
+        const bool last = (step == n_steps - 1);
         // =============================== P1: publish the half-stepped state ================
         const double time_mid = time + hdt;
 #pragma unroll
@@ -321,16 +334,17 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 const double hF = 0.5 * fma(coef, dvec[i], mag * cd[i]);
-                EFp[i * TP + jdst] = hF;
-                EFo[i * TP + odst] = -hF;
+                EFo[i * TP + s] = has_joint ? -hF : 0.0;   // the rod-one element picks up +hF through O1
                 TQp[i * TP + jdst] = fma(Qs[(3 * i) * T + s1], t1[0], fma(Qs[(3 * i + 1) * T + s1], t1[1], Qs[(3 * i + 2) * T + s1] * t1[2]));
                 TO[i * T + s] = fma(Q[3 * i], t2[0], fma(Q[3 * i + 1], t2[1], Q[3 * i + 2] * t2[2]));
             }
         }
         // one further joint per thread (tip-to-base joints, or surface joints that did not fit the
         // "own" pattern), both sides read from shared memory, descriptor from the generic tables
+        const int extra_joint = any_extra ? XI[0 * T + s] : -1;
         if (extra_joint >= 0) {
             const int j = extra_joint;
+            const int extra_row = XI[1 * T + s];
             const int *ji = tb.joint_i + j * BR2_J_NI;
             const double *jd = tb.joint_d + j * BR2_J_ND;
             const int type = ji[BR2_J_TYPE], e1 = ji[BR2_J_S1], e2 = ji[BR2_J_S2], q1 = ji[BR2_J_Q1], q2 = ji[BR2_J_Q2];
@@ -410,6 +424,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
         }
         // tip-to-base joints overwrite the downstream base element's director / omega during
         // synchronize; sources are start-of-synchronize values, still in Qs / Ws
+        const int ow_src = any_extra ? XI[2 * T + s] : -1;
         if (ow_src >= 0) {
 #pragma unroll
             for (int i = 0; i < 9; ++i) Q[i] = Qs[i * T + ow_src];
@@ -421,7 +436,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
         // =============================== P4: assemble, dynamic step =========================
         {
             double f_int[3], t_int[3], f_ext[3], t_ext[3];
-            const double ramp = fmin(1.0, time_mid * tb.act_inv_ramp);
+            const double ramp_raw = time_mid * tb.act_inv_ramp;
+            const double ramp = (ramp_raw < 1.0) ? ramp_raw : 1.0;
+            const double mass = MS[s], inv_mass = MS[T + s];
+            const int o1s = O1[s], o1p = O1[sp];
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 // own values come back from shared memory rather than staying in registers across the barriers
@@ -430,31 +448,29 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
                 const double sC = fma(prev_mask, Cv[i * T + sp], Cv[i * T + s]);
                 t_int[i] = dA + fma(0.5, sC, LT[i * T + s]);
                 // joints: node k collects the half forces of elements k and k-1 of its rod
-                const double fe = EFo[i * TP + s] + EFp[i * TP + s];
-                const double fp = EFo[i * TP + sp] + EFp[i * TP + sp];
+                // element e carries -hF of the joint it owns and +hF of the joint owned by element O1[e]
+                const double fe = EFo[i * TP + s] - EFo[i * TP + o1s];
+                const double fp = EFo[i * TP + sp] - EFo[i * TP + o1p];
                 f_ext[i] = fma(FC(BR2_FC_GRAVITY + i), mass, fma(prev_mask, fp, fe));
                 t_ext[i] = fma(TA[i * T + s], ramp, TO[i * T + s] + TQp[i * TP + s]);
             }
             if (any_extra) {  // CTA-uniform: only assemblies with tip-to-base (or otherwise unowned) joints
+                const int x_node_count = XI[3 * T + s];
+                for (int q = 0; q < x_node_count; ++q) {
+                    const int item = XI[(4 + q) * T + s];
+                    const double sgn = (item & 1) ? -1.0 : 1.0;
+                    const int j = item >> 1;
 #pragma unroll
-                for (int q = 0; q < BR2_FAST_NODE_ITEMS; ++q) {
-                    if (q < x_node_count) {
-                        const unsigned item = (x_node_items[q >> 1] >> ((q & 1) * 16)) & 0xFFFFu;
-                        const double sgn = (item & 1u) ? -1.0 : 1.0;
-                        const int j = (int)(item >> 1);
+                    for (int i = 0; i < 3; ++i) f_ext[i] = fma(sgn, JF[i * TJ + j], f_ext[i]);
+                }
 #pragma unroll
-                        for (int i = 0; i < 3; ++i) f_ext[i] = fma(sgn, JF[i * TJ + j], f_ext[i]);
+                for (int e = 0; e < 2; ++e) {
+                    const int item = XI[(12 + e) * T + s];
+                    if (item >= 0) {
+                        const int base = (item & 1) * 3 * TJ + (item >> 1);
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) t_ext[i] += JT[base + i * TJ];
                     }
-                }
-                if (x_elem_item0 >= 0) {
-                    const int base = (x_elem_item0 & 1) * 3 * TJ + (x_elem_item0 >> 1);
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) t_ext[i] += JT[base + i * TJ];
-                }
-                if (x_elem_item1 >= 0) {
-                    const int base = (x_elem_item1 & 1) * 3 * TJ + (x_elem_item1 >> 1);
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) t_ext[i] += JT[base + i * TJ];
                 }
             }
             // dynamic step, damper, rate constraints
@@ -464,7 +480,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
             const double dil4 = len4 * FC(BR2_FC_INV_REST_LEN);
             const double strain = (dil4 - 1.0) * elem_mask;
             const double e0 = strain * FC(BR2_FC_LN_CR), e1 = strain * FC(BR2_FC_LN_CR + 1), e2 = strain * FC(BR2_FC_LN_CR + 2);
-            bad |= !(fmax(fabs(e0), fmax(fabs(e1), fabs(e2))) <= 0.02);
+            bad |= !(e0 * e0 <= 4e-4) | !(e1 * e1 <= 4e-4) | !(e2 * e2 <= 4e-4);  // |e| <= 0.02
             damp[0] = FC(BR2_FC_CR) * exp_small(e0) * keep_w;
             damp[1] = (FC(BR2_FC_LN_CR + 1) == FC(BR2_FC_LN_CR))   // I1 == I2 (round cross-section)
                           ? damp[0]
@@ -479,6 +495,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
             }
             if (last && valid) {
                 // quantities the reference's callbacks report (free_simulator.py:56-72), as of this step
+                const int softfix_row = fi[BR2_FAST_SOFTFIX_ROW];
                 if (softfix_row >= 0) {
                     // FreeBaseEndSoftFixed's spring acts on node 0 in both constrain_values calls of the step;
                     // it never changes the motion (node 0's rates are zeroed) and is only visible here.

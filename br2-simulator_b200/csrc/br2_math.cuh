@@ -64,14 +64,12 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
 // t = theta^2, for t <= 0.01 (|theta| <= 0.1 rad per step, i.e. |omega| <= 5e3 rad/s at dt=2e-5).
 // Truncation error < 3e-18.
 __device__ __forceinline__ void sinc_cosc_small(double t, double &sinc, double &cosc) {
-    double s = kSincC[0], c = kCoscC[0];
-#pragma unroll
-    for (int i = 1; i < 6; ++i) {
-        s = fma(s, t, kSincC[i]);
-        c = fma(c, t, kCoscC[i]);
-    }
-    sinc = s;
-    cosc = c;
+    // Estrin: (c5 + c4 t) + t^2 (c3 + c2 t) + t^4 (c1 + c0 t), coefficients stored highest power first
+    const double t2 = t * t, t4 = t2 * t2;
+    const double s01 = fma(kSincC[4], t, kSincC[5]), s23 = fma(kSincC[2], t, kSincC[3]), s45 = fma(kSincC[0], t, kSincC[1]);
+    const double c01 = fma(kCoscC[4], t, kCoscC[5]), c23 = fma(kCoscC[2], t, kCoscC[3]), c45 = fma(kCoscC[0], t, kCoscC[1]);
+    sinc = fma(s45, t4, fma(s23, t2, s01));
+    cosc = fma(c45, t4, fma(c23, t2, c01));
 }
 
 // Row-director Rodrigues update for `mult` consecutive kinematic half steps with the same rotation
