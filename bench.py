@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=4096, help="instances per GPU")
     ap.add_argument("--substeps", type=int, default=2000, help="integration steps per launch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", type=int, default=-1, help="force a kernel variant (0 generic, 1/2 fast, 3 tile); -1 = automatic")
     return ap.parse_args()
 
 
@@ -222,6 +223,8 @@ def run_ours(args, world, rank, local):
     env.reset(ROD_DB, os.path.join(DATA, w["assembly"]), gravity=w["gravity"])
     env.simulator._callback_ops = []  # stepping only; capture is a separate (next-row) path
     engine = env.engine
+    if args.variant >= 0:
+        engine.select_kernel(args.variant)
     names = ["action1", "action2", "action3"]
     action_host = {n: torch.from_numpy(pressures[i].copy()).pin_memory().numpy() for i, n in enumerate(names)}
     env.assy.set_actuation(action_host)
@@ -319,7 +322,7 @@ def run_ours(args, world, rank, local):
         "e2e": {"value": e2e_value, "unit": "rod-element-steps/s", "h2d_bytes_per_step": int(3 * B * 8),
                 "d2h_bytes_per_step": int(B * engine.words * 8), "steps": e2e_steps},
         "gpu_launches": launches,
-        "kernel": dict(info, name="br2_step_fast_kernel" if info["variant"] else "br2_step_generic_kernel",
+        "kernel": dict(info, name=("br2_step_generic_kernel", "br2_step_fast_kernel", "br2_step_fast_kernel", "br2_step_tile_kernel")[info["variant"]],
                        launch_ms=per_launch_ms, exact_path_replays=engine.replay_count(),
                        launches_per_step="fast kernel + exact-path replay pass (exits at once unless flagged)"
                        if info["variant"] else "generic kernel"),

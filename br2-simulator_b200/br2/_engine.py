@@ -109,7 +109,7 @@ class Engine:
         _native.check(self.lib.br2_kernel_info(self.handle, *[ctypes.byref(v) for v in vals]))
         keys = ("registers", "smem_bytes", "threads", "blocks_per_sm", "sm_count", "variant")
         info = dict(zip(keys, (v.value for v in vals)))
-        info["variant_name"] = ("generic", "fast", "fast-uniform")[info["variant"]]
+        info["variant_name"] = ("generic", "fast", "fast-uniform", "tile")[info["variant"]]
         return info
 
     def replay_count(self):
@@ -119,7 +119,7 @@ class Engine:
         return count.value
 
     def select_kernel(self, variant):
-        """0 generic, 1 fast (per-slot constants), 2 fast (uniform constants), -1 automatic."""
+        """0 generic, 1 fast (per-slot constants), 2 fast (uniform constants), 3 tile (several slots per thread), -1 automatic."""
         _native.check(self.lib.br2_select_kernel(self.handle, int(variant)))
         self._variant = self.kernel_info()["variant"]
 

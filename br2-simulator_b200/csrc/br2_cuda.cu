@@ -26,6 +26,7 @@
 #include "br2_fast.cuh"
 #include "br2_generic.cuh"
 #include "br2_tables.cuh"
+#include "br2_tile.cuh"
 
 using br2::DevTables;
 using br2::StepParams;
@@ -77,6 +78,20 @@ struct KernelChoice {
     kernel_fn fn;
 };
 
+#ifndef BR2_TILE_C
+#define BR2_TILE_C 2
+#endif
+#ifndef BR2_TILE_MB64
+#define BR2_TILE_MB64 5
+#endif
+// variant 3: tile kernel (BR2_TILE_C slots per thread, uniform constants); `threads` = CTA size
+const KernelChoice kTileKernels[] = {
+    {64, br2::br2_step_tile_kernel<BR2_TILE_C, 64, BR2_TILE_MB64>},
+    {128, br2::br2_step_tile_kernel<BR2_TILE_C, 128, 2>},
+    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 1>},
+    {256, br2::br2_step_tile_kernel<BR2_TILE_C, 256, 1>},
+};
+
 // variant 0: generic, 1: fast with per-slot constants, 2: fast with uniform constants
 const KernelChoice kKernels[3][6] = {
     {{128, br2::br2_step_generic_kernel<128, 4>}, {256, br2::br2_step_generic_kernel<256, 2>},
@@ -105,7 +120,9 @@ struct br2_handle_s {
     size_t replay_smem = 0;
     int variant = 0;        // 0 generic, 1 fast, 2 fast uniform
     int auto_variant = 0;   // what br2_create picked
-    bool fast_ok = false, fast_uniform = false, has_extra = false;
+    bool fast_ok = false, fast_uniform = false, has_extra = false, tile_ok = false;
+    br2::TilePlan tile{};
+    std::string tile_why;
     double uni[BR2_FC_COUNT] = {0};
     int *status = nullptr;            // [batch] fast-kernel validity flags (library-owned)
     long long status_batch = 0;
@@ -164,6 +181,65 @@ int validate(const br2_program *p) {
             if (ji[q] < 0 || ji[q] + 1 >= p->n_slots) return fail(BR2_EINVAL, "joint slot out of range");
     }
     return BR2_OK;
+}
+
+// Plan of the thread-coarsened kernel (br2_tile.cuh), or the reason the assembly does not qualify.
+bool make_tile_plan(const br2_program *p, bool has_extra, int C, br2::TilePlan *plan, std::string *why) {
+    *plan = br2::TilePlan{};
+    plan->C = C;
+    if (!p->fast_ok || !p->fast_uniform) return *why = "assembly constants are not uniform", false;
+    if (has_extra) return *why = "joints outside the ring pattern (tip-to-base joints)", false;
+    if (p->n_rods > BR2_TILE_MAX_RODS) return *why = "too many rods", false;
+    const size_t S = (size_t)p->n_slots;
+    int threads = 0;
+    for (int r = 0; r < p->n_rods; ++r) {
+        plan->rod_t0[r] = threads;
+        threads += (p->rod_i[r * BR2_ROD_NI + BR2_ROD_N] + 1 + C - 1) / C;
+        plan->partner[r] = plan->owner[r] = -1;
+    }
+    for (int r = p->n_rods; r <= BR2_TILE_MAX_RODS; ++r) plan->rod_t0[r] = threads;
+    auto close = [](double a, double b, double tol) { return fabs(a - b) <= tol; };
+    for (int r = 0; r < p->n_rods; ++r) {
+        const int32_t *ri = p->rod_i + r * BR2_ROD_NI;
+        const int n = ri[BR2_ROD_N], slot0 = ri[BR2_ROD_SLOT0];
+        int owned = 0;
+        for (int e = 0; e < n; ++e) {
+            const int j = p->fast_i[(size_t)(slot0 + e) * BR2_FAST_NI + BR2_FAST_OWN_JOINT];
+            if (j < 0) continue;
+            ++owned;
+            const int32_t *ji = p->joint_i + (size_t)j * BR2_J_NI;
+            const double *jd = p->joint_d + (size_t)j * BR2_J_ND;
+            const int r1 = p->slot_rod[ji[BR2_J_S1]];
+            const int e1 = ji[BR2_J_S1] - p->rod_i[r1 * BR2_ROD_NI + BR2_ROD_SLOT0];
+            if (ji[BR2_J_S2] != slot0 + e || e1 != e) return *why = "a surface joint connects different element indices", false;
+            if (p->rod_i[r1 * BR2_ROD_NI + BR2_ROD_N] != n) return *why = "joined rods differ in element count", false;
+            if (owned == 1) {
+                if (plan->owner[r1] >= 0) return *why = "a rod is rod one of two rods", false;
+                plan->partner[r] = r1;
+                plan->owner[r1] = r;
+                for (int i = 0; i < 3; ++i) {
+                    plan->jd[r][i] = jd[6 + i];       // dv2: this rod's side
+                    plan->jd[r1][4 + i] = jd[3 + i];  // dv1: the partner's side
+                }
+                plan->jd[r][3] = plan->jd[r1][7] = 0.5 * jd[9];
+            } else {
+                if (plan->partner[r] != r1) return *why = "a rod owns joints with two rods", false;
+                bool same = close(0.5 * jd[9], plan->jd[r][3], 1e-16);
+                for (int i = 0; i < 3; ++i)
+                    same = same && close(jd[6 + i], plan->jd[r][i], 1e-15) && close(jd[3 + i], plan->jd[r1][4 + i], 1e-15);
+                if (!same) return *why = "joint descriptors vary along a rod", false;
+            }
+            // the per-joint parameters must be the uniform ones the kernel reads from the constant bank
+            const double *fc = p->fast_c;
+            if (jd[0] != fc[(size_t)BR2_FC_JK * S] || jd[1] != fc[(size_t)BR2_FC_JNU * S] || jd[2] != fc[(size_t)BR2_FC_JKREP * S])
+                return *why = "joint parameters are not uniform", false;
+        }
+        if (owned != 0 && owned != n) return *why = "only some elements of a rod own a joint", false;
+    }
+    const double *fc = p->fast_c;
+    const double l0 = fc[(size_t)BR2_FC_LN_CR * S], l1 = fc[(size_t)(BR2_FC_LN_CR + 1) * S], l2 = fc[(size_t)(BR2_FC_LN_CR + 2) * S];
+    plan->round_section = (l0 == l1 && fabs(l0 - 2.0 * l2) <= 1e-13 * fabs(l0)) ? 1 : 0;
+    return true;
 }
 
 }  // namespace
@@ -237,7 +313,8 @@ int br2_create(const br2_program *p, int device, br2_handle *out) {
             return fail(BR2_ECUDA, std::string("replay counter: ") + cudaGetErrorString(e));
         }
     }
-    h->auto_variant = h->fast_ok ? (h->fast_uniform ? 2 : 1) : 0;
+    h->tile_ok = h->fast_ok && make_tile_plan(p, h->has_extra, BR2_TILE_C, &h->tile, &h->tile_why);
+    h->auto_variant = h->tile_ok ? 3 : h->fast_ok ? (h->fast_uniform ? 2 : 1) : 0;
     rc = br2_select_kernel(h, -1);
     if (rc != BR2_OK) {
         br2_destroy(h);
@@ -250,21 +327,33 @@ int br2_create(const br2_program *p, int device, br2_handle *out) {
 int br2_select_kernel(br2_handle h, int32_t variant) {
     if (!h) return fail(BR2_EINVAL, "br2_select_kernel: NULL handle");
     if (variant < 0) variant = h->auto_variant;
-    if (variant > 2) return fail(BR2_EINVAL, "br2_select_kernel: unknown variant");
+    if (variant > 3) return fail(BR2_EINVAL, "br2_select_kernel: unknown variant");
+    if (variant == 3 && !h->tile_ok)
+        return fail(BR2_EINVAL, "br2_select_kernel: assembly does not qualify for the tile kernel: " + h->tile_why);
     if (variant >= 1 && !h->fast_ok) return fail(BR2_EINVAL, "br2_select_kernel: assembly does not qualify for the fast kernel");
     if (variant == 2 && !h->fast_uniform) return fail(BR2_EINVAL, "br2_select_kernel: assembly constants are not uniform");
     CUDA_TRY(cudaSetDevice(h->device));
     const size_t S = (size_t)h->t.n_slots;
     KernelChoice pick{0, nullptr};
-    for (const KernelChoice &kc : kKernels[variant])
-        if (kc.threads >= h->t.n_slots) {
-            pick = kc;
-            break;
-        }
+    if (variant == 3) {
+        for (const KernelChoice &kc : kTileKernels)
+            if (kc.threads >= h->tile.rod_t0[h->t.n_rods]) {
+                pick = kc;
+                break;
+            }
+    } else {
+        for (const KernelChoice &kc : kKernels[variant])
+            if (kc.threads >= h->t.n_slots) {
+                pick = kc;
+                break;
+            }
+    }
     if (!pick.fn) return fail(BR2_ELIMIT, "no kernel variant holds this many slots");
     size_t smem;
     if (variant == 0)
         smem = sizeof(double) * (30 * S + 9 * (size_t)h->t.n_joints + 32);
+    else if (variant == 3)
+        smem = sizeof(double) * (size_t)br2::TileSmem<BR2_TILE_C, 0>::WORDS * (size_t)(pick.threads + 1);
     else
     {
         // fixed part: 45 T doubles + two [3][T+8] accumulators + O1 (T ints); tail (omega, extra-joint rows,
@@ -367,6 +456,7 @@ int br2_step(br2_handle h, int64_t n_steps, double t0, double dt, void *stream, 
     sp.t0 = t0;
     sp.dt = dt;
     memcpy(sp.uni, h->uni, sizeof(sp.uni));
+    sp.tile = h->tile;
     sp.status = h->status;
     sp.replays = h->replays;
     sp.only_flagged = 0;

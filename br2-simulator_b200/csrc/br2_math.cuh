@@ -139,4 +139,96 @@ __device__ __forceinline__ double exp_small(double d) {
     return fma(p, d, 1.0);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Second generation of the helpers (tile kernel, br2_tile.cuh): shorter series with tighter validity
+// ranges -- still far outside anything a BR2 assembly does in one 2e-5 s step -- and guards evaluated at
+// hardware-seed accuracy where they only multiply 1e-14.
+// ---------------------------------------------------------------------------------------------
+__constant__ double kSinc4[5] = {1.0 / 362880.0, -1.0 / 5040.0, 1.0 / 120.0, -1.0 / 6.0, 1.0};
+__constant__ double kCosc4[5] = {1.0 / 3628800.0, -1.0 / 40320.0, 1.0 / 720.0, -1.0 / 24.0, 0.5};
+__constant__ double kExp5[5] = {1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0};
+__constant__ double kMisc2[6] = {2e-3, 0.03, 2.5e-5, 0.01, 0.25, 0.3125};
+#define BR2_TPHI_MAX kMisc2[0]
+#define BR2_Y_MAX kMisc2[1]
+#define BR2_E2_MAX kMisc2[2]
+
+// sinc / cosc of theta as functions of t = theta^2 <= 2e-3 (|theta| <= 0.0447 rad in one step); degree 4,
+// truncation < t^5 / 11! = 8e-22.
+__device__ __forceinline__ void sinc_cosc_tiny(double t, double &sinc, double &cosc) {
+    double s = kSinc4[0], c = kCosc4[0];
+#pragma unroll
+    for (int i = 1; i < 5; ++i) {
+        s = fma(s, t, kSinc4[i]);
+        c = fma(c, t, kCosc4[i]);
+    }
+    sinc = s;
+    cosc = c;
+}
+
+// Q <- R Q for `mult` (1 or 2) consecutive kinematic half steps with rotation vector u = hdt * w each.
+// Same rotation as rotate_directors(); the reference's guard g = |u| / (|u| + 1e-14) = 1 - 1e-14 / (|u| + 1e-14)
+// only needs |u| to seed accuracy.  hmult = mult * hdt.  Returns true when the angle left the series' range.
+__device__ __forceinline__ bool rotate_directors_tiny(double (&Q)[9], const double (&w)[3], double hdt, double hmult) {
+    const double tw = fma(w[0], w[0], fma(w[1], w[1], w[2] * w[2]));
+    const double tt = tw + BR2_TINY;
+    const double absu = hdt * (tt * seed_rsqrt(tt));
+    const double g = fma(-BR2_EPS14, seed_rcp(absu + BR2_EPS14), 1.0);
+    const double hm = hmult * g;
+    const double u0 = hm * w[0], u1 = hm * w[1], u2 = hm * w[2];
+    const double tphi = (hm * hm) * tw;  // phi^2
+    double sinc, cosc;
+    sinc_cosc_tiny(tphi, sinc, cosc);
+    const double a0 = sinc * u0, a1 = sinc * u1, a2 = sinc * u2;
+    const double b0 = cosc * u0, b1 = cosc * u1, b2 = cosc * u2;
+    const double R00 = fma(-b1, u1, fma(-b2, u2, 1.0));
+    const double R11 = fma(-b0, u0, fma(-b2, u2, 1.0));
+    const double R22 = fma(-b0, u0, fma(-b1, u1, 1.0));
+    const double R01 = fma(b0, u1, a2), R10 = fma(b0, u1, -a2);
+    const double R02 = fma(b0, u2, -a1), R20 = fma(b0, u2, a1);
+    const double R12 = fma(b1, u2, a0), R21 = fma(b1, u2, -a0);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const double q0 = Q[c], q1 = Q[3 + c], q2 = Q[6 + c];
+        Q[c] = fma(R00, q0, fma(R01, q1, R02 * q2));
+        Q[3 + c] = fma(R10, q0, fma(R11, q1, R12 * q2));
+        Q[6 + c] = fma(R20, q0, fma(R21, q1, R22 * q2));
+    }
+    return !(tphi <= BR2_TPHI_MAX);
+}
+
+// theta / sin(theta + 1e-14) from y = 1 - cos(theta) <= 0.03 (neighbouring elements rotated by <= 0.245 rad):
+// degree-9 series in z = y/2 (two Horner chains in z^2; truncation 0.27 z^10 < 2e-19) times the guard
+// 1 - 1e-14 cos/sin with 1/sin = rsqrt(y (2 - y)) from the hardware seed.
+__device__ __forceinline__ double logmap_ratio_tiny(double y) {
+    const double z = 0.5 * y, z2 = z * z;
+    double pe = kLogC[8], po = kLogC[9];
+    pe = fma(pe, z2, kLogC[6]);
+    po = fma(po, z2, kLogC[7]);
+    pe = fma(pe, z2, kLogC[4]);
+    po = fma(po, z2, kLogC[5]);
+    pe = fma(pe, z2, kLogC[2]);
+    po = fma(po, z2, kLogC[3]);
+    pe = fma(pe, z2, kLogC[0]);
+    po = fma(po, z2, kLogC[1]);
+    const double f = fma(po, z, pe);
+    const double inv_sin = seed_rsqrt(fma(-y, y, y + y));
+    const double guard = fma(fma(BR2_EPS14, y, -BR2_EPS14), inv_sin, 1.0);
+    return f * guard;
+}
+
+// exp(d) for |d| <= 5e-3; degree 5, truncation d^6 / 720 < 2.2e-17.
+__device__ __forceinline__ double exp_tiny(double d) {
+    double p = kExp5[0];
+#pragma unroll
+    for (int i = 1; i < 5; ++i) p = fma(p, d, kExp5[i]);
+    return fma(p, d, 1.0);
+}
+
+// sqrt(x) for x >= 0 to ~2^-40 relative (seed + one Newton step); 0 for x = 0.
+__device__ __forceinline__ double sqrt_mid(double x) {
+    const double y = seed_rsqrt(x + BR2_TINY);
+    const double s = x * y;
+    return fma(0.5 * y, fma(-s, s, x), s);
+}
+
 }  // namespace br2

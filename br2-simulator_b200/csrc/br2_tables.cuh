@@ -28,6 +28,17 @@ struct DevTables {
     double act_inv_ramp;    // 1 / ramp_up_time shared by every actuation row
 };
 
+// Thread-coarsened ("tile") kernel: every thread owns C consecutive slots of one rod (br2_tile.cuh).
+#define BR2_TILE_MAX_RODS 12
+struct TilePlan {
+    int C;                                  // slots per thread
+    int round_section;                      // ln c_r1 = ln c_r2 = 2 ln c_r3: one exponential per element and step
+    int rod_t0[BR2_TILE_MAX_RODS + 1];      // first thread of each rod; [n_rods] = threads in use
+    int partner[BR2_TILE_MAX_RODS];         // rod whose elements are rod one of the joints this rod's elements own, or -1
+    int owner[BR2_TILE_MAX_RODS];           // rod whose elements own the joints in which this rod's elements are rod one, or -1
+    double jd[BR2_TILE_MAX_RODS][8];        // {dv2[3], offset/2} of the joints the rod owns, {dv1[3], offset/2} as rod one
+};
+
 struct StepParams {
     DevTables t;
     double *state;
@@ -39,6 +50,7 @@ struct StepParams {
     int only_flagged;   // generic kernel: integrate only instances whose status is set, then clear it
     unsigned long long *replays;  // counts instance-launches redone by the exact path
     double uni[BR2_FC_COUNT];  // uniform copy of fast_c (all element slots identical), constant bank
+    TilePlan tile;
 };
 
 }  // namespace br2

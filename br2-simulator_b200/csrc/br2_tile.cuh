@@ -1,0 +1,578 @@
+// br2_tile.cuh -- the shared-memory-lean performance kernel for ring-structured BR2 assemblies.
+//
+// The first fast kernel (br2_fast.cuh, one slot per thread) turned out to be bound by the SM's shared-memory
+// crossbar (128 B/clk): 152 eight-byte accesses per slot and step = 77 % of the crossbar while the fp64 pipe
+// sat at 57 % (profiles/r01_ncu_fast_kernel_c.txt).  This kernel gives every thread C CONSECUTIVE slots of one
+// rod (node k, element k, Voronoi cell k for k = k0 .. k0+C-1):
+//   * neighbour differences inside a thread's run come from registers; only the run's first node / element
+//     is published for the previous thread, only the run's last shear force / bending couple for the next;
+//   * a surface joint is evaluated once, by its rod-two element; the rod-one element publishes what the
+//     joint needs from it (sum of its two nodes' positions and velocities, its world-frame lever arm and
+//     arm length: 10 doubles) instead of its director, nodes and radius (23 doubles), and picks up the
+//     force afterwards to form its own torque, so nobody reads a partner's director at all;
+//   * forces go into the node velocities as soon as they exist (the update is linear in the force), so no
+//     force accumulator lives across a barrier.
+// Result: about half the shared-memory traffic per slot and step, and the C slots of a thread are independent
+// instruction streams for the fp64 pipe (8-cycle dependent-issue latency, 2 cycles per warp instruction:
+// profiles/probes/dfma_latency_probe.cu).
+//
+// Semantics are those of br2_fast.cuh / br2_generic.cuh; the optimistic-series
+// protocol is the same: a CTA that leaves a series' validity range flags its instance, does not write back,
+// and the generic kernel redoes the launch for it right behind on the stream.
+//
+// Applicability (decided on the host, br2_cuda.cu: make_tile_plan): fast-path assembly with uniform element
+// constants, no "extra" joints / director overwrites (single-segment assemblies), every surface joint
+// connects equal element indices of two rods and all joints of a rod pair share one descriptor.
+#pragma once
+
+#include "br2_math.cuh"
+#include "br2_tables.cuh"
+
+namespace br2 {
+
+#ifndef BR2_TILE_JD_REGS
+#define BR2_TILE_JD_REGS 0   // joint direction vectors: 1 = registers, 0 = shared-memory rows
+#endif
+#ifndef BR2_TILE_TA_REGS
+#define BR2_TILE_TA_REGS 0   // actuation torques: 1 = registers, 0 = shared-memory rows
+#endif
+
+template <int C, int NT>
+struct TileSmem {
+    static constexpr int R = NT + 1;  // rows of every exchange array; row ZR is all zeros and never written
+    static constexpr int ZR = NT;
+    static constexpr int XF = 0;                  // [3][R]    position of the run's first node
+    static constexpr int VF = XF + 3 * R;         // [3][R]    velocity of the run's first node
+    static constexpr int QF = VF + 3 * R;         // [9][R]    director of the run's first element
+    static constexpr int LF = QF + 9 * R;         // [R]       length of the run's first element
+    static constexpr int SKL = LF + R;            // [3][R]    Q^T n_L / e of the run's last element
+    static constexpr int AL = SKL + 3 * R;        // [3][R]    tau_L / E^3 of the run's last Voronoi cell
+    static constexpr int CL = AL + 3 * R;         // [3][R]    (kappa x tau_L) D / E^3 of the run's last Voronoi cell
+    static constexpr int PC = CL + 3 * R;         // [C][3][R] x_k + x_{k+1} of each element (twice its centre)
+    static constexpr int PR = PC + 3 * C * R;     // [C][3][R] world-frame lever arm of the element as rod one
+    static constexpr int PV = PR + 3 * C * R;     // [C][3][R] v_k + v_{k+1}
+    static constexpr int PA = PV + 3 * C * R;     // [C][R]    arm length as rod one (radius + its share of the rest gap)
+    static constexpr int HF = PA + C * R;         // [C][3][R] half force of the joint the element owns (it is rod two)
+    static constexpr int FS = HF + 3 * C * R;     // [C][3][R] spring part k d of that joint (the torques use only this)
+    static constexpr int ZERO_END = FS + 3 * C * R;  // everything above is zeroed at launch
+    static constexpr int JD = ZERO_END;           // [8][R]    {dv2[3], offset/2, dv1[3], offset/2} of the thread's rod
+    static constexpr int TA = JD + 8 * R;         // [C][3][R] actuation torque at full ramp (material frame)
+    static constexpr int WORDS = TA + 3 * C * R;
+};
+
+constexpr int TILE_F_VALID = 1, TILE_F_ELEM = 2, TILE_F_VOR = 4, TILE_F_ZERO_V = 8, TILE_F_ZERO_W = 16, TILE_F_OWN = 32,
+              TILE_F_REPORT0 = 64, TILE_F_SOFTFIX = 128;
+
+template <int C>
+struct TileThread {
+    double x[C][3], v[C][3], Q[C][9], w[C][3];
+    double dtmc[C];  // dt c_t / node mass
+    int fl[C];
+    int t, tn, tprev, t1, to, top;
+    int k0, n, s0;
+    double *inst;
+#if BR2_TILE_JD_REGS
+    double jd[8];
+#endif
+#if BR2_TILE_TA_REGS
+    double ta[C][3];
+#endif
+    bool bad;
+};
+
+// One PositionVerlet step of a thread's run.  kLast: last step of the launch (reports the callback quantities,
+// ends with a single kinematic half step instead of the fused pair).
+template <int C, int NT, bool kLast>
+__device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileThread<C> &th, double time_mid) {
+    using L = TileSmem<C, NT>;
+    constexpr int R = L::R;
+    const DevTables &tb = p.t;
+    const int t = th.t;
+    const double dt = p.dt, hdt = 0.5 * p.dt;
+    const int n = th.n, np1 = th.n + 1;
+    double *const inst = th.inst;
+#define UNI(idx) p.uni[(idx)]
+#if BR2_TILE_JD_REGS
+#define JDV(i) th.jd[(i)]
+#else
+#define JDV(i) sm[L::JD + (i) * R + t]
+#endif
+#if BR2_TILE_TA_REGS
+#define TAV(j, i) th.ta[(j)][(i)]
+#else
+#define TAV(j, i) sm[L::TA + (3 * (j) + (i)) * R + t]
+#endif
+    double (&x)[C][3] = th.x;
+    double (&v)[C][3] = th.v;
+    double (&Q)[C][9] = th.Q;
+    double (&w)[C][3] = th.w;
+
+    // reported quantities (kLast only)
+    double r_fint[C][3], r_fext[C][3];
+
+    // =============================== P1: publish the run's first node / element ==============
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        sm[L::XF + i * R + t] = x[0][i];
+        sm[L::VF + i * R + t] = v[0][i];
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) sm[L::QF + i * R + t] = Q[0][i];
+    __syncthreads();
+
+    // =============================== P2: element quantities ==================================
+    double len[C], ra2[C];
+    double tint[C][3];   // internal couple on element k (complete except for the previous run's last cell)
+    {
+        const double dtg[3] = {dt * UNI(BR2_FC_CT) * UNI(BR2_FC_GRAVITY), dt * UNI(BR2_FC_CT) * UNI(BR2_FC_GRAVITY + 1),
+                               dt * UNI(BR2_FC_CT) * UNI(BR2_FC_GRAVITY + 2)};
+        double skp[3];  // the previous element's Q^T n_L / e
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+            const bool elem = th.fl[j] & TILE_F_ELEM;
+            double d[3], dv[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const double xn = (j + 1 < C) ? x[(j + 1) % C][i] : sm[L::XF + i * R + th.tn];
+                const double vn = (j + 1 < C) ? v[(j + 1) % C][i] : sm[L::VF + i * R + th.tn];
+                d[i] = xn - x[j][i];
+                dv[i] = vn - v[j][i];
+                sm[L::PC + (3 * j + i) * R + t] = xn + x[j][i];
+                sm[L::PV + (3 * j + i) * R + t] = vn + v[j][i];
+            }
+            double d2 = fma(d[0], d[0], fma(d[1], d[1], d[2] * d[2]));
+            d2 = elem ? d2 : 1.0;  // keeps the node-only slot finite
+            const double rs = fast_rsqrt(d2);
+            len[j] = fma(d2, rs, BR2_EPS14);
+            const double inv_len = rs * fma(-BR2_EPS14, rs, 1.0);  // 1/(|d| + 1e-14), second order 1e-23
+            const double rest_len = UNI(BR2_FC_REST_LEN), inv_rest_len = UNI(BR2_FC_INV_REST_LEN);
+            const double r2 = UNI(BR2_FC_VOL_OVER_PI) * inv_len;
+            const double rad = r2 * fast_rsqrt(r2);
+            const double dil = len[j] * inv_rest_len;
+            const double inv_dil = rest_len * inv_len;
+            const double rse = seed_rsqrt(dil);  // only thins the ~1e-8 m rest gap of a joint: 2^-20 relative is ample
+            ra2[j] = fma(JDV(3), rse, rad);
+            if (kLast && elem) {
+                inst[15 * np1 + 21 * n + th.k0 + j] = len[j];
+                inst[15 * np1 + 22 * n + th.k0 + j] = dil;
+                inst[15 * np1 + 23 * n + th.k0 + j] = rad;
+            }
+            double qt[3], nL[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                qt[i] = fma(Q[j][3 * i], d[0], fma(Q[j][3 * i + 1], d[1], Q[j][3 * i + 2] * d[2])) * inv_len;
+                const double sigma = fma(dil, qt[i], (i == 2) ? -1.0 : 0.0);
+                nL[i] = UNI(BR2_FC_SHEAR + i) * sigma;
+            }
+            // damping and gravity first (the update is linear), then the shear forces of elements k and k-1
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const double raw = fma(Q[j][i], nL[0], fma(Q[j][3 + i], nL[1], Q[j][6 + i] * nL[2])) * inv_dil;
+                const double sk = elem ? raw : 0.0;
+                const double fi = (j == 0) ? sk : sk - skp[i];
+                skp[i] = sk;
+                v[j][i] = fma(th.dtmc[j], fi, fma(v[j][i], UNI(BR2_FC_CT), dtg[i]));
+                if (kLast) r_fint[j][i] = fi;
+            }
+            {
+                // d(e)/dt = (x_{k+1} - x_k).(v_{k+1} - v_k) / l / l_hat  (expanded form in the reference)
+                const double edot = fma(d[0], dv[0], fma(d[1], dv[1], d[2] * dv[2])) * inv_len * inv_rest_len;
+                double jw[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) jw[i] = UNI(BR2_FC_J + i) * w[j][i] * inv_dil;
+                const double ue = edot * inv_dil;
+                tint[j][0] = fma(fma(qt[1], nL[2], -qt[2] * nL[1]), rest_len, fma(jw[1], w[j][2], fma(-jw[2], w[j][1], jw[0] * ue)));
+                tint[j][1] = fma(fma(qt[2], nL[0], -qt[0] * nL[2]), rest_len, fma(jw[2], w[j][0], fma(-jw[0], w[j][2], jw[1] * ue)));
+                tint[j][2] = fma(fma(qt[0], nL[1], -qt[1] * nL[0]), rest_len, fma(jw[0], w[j][1], fma(-jw[1], w[j][0], jw[2] * ue)));
+            }
+            // what the joint in which this element is rod one needs from it
+            const double ra1 = fma(JDV(7), rse, rad);
+            const double a0 = JDV(4) * ra1, a1 = JDV(5) * ra1, a2 = JDV(6) * ra1;
+            sm[L::PA + j * R + t] = ra1;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                sm[L::PR + (3 * j + i) * R + t] = fma(Q[j][i], a0, fma(Q[j][3 + i], a1, Q[j][6 + i] * a2));  // Q^T dv1 (r + o)
+        }
+        sm[L::LF + t] = len[0];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) sm[L::SKL + i * R + t] = skp[i];
+    }
+    __syncthreads();
+
+    // =============================== P3: Voronoi couples and own joints ======================
+    double tw[C][3];  // world-frame joint torque on my element (own joint now, rod-one joint in P4)
+    {
+        double ap[3], cp[3];  // previous cell's A and C
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+            const bool vor = th.fl[j] & TILE_F_VOR;
+            double Qn[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Qn[i] = (j + 1 < C) ? Q[(j + 1) % C][i] : sm[L::QF + i * R + th.tn];
+            const double lenn = (j + 1 < C) ? len[(j + 1) % C] : sm[L::LF + th.tn];
+            const double *q = Q[j];
+            // antisymmetric part and trace of Qn Q^T
+            const double w0 = fma(Qn[6], q[3], fma(Qn[7], q[4], fma(Qn[8], q[5], fma(-Qn[3], q[6], fma(-Qn[4], q[7], -Qn[5] * q[8])))));
+            const double w1 = fma(Qn[0], q[6], fma(Qn[1], q[7], fma(Qn[2], q[8], fma(-Qn[6], q[0], fma(-Qn[7], q[1], -Qn[8] * q[2])))));
+            const double w2 = fma(Qn[3], q[0], fma(Qn[4], q[1], fma(Qn[5], q[2], fma(-Qn[0], q[3], fma(-Qn[1], q[4], -Qn[2] * q[5])))));
+            const double tr = fma(Qn[0], q[0], fma(Qn[1], q[1], fma(Qn[2], q[2], fma(Qn[3], q[3], fma(Qn[4], q[4],
+                              fma(Qn[5], q[5], fma(Qn[6], q[6], fma(Qn[7], q[7], Qn[8] * q[8]))))))));
+            // y = 1 - cos(theta) with the reference's -1e-10 guard; a benign value off the rod
+            const double y = vor ? fma(-0.5, tr, kMisc[7]) : kMisc2[3];
+            th.bad |= !(y <= BR2_Y_MAX && y > 0.0);
+            const double ksr = logmap_ratio_tiny(y) * (-0.5 * UNI(BR2_FC_INV_REST_VLEN));
+            const double ks = vor ? ksr : 0.0;
+            const double kap[3] = {w0 * ks, w1 * ks, w2 * ks};
+            const double tau[3] = {UNI(BR2_FC_BEND) * kap[0], UNI(BR2_FC_BEND + 1) * kap[1], UNI(BR2_FC_BEND + 2) * kap[2]};
+            const double vdil = (lenn + len[j]) * (0.5 * UNI(BR2_FC_INV_REST_VLEN));
+            const double iv = fast_rcp(vdil);
+            const double inv3 = iv * iv * iv;
+            const double dinv3 = UNI(BR2_FC_REST_VLEN) * inv3;
+            double Ak[3], Ck[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) Ak[i] = tau[i] * inv3;
+            Ck[0] = fma(kap[1], tau[2], -kap[2] * tau[1]) * dinv3;
+            Ck[1] = fma(kap[2], tau[0], -kap[0] * tau[2]) * dinv3;
+            Ck[2] = fma(kap[0], tau[1], -kap[1] * tau[0]) * dinv3;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                // couple on element k: (A_k - A_{k-1}) + (C_k + C_{k-1}) / 2 + shear and transport terms
+                double acc = tint[j][i] + fma(0.5, Ck[i], Ak[i]);
+                if (j > 0) acc += fma(0.5, cp[i], -ap[i]);
+                tint[j][i] = acc;
+                ap[i] = Ak[i];
+                cp[i] = Ck[i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            sm[L::AL + i * R + t] = ap[i];
+            sm[L::CL + i * R + t] = cp[i];
+        }
+    }
+    // own joints (Appendix A.7): my element is rod two; rod one's contribution comes from its published rows
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+        const bool own = th.fl[j] & TILE_F_OWN;
+        const double b0 = JDV(0) * ra2[j], b1 = JDV(1) * ra2[j], b2 = JDV(2) * ra2[j];
+        const double ra1 = sm[L::PA + j * R + th.t1];
+        double rd2[3], cd2[3], dvec[3];
+        double proj2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            rd2[i] = fma(Q[j][i], b0, fma(Q[j][3 + i], b1, Q[j][6 + i] * b2));  // Q^T dv2 (r + o)
+            const double xn = (j + 1 < C) ? x[(j + 1) % C][i] : sm[L::XF + i * R + th.tn];
+            cd2[i] = (xn + x[j][i]) - sm[L::PC + (3 * j + i) * R + th.t1];       // 2 (c2 - c1)
+            const double g = rd2[i] - sm[L::PR + (3 * j + i) * R + th.t1];
+            // (c2 + rd2) - (c1 + rd1), rounded to 12 decimals like np.round_(x, 12)
+            dvec[i] = rint(fma(0.5, cd2[i], g) * BR2_1E12) * BR2_1EM12;
+            const double vr2 = sm[L::PV + (3 * j + i) * R + t] - sm[L::PV + (3 * j + i) * R + th.t1];  // 2 v_rel
+            proj2 = fma(vr2, dvec[i], proj2);
+        }
+        const double dist2 = fma(dvec[0], dvec[0], fma(dvec[1], dvec[1], dvec[2] * dvec[2]));
+        // F = k d - nu (v_rel . d_hat) d_hat = (k - nu (v_rel . d) / |d|^2) d ; no damping below |d| = 1e-12
+        const double inv_d2 = (dist2 >= BR2_1EM24) ? seed_rcp(dist2) : 0.0;  // damping term ~1e-8 N: seed accuracy is ample
+        const double jk = UNI(BR2_FC_JK);
+        const double hcoef = fma((-0.25 * UNI(BR2_FC_JNU)) * proj2, inv_d2, 0.5 * jk);  // half of the bracket
+        // Hertz-like repulsion when the surfaces interpenetrate: -k_rep pen^1.5 along the centre line
+        const double cn2 = fma(cd2[0], cd2[0], fma(cd2[1], cd2[1], cd2[2] * cd2[2])) + BR2_TINY;  // 4 |cd|^2
+        const double rcn = fast_rsqrt(cn2);                                  // 1 / (2 |cd|)
+        const double pen = fmax(fma(-0.5 * cn2, rcn, ra1 + ra2[j]), 0.0);     // max(r1 + r2 - |cd|, 0)
+        const double hmag = (-0.5 * UNI(BR2_FC_JKREP)) * (pen * sqrt_mid(pen)) * rcn;  // times cd2 = half the repulsion
+        double fs[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double h = fma(hcoef, dvec[i], hmag * cd2[i]);
+            const double hf = own ? h : 0.0;
+            fs[i] = own ? jk * dvec[i] : 0.0;
+            sm[L::HF + (3 * j + i) * R + t] = hf;
+            sm[L::FS + (3 * j + i) * R + t] = fs[i];
+            // rod two takes -F: half on each node of the element (node k+1 of the run's last element belongs
+            // to the next thread, which reads HF)
+            v[j][i] = fma(-th.dtmc[j], hf, v[j][i]);
+            if (j + 1 < C) v[(j + 1) % C][i] = fma(-th.dtmc[(j + 1) % C], hf, v[(j + 1) % C][i]);
+            if (kLast) {
+                r_fext[j][i] = (j == 0) ? -hf : r_fext[j][i] - hf;
+                if (j + 1 < C) r_fext[(j + 1) % C][i] = -hf;
+            }
+        }
+        // torques use the spring part only; on rod two: -(rd2 x k d), still in the world frame
+        tw[j][0] = fma(rd2[2], fs[1], -rd2[1] * fs[2]);
+        tw[j][1] = fma(rd2[0], fs[2], -rd2[2] * fs[0]);
+        tw[j][2] = fma(rd2[1], fs[0], -rd2[0] * fs[1]);
+    }
+    __syncthreads();
+
+    // =============================== P4: assemble, dynamic step ==============================
+    {
+        const double ramp_raw = time_mid * tb.act_inv_ramp;
+        const double ramp = (ramp_raw < 1.0) ? ramp_raw : 1.0;
+        // what the previous run's last element contributes to my first node / element
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double fp = sm[L::HF + (3 * (C - 1) + i) * R + th.top] - sm[L::HF + (3 * (C - 1) + i) * R + th.tprev];
+            const double sp = sm[L::SKL + i * R + th.tprev];
+            v[0][i] = fma(th.dtmc[0], fp - sp, v[0][i]);
+            tint[0][i] += fma(0.5, sm[L::CL + i * R + th.tprev], -sm[L::AL + i * R + th.tprev]);
+            if (kLast) {
+                r_fint[0][i] -= sp;
+                r_fext[0][i] += fp;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+            const int k = th.k0 + j;
+            double text[3];
+            {
+                double fso[3], rd1[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    // rod one takes +F of the joint its partner owns: half on each node of the element
+                    const double fo = sm[L::HF + (3 * j + i) * R + th.to];
+                    v[j][i] = fma(th.dtmc[j], fo, v[j][i]);
+                    if (j + 1 < C) v[(j + 1) % C][i] = fma(th.dtmc[(j + 1) % C], fo, v[(j + 1) % C][i]);
+                    if (kLast) {
+                        r_fext[j][i] += fo;
+                        if (j + 1 < C) r_fext[(j + 1) % C][i] += fo;
+                    }
+                    fso[i] = sm[L::FS + (3 * j + i) * R + th.to];
+                    rd1[i] = sm[L::PR + (3 * j + i) * R + t];
+                }
+                // rod-one side of the joint owned by my partner: +(rd1 x k d); then both into my material frame
+                tw[j][0] += fma(rd1[1], fso[2], -rd1[2] * fso[1]);
+                tw[j][1] += fma(rd1[2], fso[0], -rd1[0] * fso[2]);
+                tw[j][2] += fma(rd1[0], fso[1], -rd1[1] * fso[0]);
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                text[i] = fma(TAV(j, i), ramp, fma(Q[j][3 * i], tw[j][0], fma(Q[j][3 * i + 1], tw[j][1], Q[j][3 * i + 2] * tw[j][2])));
+            const double dil = len[j] * UNI(BR2_FC_INV_REST_LEN);
+            const double strain = (th.fl[j] & TILE_F_ELEM) ? dil - 1.0 : 0.0;
+            double damp[3];
+            if (p.tile.round_section) {
+                const double e2 = strain * UNI(BR2_FC_LN_CR + 2);
+                th.bad |= !(e2 * e2 <= BR2_E2_MAX);
+                const double ex = exp_tiny(e2);
+                damp[2] = UNI(BR2_FC_CR + 2) * ex;
+                damp[0] = damp[1] = UNI(BR2_FC_CR) * (ex * ex);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const double e = strain * UNI(BR2_FC_LN_CR + i);
+                    th.bad |= !(e * e <= BR2_E2_MAX);
+                    damp[i] = UNI(BR2_FC_CR + i) * exp_tiny(e);
+                }
+            }
+            double wnew[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                wnew[i] = fma((dt * UNI(BR2_FC_JINV + i)) * dil, tint[j][i] + text[i], w[j][i]) * damp[i];
+            if (kLast && (th.fl[j] & TILE_F_VALID)) {
+                // quantities the reference's callbacks report (free_simulator.py:56-72), as of this step
+                const double mass = tb.slot_c[(long long)BR2_SC_MASS * tb.n_slots + th.s0 + j];
+                double a[3], alpha[3], fext[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    fext[i] = fma(UNI(BR2_FC_GRAVITY + i), mass, r_fext[j][i]);
+                    a[i] = (r_fint[j][i] + fext[i]) / mass;
+                    alpha[i] = UNI(BR2_FC_JINV + i) * (tint[j][i] + text[i]) * dil;
+                }
+                if (th.fl[j] & TILE_F_SOFTFIX) {
+                    // FreeBaseEndSoftFixed's spring acts on node 0 in both constrain_values calls of the step;
+                    // it never changes the motion (node 0's rates are zeroed) and is only visible here.
+                    const double *cd = tb.cons_d + tb.fast_i[(th.s0 + j) * BR2_FAST_NI + BR2_FAST_SOFTFIX_ROW] * BR2_C_ND;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const double spring = cd[12] * (cd[i] - x[j][i]);
+                        fext[i] = (fext[i] + spring) + spring;
+                    }
+                }
+                if (th.fl[j] & TILE_F_REPORT0) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) a[i] = alpha[i] = 0.0;
+                }
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    inst[6 * np1 + 12 * n + i * np1 + k] = a[i];
+                    inst[9 * np1 + 15 * n + i * np1 + k] = r_fint[j][i];
+                    inst[12 * np1 + 18 * n + i * np1 + k] = fext[i];
+                }
+                if (th.fl[j] & TILE_F_ELEM) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        inst[9 * np1 + 12 * n + i * n + k] = alpha[i];
+                        inst[12 * np1 + 15 * n + i * n + k] = tint[j][i];
+                        inst[15 * np1 + 18 * n + i * n + k] = text[i];
+                    }
+                }
+            }
+            // rate constraints
+#pragma unroll
+            for (int i = 0; i < 3; ++i) w[j][i] = (th.fl[j] & TILE_F_ZERO_W) ? 0.0 : wnew[i];
+        }
+        // node rates are complete only now (the element after a node lives in the same thread, later in the loop):
+        // constraints, then the trailing kinematic half step of this step fused with the leading half step of the
+        // next one (unless this is the last step of the launch)
+        const double hmult = kLast ? hdt : dt;
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                v[j][i] = (th.fl[j] & TILE_F_ZERO_V) ? 0.0 : v[j][i];
+                x[j][i] = fma(hmult, v[j][i], x[j][i]);
+            }
+            th.bad |= rotate_directors_tiny(Q[j], w[j], hdt, hmult);
+        }
+    }
+#undef UNI
+#undef JDV
+#undef TAV
+}
+
+template <int C, int NT, int kMinBlocks>
+__global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __grid_constant__ StepParams p) {
+    using L = TileSmem<C, NT>;
+    constexpr int R = L::R, ZR = L::ZR;
+    extern __shared__ double sm[];
+
+    const DevTables &tb = p.t;
+    const TilePlan &tp = p.tile;
+    const int t = threadIdx.x;
+    const long long b = blockIdx.x;
+    if (p.status[b] != 0) return;  // already waiting for the exact-path replay (whole CTA, before any barrier)
+
+    TileThread<C> th;
+    th.t = t;
+    th.bad = false;
+    // ---- which run is mine -------------------------------------------------------------------
+    const bool active = t < tp.rod_t0[tb.n_rods];
+    int rod = 0;
+    for (int r = 1; r < tb.n_rods; ++r) rod = (t >= tp.rod_t0[r]) ? r : rod;
+    const int *ri = tb.rod_i + rod * BR2_ROD_NI;
+    const int n = ri[BR2_ROD_N];
+    const int k0 = active ? C * (t - tp.rod_t0[rod]) : n + 1;
+    th.n = n;
+    th.k0 = k0;
+    th.s0 = ri[BR2_ROD_SLOT0] + k0;  // table slot of my first node (when valid)
+    const int S = tb.n_slots;
+    th.inst = p.state + b * tb.words + ri[BR2_ROD_WOFF];
+
+    // rows I read from: next / previous run of my rod, my partner as rod one of the joints I own, the owner
+    // of the joints in which I am rod one (and the owner of my predecessor's); the zero row when there is none
+    th.tn = (active && k0 + C <= n) ? t + 1 : ZR;
+    th.tprev = (active && k0 > 0) ? t - 1 : ZR;
+    const int r1 = tp.partner[rod], ro = tp.owner[rod];
+    th.t1 = (active && r1 >= 0) ? tp.rod_t0[r1] + (t - tp.rod_t0[rod]) : ZR;
+    th.to = (active && ro >= 0) ? tp.rod_t0[ro] + (t - tp.rod_t0[rod]) : ZR;
+    th.top = (th.to != ZR && k0 > 0) ? th.to - 1 : ZR;
+
+    const double dt = p.dt, hdt = 0.5 * p.dt;
+    const int np1 = n + 1;
+    double *const inst = th.inst;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+        const int k = k0 + j;
+        const bool valid = k <= n, elem = k < n, vor = k < n - 1;
+        const int sc = valid ? th.s0 + j : S - 1;
+        const int *fi = tb.fast_i + sc * BR2_FAST_NI;
+        const int pf = valid ? fi[BR2_FAST_FLAGS] : 0;
+        int f = (valid ? TILE_F_VALID : 0) | (elem ? TILE_F_ELEM : 0) | (vor ? TILE_F_VOR : 0);
+        if (!valid || (pf & BR2_FAST_ZERO_NODE_RATE)) f |= TILE_F_ZERO_V;
+        if (!elem || (pf & BR2_FAST_ZERO_ELEM_RATE)) f |= TILE_F_ZERO_W;
+        if (elem && fi[BR2_FAST_OWN_JOINT] >= 0) f |= TILE_F_OWN;
+        if (pf & BR2_FAST_ZERO_REPORTED) f |= TILE_F_REPORT0;
+        if (valid && fi[BR2_FAST_SOFTFIX_ROW] >= 0) f |= TILE_F_SOFTFIX;
+        th.fl[j] = f;
+        th.dtmc[j] = dt * p.uni[BR2_FC_CT] / tb.slot_c[(long long)BR2_SC_MASS * S + sc];
+        double ta[3] = {0.0, 0.0, 0.0};
+        if (valid) {
+            for (int r = fi[BR2_FAST_ACT_BEGIN]; r < fi[BR2_FAST_ACT_END]; ++r) {
+                const double P = p.pressures[(long long)tb.act_i[r] * p.batch + b];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) ta[i] = fma(P, tb.act_d[r * 3 + i], ta[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+#if BR2_TILE_TA_REGS
+            th.ta[j][i] = ta[i];
+#else
+            sm[L::TA + (3 * j + i) * R + t] = ta[i];
+#endif
+            th.x[j][i] = valid ? inst[i * np1 + k] : 0.0;
+            th.v[j][i] = valid ? inst[3 * np1 + i * np1 + k] : 0.0;
+            th.w[j][i] = elem ? inst[6 * np1 + 9 * n + i * n + k] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) th.Q[j][i] = elem ? inst[6 * np1 + i * n + k] : ((i % 4 == 0) ? 1.0 : 0.0);
+        // pinned values are constants of the launch: set once; their rates are zero from here on
+        const double *FCg = tb.fast_c + sc;
+        if (pf & BR2_FAST_PIN_POSITION) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                th.x[j][i] = FCg[(long long)(BR2_FC_PIN + i) * S];
+                th.v[j][i] = 0.0;
+            }
+        }
+        if (pf & BR2_FAST_PIN_DIRECTOR) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) th.Q[j][i] = FCg[(long long)(BR2_FC_PIN + 3 + i) * S];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) th.w[j][i] = 0.0;
+        }
+    }
+    // joint descriptors of my rod: as rod two of the joints I own {dv2[3], offset/2}, as rod one {dv1[3], offset/2}
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#if BR2_TILE_JD_REGS
+        th.jd[i] = tp.jd[rod][i];
+#else
+        sm[L::JD + i * R + t] = tp.jd[rod][i];
+#endif
+    }
+    // zero the exchange arrays (the zero row stays zero for the whole launch)
+    for (int i = t; i < L::ZERO_END; i += NT) sm[i] = 0.0;
+    __syncthreads();
+
+    double time = p.t0;
+    const int n_steps = (int)p.n_steps;
+
+    // leading kinematic half step of the first step; every later one is fused with the trailing half step
+    // of the step before it (same velocities, same omega)
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) th.x[j][i] = fma(hdt, th.v[j][i], th.x[j][i]);
+        th.bad |= rotate_directors_tiny(th.Q[j], th.w[j], hdt, hdt);
+    }
+    for (int step = 0; step < n_steps - 1; ++step) {
+        tile_step<C, NT, false>(p, sm, th, time + hdt);
+        time = (time + hdt) + hdt;
+    }
+    tile_step<C, NT, true>(p, sm, th, time + hdt);
+
+    // a CTA that left the series' validity range keeps its launch-start state and asks for the exact path
+    if (__syncthreads_or(th.bad)) {
+        if (t == 0) p.status[b] = 1;
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+        const int k = k0 + j;
+        if (th.fl[j] & TILE_F_VALID) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                inst[i * np1 + k] = th.x[j][i];
+                inst[3 * np1 + i * np1 + k] = th.v[j][i];
+            }
+        }
+        if (th.fl[j] & TILE_F_ELEM) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) inst[6 * np1 + i * n + k] = th.Q[j][i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) inst[6 * np1 + 9 * n + i * n + k] = th.w[j][i];
+        }
+    }
+}
+
+}  // namespace br2

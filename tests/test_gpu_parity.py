@@ -24,7 +24,9 @@ SHORT = {"position_collection": "x", "velocity_collection": "v", "director_colle
          "omega_collection": "w", "acceleration_collection": "a"}
 
 
-VARIANTS = {"generic": 0, "fast": 1, "fast-uniform": 2}
+VARIANTS = {"generic": 0, "fast": 1, "fast-uniform": 2, "tile": 3}
+TILE_ASSEMBLIES = ("single",)  # single-segment assemblies qualify for the tile kernel (no tip-to-base joints)
+AUTO_VARIANT = {"single": "tile", "double": "fast-uniform", "triple": "fast-uniform"}
 
 
 def make_env(assembly, batch, fps=25, variant=None, **kwargs):
@@ -44,7 +46,7 @@ def test_golden_trajectories(case):
     name, assembly, kwargs, action, duration, fps = case
     g = np.load(os.path.join(GOLDEN, "traj_%s.npz" % name))
     env = make_env(assembly, 1, fps=fps, **kwargs)
-    assert env.engine.kernel_info()["variant_name"] == "fast-uniform"  # the sample assemblies take the fast path
+    assert env.engine.kernel_info()["variant_name"] == AUTO_VARIANT[assembly]  # the sample assemblies take the fast paths
     status = env.run(action, duration=duration, disable_progress_bar=True, check_nan=True, check_steady_state=1)
     assert env.time == float(g["final_time"]) and env.step_skip == int(g["step_skip"])
     assert list(env.shearable_rods.keys()) == list(g["rod_names"])
@@ -98,6 +100,8 @@ BATCH_CASES = [
 @pytest.mark.parametrize("variant", list(VARIANTS))
 @pytest.mark.parametrize("assembly,kwargs,seed,n_steps", BATCH_CASES, ids=[c[0] for c in BATCH_CASES])
 def test_batched_random_pressures_match_oracle(assembly, kwargs, seed, n_steps, variant):
+    if variant == "tile" and assembly not in TILE_ASSEMBLIES:
+        pytest.skip("assembly has tip-to-base joints: served by the one-slot-per-thread fast kernel")
     batch, dt = 64, 2.0e-5
     rng = np.random.default_rng(seed)
     pressures = rng.uniform(0.0, 40.0, size=(3, batch)) * PSI
@@ -136,7 +140,7 @@ def test_batched_random_pressures_match_oracle(assembly, kwargs, seed, n_steps, 
     solo.close()
 
 
-@pytest.mark.parametrize("variant", ["generic", "fast-uniform"])
+@pytest.mark.parametrize("variant", ["generic", "fast-uniform", "tile"])
 def test_chunked_launches_equal_one_launch(variant):
     """Splitting a run into launches (as capture steps do) must not change the result: bit for bit with the
     generic kernel; to rounding noise with the fast kernel, which fuses the trailing and leading kinematic
@@ -252,6 +256,6 @@ def test_benchmark_workload_never_leaves_the_fast_path():
     rng = np.random.default_rng(0)
     action = {name: rng.uniform(0.0, 40.0, size=256) * PSI for name in NAMES}
     env.run(action, duration=0.1, disable_progress_bar=True)
-    assert env.engine.kernel_info()["variant_name"] == "fast-uniform"
+    assert env.engine.kernel_info()["variant_name"] == "tile"
     assert env.engine.replay_count() == 0
     env.close()
