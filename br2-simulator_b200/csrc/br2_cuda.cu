@@ -9,6 +9,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -82,7 +83,10 @@ struct KernelChoice {
 #define BR2_TILE_C 2
 #endif
 #ifndef BR2_TILE_MB64
-#define BR2_TILE_MB64 5
+#define BR2_TILE_MB64 6
+#endif
+#ifndef BR2_TILE_MIN_CHUNK_STEPS
+#define BR2_TILE_MIN_CHUNK_STEPS 125  // a launch is cut into at most BR2_MAX_CHUNKS chunks of at least this many steps
 #endif
 // variant 3: tile kernel (BR2_TILE_C slots per thread, uniform constants); `threads` = CTA size
 const KernelChoice kTileKernels[] = {
@@ -126,6 +130,8 @@ struct br2_handle_s {
     double uni[BR2_FC_COUNT] = {0};
     int *status = nullptr;            // [batch] fast-kernel validity flags (library-owned)
     long long status_batch = 0;
+    unsigned long long *work = nullptr;  // tile kernel's queue: [0] item counter, then int progress[batch]
+    int tile_capacity = 0;            // CTAs of the tile kernel resident on the device
     unsigned long long *replays = nullptr;  // device counter
     double *scratch_state = nullptr;  // br2_step_host
     double *scratch_pressures = nullptr;
@@ -368,6 +374,13 @@ int br2_select_kernel(br2_handle h, int32_t variant) {
     h->kernel = pick;
     h->smem_bytes = smem;
     h->variant = variant;
+    if (variant == 3) {
+        int blocks = 0, sms = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, (const void *)pick.fn, pick.threads, smem));
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+        if (blocks < 1) return fail(BR2_ELIMIT, "the tile kernel does not fit on an SM");
+        h->tile_capacity = blocks * sms;
+    }
     if (variant != 0) {
         for (const KernelChoice &kc : kKernels[0])
             if (kc.threads >= h->t.n_slots) {
@@ -387,6 +400,7 @@ int br2_destroy(br2_handle h) {
     cudaSetDevice(h->device);
     for (void *d : h->owned) cudaFree(d);
     if (h->status) cudaFree(h->status);
+    if (h->work) cudaFree(h->work);
     if (h->replays) cudaFree(h->replays);
     if (h->scratch_state) cudaFree(h->scratch_state);
     if (h->scratch_pressures) cudaFree(h->scratch_pressures);
@@ -405,6 +419,9 @@ int br2_bind_state(br2_handle h, double *dev_state, int64_t batch) {
         if (h->status) cudaFree(h->status);
         h->status = nullptr;
         CUDA_TRY(cudaMalloc((void **)&h->status, sizeof(int) * (size_t)batch));
+        if (h->work) cudaFree(h->work);
+        h->work = nullptr;
+        CUDA_TRY(cudaMalloc((void **)&h->work, sizeof(unsigned long long) + sizeof(int) * (size_t)batch));
         h->status_batch = batch;
     }
     CUDA_TRY(cudaMemset(h->status, 0, sizeof(int) * (size_t)batch));
@@ -460,8 +477,38 @@ int br2_step(br2_handle h, int64_t n_steps, double t0, double dt, void *stream, 
     sp.status = h->status;
     sp.replays = h->replays;
     sp.only_flagged = 0;
+    sp.work_counter = h->work;
+    sp.progress = (int *)(h->work + 1);
+    // chunking: the tile kernel's persistent CTAs pull (chunk, instance) items; everything else runs one chunk
+    sp.n_chunks = 1;
+    if (h->variant == 3) {
+        long long c = n_steps / BR2_TILE_MIN_CHUNK_STEPS;
+        if (const char *env = getenv("BR2_TILE_CHUNKS")) {  // tuning knob: upper bound on the chunks per launch
+            const long long cap = atoll(env);
+            if (cap >= 1 && c > cap) c = cap;
+        }
+        sp.n_chunks = (int)(c < 1 ? 1 : (c > BR2_MAX_CHUNKS ? BR2_MAX_CHUNKS : c));
+    }
+    sp.chunk_steps = (int)((n_steps + sp.n_chunks - 1) / sp.n_chunks);
+    sp.n_chunks = (int)((n_steps + sp.chunk_steps - 1) / sp.chunk_steps);
+    {
+        volatile double tc = t0;
+        for (int c = 0; c < sp.n_chunks; ++c) {
+            sp.chunk_t0[c] = tc;
+            for (int i = 0; i < sp.chunk_steps; ++i) {
+                tc += half;
+                tc += half;
+            }
+        }
+    }
     void *args[] = {&sp};
-    CUDA_TRY(cudaLaunchKernel((const void *)h->kernel.fn, dim3((unsigned)h->batch), dim3((unsigned)h->kernel.threads), args,
+    unsigned grid = (unsigned)h->batch;
+    if (h->variant == 3) {
+        CUDA_TRY(cudaMemsetAsync(h->work, 0, sizeof(unsigned long long) + sizeof(int) * (size_t)h->batch, (cudaStream_t)stream));
+        const long long items = h->batch * (long long)sp.n_chunks;
+        grid = (unsigned)(items < h->tile_capacity ? items : h->tile_capacity);
+    }
+    CUDA_TRY(cudaLaunchKernel((const void *)h->kernel.fn, dim3(grid), dim3((unsigned)h->kernel.threads), args,
                               h->smem_bytes, (cudaStream_t)stream));
     if (h->variant != 0) {
         // exact-path replay, stream-ordered behind the fast kernel: CTAs of unflagged instances exit at once
@@ -496,6 +543,9 @@ int br2_step_host(br2_handle h, double *host_state, const double *host_pressures
         if (h->status) cudaFree(h->status);
         h->status = nullptr;
         CUDA_TRY(cudaMalloc((void **)&h->status, sizeof(int) * (size_t)batch));
+        if (h->work) cudaFree(h->work);
+        h->work = nullptr;
+        CUDA_TRY(cudaMalloc((void **)&h->work, sizeof(unsigned long long) + sizeof(int) * (size_t)batch));
         h->status_batch = batch;
         CUDA_TRY(cudaMemset(h->status, 0, sizeof(int) * (size_t)batch));
     }

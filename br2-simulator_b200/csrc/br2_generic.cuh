@@ -110,7 +110,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_generic_kernel(
     for (int i = 0; i < 9; ++i) Q[i] = is_elem ? g_Q[i * n + k] : ((i % 4 == 0) ? 1.0 : 0.0);
 
     const double dt = p.dt, hdt = 0.5 * p.dt;
-    double time = p.t0;
+    // exact-path replay: resume at the chunk in which the optimistic kernel left its range (status = 1 + chunk)
+    const int resume_chunk = p.only_flagged ? p.status[b] - 1 : 0;
+    const long long first_step = (long long)resume_chunk * p.chunk_steps;
+    double time = p.only_flagged ? p.chunk_t0[resume_chunk] : p.t0;
 
     // values carried from P2 to P4
     double len = 1.0, rad = 1.0, dil = 1.0;
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_generic_kernel(
 
     __syncthreads();  // Pr visible
 
-    for (long long step = 0; step < p.n_steps; ++step) {
+    for (long long step = first_step; step < p.n_steps; ++step) {
         // =============================== P1: kinematic half step ===========================
 #pragma unroll
         for (int i = 0; i < 3; ++i) x[i] += hdt * v[i];

@@ -30,6 +30,7 @@ struct DevTables {
 
 // Thread-coarsened ("tile") kernel: every thread owns C consecutive slots of one rod (br2_tile.cuh).
 #define BR2_TILE_MAX_RODS 12
+#define BR2_MAX_CHUNKS 8
 struct TilePlan {
     int C;                                  // slots per thread
     int round_section;                      // ln c_r1 = ln c_r2 = 2 ln c_r3: one exponential per element and step
@@ -51,6 +52,12 @@ struct StepParams {
     unsigned long long *replays;  // counts instance-launches redone by the exact path
     double uni[BR2_FC_COUNT];  // uniform copy of fast_c (all element slots identical), constant bank
     TilePlan tile;
+    // launch chunking (tile kernel's work queue; the exact-path replay resumes at the chunk that failed:
+    // status = 1 + chunk).  One chunk = the whole launch for the other kernels.
+    int chunk_steps, n_chunks;
+    double chunk_t0[BR2_MAX_CHUNKS];      // fp64-accumulated start time of each chunk
+    unsigned long long *work_counter;     // next item of the queue (zeroed before every launch)
+    int *progress;                        // [batch] chunks of the instance already written back
 };
 
 }  // namespace br2

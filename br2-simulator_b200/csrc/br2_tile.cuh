@@ -69,8 +69,6 @@ struct TileThread {
     double dtmc[C];  // dt c_t / node mass
     int fl[C];
     int t, tn, tprev, t1, to, top;
-    int k0, n, s0;
-    double *inst;
 #if BR2_TILE_JD_REGS
     double jd[8];
 #endif
@@ -80,17 +78,45 @@ struct TileThread {
     bool bad;
 };
 
-// One PositionVerlet step of a thread's run.  kLast: last step of the launch (reports the callback quantities,
-// ends with a single kinematic half step instead of the fused pair).
-template <int C, int NT, bool kLast>
-__device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileThread<C> &th, double time_mid) {
+// Where a thread's run sits in the assembly and in the instance's state block.  Recomputed (behind an opaque
+// copy of the thread index, so the compiler cannot keep it alive) wherever it is needed outside the step loop:
+// these five values would otherwise occupy registers for the whole launch.
+struct TileWhere {
+    int rod, n, k0, s0;
+    double *inst;
+};
+
+template <int C>
+__device__ __forceinline__ TileWhere tile_where(const StepParams &p, int t, long long b) {
+    asm volatile("" : "+r"(t));
+    const DevTables &tb = p.t;
+    const TilePlan &tp = p.tile;
+    TileWhere wh;
+    int rod = 0;
+    for (int r = 1; r < tb.n_rods; ++r) rod = (t >= tp.rod_t0[r]) ? r : rod;
+    const int *ri = tb.rod_i + rod * BR2_ROD_NI;
+    wh.rod = rod;
+    wh.n = ri[BR2_ROD_N];
+    wh.k0 = (t < tp.rod_t0[tb.n_rods]) ? C * (t - tp.rod_t0[rod]) : wh.n + 1;
+    wh.s0 = ri[BR2_ROD_SLOT0] + wh.k0;  // table slot of my first node (when valid)
+    wh.inst = p.state + b * tb.words + ri[BR2_ROD_WOFF];
+    return wh;
+}
+
+// One PositionVerlet step of a thread's run.  kEnd: last step of a chunk (ends with a single kinematic half step
+// instead of the fused pair, so the state is a whole-step state); kLast: last step of the launch (also reports
+// the callback quantities).
+template <int C, int NT, bool kEnd, bool kLast>
+__device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileThread<C> &th, double time_mid, long long b) {
     using L = TileSmem<C, NT>;
     constexpr int R = L::R;
     const DevTables &tb = p.t;
     const int t = th.t;
     const double dt = p.dt, hdt = 0.5 * p.dt;
-    const int n = th.n, np1 = th.n + 1;
-    double *const inst = th.inst;
+    TileWhere wh{};
+    if (kLast) wh = tile_where<C>(p, t, b);
+    const int n = wh.n, np1 = wh.n + 1;
+    double *const inst = wh.inst;
 #define UNI(idx) p.uni[(idx)]
 #if BR2_TILE_JD_REGS
 #define JDV(i) th.jd[(i)]
@@ -153,21 +179,23 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
             const double rse = seed_rsqrt(dil);  // only thins the ~1e-8 m rest gap of a joint: 2^-20 relative is ample
             ra2[j] = fma(JDV(3), rse, rad);
             if (kLast && elem) {
-                inst[15 * np1 + 21 * n + th.k0 + j] = len[j];
-                inst[15 * np1 + 22 * n + th.k0 + j] = dil;
-                inst[15 * np1 + 23 * n + th.k0 + j] = rad;
+                inst[15 * np1 + 21 * n + wh.k0 + j] = len[j];
+                inst[15 * np1 + 22 * n + wh.k0 + j] = dil;
+                inst[15 * np1 + 23 * n + wh.k0 + j] = rad;
             }
-            double qt[3], nL[3];
+            // sigma = e Q t - d3 = Q d / l_hat - d3 (the 1/|d| of the tangent cancels against the dilatation);
+            // nL holds n_L / e, which is what both the nodal force Q^T n_L / e and the couple (Q t x n_L) l_hat need
+            double qd[3], nL[3];
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                qt[i] = fma(Q[j][3 * i], d[0], fma(Q[j][3 * i + 1], d[1], Q[j][3 * i + 2] * d[2])) * inv_len;
-                const double sigma = fma(dil, qt[i], (i == 2) ? -1.0 : 0.0);
-                nL[i] = UNI(BR2_FC_SHEAR + i) * sigma;
+                qd[i] = fma(Q[j][3 * i], d[0], fma(Q[j][3 * i + 1], d[1], Q[j][3 * i + 2] * d[2]));
+                const double sigma = fma(inv_rest_len, qd[i], (i == 2) ? -1.0 : 0.0);
+                nL[i] = (UNI(BR2_FC_SHEAR + i) * inv_dil) * sigma;
             }
             // damping and gravity first (the update is linear), then the shear forces of elements k and k-1
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                const double raw = fma(Q[j][i], nL[0], fma(Q[j][3 + i], nL[1], Q[j][6 + i] * nL[2])) * inv_dil;
+                const double raw = fma(Q[j][i], nL[0], fma(Q[j][3 + i], nL[1], Q[j][6 + i] * nL[2]));
                 const double sk = elem ? raw : 0.0;
                 const double fi = (j == 0) ? sk : sk - skp[i];
                 skp[i] = sk;
@@ -181,9 +209,9 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 #pragma unroll
                 for (int i = 0; i < 3; ++i) jw[i] = UNI(BR2_FC_J + i) * w[j][i] * inv_dil;
                 const double ue = edot * inv_dil;
-                tint[j][0] = fma(fma(qt[1], nL[2], -qt[2] * nL[1]), rest_len, fma(jw[1], w[j][2], fma(-jw[2], w[j][1], jw[0] * ue)));
-                tint[j][1] = fma(fma(qt[2], nL[0], -qt[0] * nL[2]), rest_len, fma(jw[2], w[j][0], fma(-jw[0], w[j][2], jw[1] * ue)));
-                tint[j][2] = fma(fma(qt[0], nL[1], -qt[1] * nL[0]), rest_len, fma(jw[0], w[j][1], fma(-jw[1], w[j][0], jw[2] * ue)));
+                tint[j][0] = fma(jw[1], w[j][2], fma(-jw[2], w[j][1], fma(jw[0], ue, fma(qd[1], nL[2], -qd[2] * nL[1]))));
+                tint[j][1] = fma(jw[2], w[j][0], fma(-jw[0], w[j][2], fma(jw[1], ue, fma(qd[2], nL[0], -qd[0] * nL[2]))));
+                tint[j][2] = fma(jw[0], w[j][1], fma(-jw[1], w[j][0], fma(jw[2], ue, fma(qd[0], nL[1], -qd[1] * nL[0]))));
             }
             // what the joint in which this element is rod one needs from it
             const double ra1 = fma(JDV(7), rse, rad);
@@ -321,7 +349,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
         }
 #pragma unroll
         for (int j = 0; j < C; ++j) {
-            const int k = th.k0 + j;
+            const int k = wh.k0 + j;
             double text[3];
             {
                 double fso[3], rd1[3];
@@ -369,7 +397,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
                 wnew[i] = fma((dt * UNI(BR2_FC_JINV + i)) * dil, tint[j][i] + text[i], w[j][i]) * damp[i];
             if (kLast && (th.fl[j] & TILE_F_VALID)) {
                 // quantities the reference's callbacks report (free_simulator.py:56-72), as of this step
-                const double mass = tb.slot_c[(long long)BR2_SC_MASS * tb.n_slots + th.s0 + j];
+                const double mass = tb.slot_c[(long long)BR2_SC_MASS * tb.n_slots + wh.s0 + j];
                 double a[3], alpha[3], fext[3];
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
@@ -380,7 +408,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
                 if (th.fl[j] & TILE_F_SOFTFIX) {
                     // FreeBaseEndSoftFixed's spring acts on node 0 in both constrain_values calls of the step;
                     // it never changes the motion (node 0's rates are zeroed) and is only visible here.
-                    const double *cd = tb.cons_d + tb.fast_i[(th.s0 + j) * BR2_FAST_NI + BR2_FAST_SOFTFIX_ROW] * BR2_C_ND;
+                    const double *cd = tb.cons_d + tb.fast_i[(wh.s0 + j) * BR2_FAST_NI + BR2_FAST_SOFTFIX_ROW] * BR2_C_ND;
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
                         const double spring = cd[12] * (cd[i] - x[j][i]);
@@ -413,7 +441,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
         // node rates are complete only now (the element after a node lives in the same thread, later in the loop):
         // constraints, then the trailing kinematic half step of this step fused with the leading half step of the
         // next one (unless this is the last step of the launch)
-        const double hmult = kLast ? hdt : dt;
+        const double hmult = kEnd ? hdt : dt;
 #pragma unroll
         for (int j = 0; j < C; ++j) {
 #pragma unroll
@@ -429,149 +457,192 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 #undef TAV
 }
 
+#ifdef BR2_TILE_MAXREG
+#define BR2_TILE_BOUNDS(NT, MB) __maxnreg__(BR2_TILE_MAXREG)
+#else
+#define BR2_TILE_BOUNDS(NT, MB) __launch_bounds__(NT, MB)
+#endif
 template <int C, int NT, int kMinBlocks>
-__global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __grid_constant__ StepParams p) {
+__global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __grid_constant__ StepParams p) {
     using L = TileSmem<C, NT>;
     constexpr int R = L::R, ZR = L::ZR;
     extern __shared__ double sm[];
+    __shared__ long long s_item;
 
     const DevTables &tb = p.t;
     const TilePlan &tp = p.tile;
     const int t = threadIdx.x;
-    const long long b = blockIdx.x;
-    if (p.status[b] != 0) return;  // already waiting for the exact-path replay (whole CTA, before any barrier)
+    const long long total_items = p.batch * (long long)p.n_chunks;
 
-    TileThread<C> th;
-    th.t = t;
-    th.bad = false;
-    // ---- which run is mine -------------------------------------------------------------------
-    const bool active = t < tp.rod_t0[tb.n_rods];
-    int rod = 0;
-    for (int r = 1; r < tb.n_rods; ++r) rod = (t >= tp.rod_t0[r]) ? r : rod;
-    const int *ri = tb.rod_i + rod * BR2_ROD_NI;
-    const int n = ri[BR2_ROD_N];
-    const int k0 = active ? C * (t - tp.rod_t0[rod]) : n + 1;
-    th.n = n;
-    th.k0 = k0;
-    th.s0 = ri[BR2_ROD_SLOT0] + k0;  // table slot of my first node (when valid)
-    const int S = tb.n_slots;
-    th.inst = p.state + b * tb.words + ri[BR2_ROD_WOFF];
-
-    // rows I read from: next / previous run of my rod, my partner as rod one of the joints I own, the owner
-    // of the joints in which I am rod one (and the owner of my predecessor's); the zero row when there is none
-    th.tn = (active && k0 + C <= n) ? t + 1 : ZR;
-    th.tprev = (active && k0 > 0) ? t - 1 : ZR;
-    const int r1 = tp.partner[rod], ro = tp.owner[rod];
-    th.t1 = (active && r1 >= 0) ? tp.rod_t0[r1] + (t - tp.rod_t0[rod]) : ZR;
-    th.to = (active && ro >= 0) ? tp.rod_t0[ro] + (t - tp.rod_t0[rod]) : ZR;
-    th.top = (th.to != ZR && k0 > 0) ? th.to - 1 : ZR;
-
-    const double dt = p.dt, hdt = 0.5 * p.dt;
-    const int np1 = n + 1;
-    double *const inst = th.inst;
-#pragma unroll
-    for (int j = 0; j < C; ++j) {
-        const int k = k0 + j;
-        const bool valid = k <= n, elem = k < n, vor = k < n - 1;
-        const int sc = valid ? th.s0 + j : S - 1;
-        const int *fi = tb.fast_i + sc * BR2_FAST_NI;
-        const int pf = valid ? fi[BR2_FAST_FLAGS] : 0;
-        int f = (valid ? TILE_F_VALID : 0) | (elem ? TILE_F_ELEM : 0) | (vor ? TILE_F_VOR : 0);
-        if (!valid || (pf & BR2_FAST_ZERO_NODE_RATE)) f |= TILE_F_ZERO_V;
-        if (!elem || (pf & BR2_FAST_ZERO_ELEM_RATE)) f |= TILE_F_ZERO_W;
-        if (elem && fi[BR2_FAST_OWN_JOINT] >= 0) f |= TILE_F_OWN;
-        if (pf & BR2_FAST_ZERO_REPORTED) f |= TILE_F_REPORT0;
-        if (valid && fi[BR2_FAST_SOFTFIX_ROW] >= 0) f |= TILE_F_SOFTFIX;
-        th.fl[j] = f;
-        th.dtmc[j] = dt * p.uni[BR2_FC_CT] / tb.slot_c[(long long)BR2_SC_MASS * S + sc];
-        double ta[3] = {0.0, 0.0, 0.0};
-        if (valid) {
-            for (int r = fi[BR2_FAST_ACT_BEGIN]; r < fi[BR2_FAST_ACT_END]; ++r) {
-                const double P = p.pressures[(long long)tb.act_i[r] * p.batch + b];
-#pragma unroll
-                for (int i = 0; i < 3; ++i) ta[i] = fma(P, tb.act_d[r * 3 + i], ta[i]);
-            }
+    // Persistent CTAs pull (chunk, instance) items off one queue, chunk-major: the launch is cut into n_chunks
+    // runs of chunk_steps steps so that the last wave of instances does not leave most SMs idle (4096 instances
+    // on 888 resident CTAs would otherwise cost 5 full waves for 4.6 waves of work).  Chunk c of an instance
+    // starts when chunk c-1 of the same instance has been written back (progress[instance] == c); with the
+    // chunk-major order that was `batch` items ago, so nobody actually waits unless the batch is tiny.
+    for (;;) {
+        if (t == 0) s_item = (long long)atomicAdd(p.work_counter, 1ULL);
+        __syncthreads();
+        const long long item = s_item;
+        __syncthreads();
+        if (item >= total_items) break;
+        const long long b = item % p.batch;
+        const int chunk = (int)(item / p.batch);
+        if (t == 0) {
+            while (*(volatile int *)(p.progress + b) < chunk) __nanosleep(100);
+            __threadfence();
         }
+        __syncthreads();
+        if (*(volatile int *)(p.status + b) != 0) {  // waiting for the exact-path replay: skip the rest of the launch
+            if (t == 0) *(volatile int *)(p.progress + b) = chunk + 1;
+            continue;
+        }
+        const int first_step = chunk * p.chunk_steps;
+        const int n_steps = min(p.chunk_steps, (int)p.n_steps - first_step);
+        const bool final_chunk = (chunk == p.n_chunks - 1);
+
+        TileThread<C> th;
+        th.t = t;
+        th.bad = false;
+        // ---- which run is mine -------------------------------------------------------------------
+        const bool active = t < tp.rod_t0[tb.n_rods];
+        const int S = tb.n_slots;
+        {
+            const TileWhere wh = tile_where<C>(p, t, b);
+            const int rod = wh.rod, n = wh.n, k0 = wh.k0;
+
+            // rows I read from: next / previous run of my rod, my partner as rod one of the joints I own, the owner
+            // of the joints in which I am rod one (and the owner of my predecessor's); the zero row when there is none
+            th.tn = (active && k0 + C <= n) ? t + 1 : ZR;
+            th.tprev = (active && k0 > 0) ? t - 1 : ZR;
+            const int r1 = tp.partner[rod], ro = tp.owner[rod];
+            th.t1 = (active && r1 >= 0) ? tp.rod_t0[r1] + (t - tp.rod_t0[rod]) : ZR;
+            th.to = (active && ro >= 0) ? tp.rod_t0[ro] + (t - tp.rod_t0[rod]) : ZR;
+            th.top = (th.to != ZR && k0 > 0) ? th.to - 1 : ZR;
+
+            const double dt = p.dt;
+            const int np1 = n + 1;
+            const double *const inst = wh.inst;  // read through L2 (__ldcg): another SM wrote the previous chunk
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < C; ++j) {
+                const int k = k0 + j;
+                const bool valid = k <= n, elem = k < n, vor = k < n - 1;
+                const int sc = valid ? wh.s0 + j : S - 1;
+                const int *fi = tb.fast_i + sc * BR2_FAST_NI;
+                const int pf = valid ? fi[BR2_FAST_FLAGS] : 0;
+                int f = (valid ? TILE_F_VALID : 0) | (elem ? TILE_F_ELEM : 0) | (vor ? TILE_F_VOR : 0);
+                if (!valid || (pf & BR2_FAST_ZERO_NODE_RATE)) f |= TILE_F_ZERO_V;
+                if (!elem || (pf & BR2_FAST_ZERO_ELEM_RATE)) f |= TILE_F_ZERO_W;
+                if (elem && fi[BR2_FAST_OWN_JOINT] >= 0) f |= TILE_F_OWN;
+                if (pf & BR2_FAST_ZERO_REPORTED) f |= TILE_F_REPORT0;
+                if (valid && fi[BR2_FAST_SOFTFIX_ROW] >= 0) f |= TILE_F_SOFTFIX;
+                th.fl[j] = f;
+                th.dtmc[j] = dt * p.uni[BR2_FC_CT] / tb.slot_c[(long long)BR2_SC_MASS * S + sc];
+                double ta[3] = {0.0, 0.0, 0.0};
+                if (valid) {
+                    for (int r = fi[BR2_FAST_ACT_BEGIN]; r < fi[BR2_FAST_ACT_END]; ++r) {
+                        const double P = p.pressures[(long long)tb.act_i[r] * p.batch + b];
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) ta[i] = fma(P, tb.act_d[r * 3 + i], ta[i]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
 #if BR2_TILE_TA_REGS
-            th.ta[j][i] = ta[i];
+                    th.ta[j][i] = ta[i];
 #else
-            sm[L::TA + (3 * j + i) * R + t] = ta[i];
+                    sm[L::TA + (3 * j + i) * R + t] = ta[i];
 #endif
-            th.x[j][i] = valid ? inst[i * np1 + k] : 0.0;
-            th.v[j][i] = valid ? inst[3 * np1 + i * np1 + k] : 0.0;
-            th.w[j][i] = elem ? inst[6 * np1 + 9 * n + i * n + k] : 0.0;
-        }
+                    th.x[j][i] = valid ? __ldcg(inst + i * np1 + k) : 0.0;
+                    th.v[j][i] = valid ? __ldcg(inst + 3 * np1 + i * np1 + k) : 0.0;
+                    th.w[j][i] = elem ? __ldcg(inst + 6 * np1 + 9 * n + i * n + k) : 0.0;
+                }
 #pragma unroll
-        for (int i = 0; i < 9; ++i) th.Q[j][i] = elem ? inst[6 * np1 + i * n + k] : ((i % 4 == 0) ? 1.0 : 0.0);
-        // pinned values are constants of the launch: set once; their rates are zero from here on
-        const double *FCg = tb.fast_c + sc;
-        if (pf & BR2_FAST_PIN_POSITION) {
+                for (int i = 0; i < 9; ++i) th.Q[j][i] = elem ? __ldcg(inst + 6 * np1 + i * n + k) : ((i % 4 == 0) ? 1.0 : 0.0);
+                // pinned values are constants of the launch: set once; their rates are zero from here on
+                const double *FCg = tb.fast_c + sc;
+                if (pf & BR2_FAST_PIN_POSITION) {
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                th.x[j][i] = FCg[(long long)(BR2_FC_PIN + i) * S];
-                th.v[j][i] = 0.0;
+                    for (int i = 0; i < 3; ++i) {
+                        th.x[j][i] = FCg[(long long)(BR2_FC_PIN + i) * S];
+                        th.v[j][i] = 0.0;
+                    }
+                }
+                if (pf & BR2_FAST_PIN_DIRECTOR) {
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) th.Q[j][i] = FCg[(long long)(BR2_FC_PIN + 3 + i) * S];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) th.w[j][i] = 0.0;
+                }
             }
-        }
-        if (pf & BR2_FAST_PIN_DIRECTOR) {
+            // joint descriptors of my rod: as rod two of the joints I own {dv2[3], offset/2}, as rod one {dv1[3], offset/2}
 #pragma unroll
-            for (int i = 0; i < 9; ++i) th.Q[j][i] = FCg[(long long)(BR2_FC_PIN + 3 + i) * S];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) th.w[j][i] = 0.0;
-        }
-    }
-    // joint descriptors of my rod: as rod two of the joints I own {dv2[3], offset/2}, as rod one {dv1[3], offset/2}
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < 8; ++i) {
 #if BR2_TILE_JD_REGS
-        th.jd[i] = tp.jd[rod][i];
+                th.jd[i] = tp.jd[rod][i];
 #else
-        sm[L::JD + i * R + t] = tp.jd[rod][i];
+                sm[L::JD + i * R + t] = tp.jd[rod][i];
 #endif
-    }
-    // zero the exchange arrays (the zero row stays zero for the whole launch)
-    for (int i = t; i < L::ZERO_END; i += NT) sm[i] = 0.0;
-    __syncthreads();
-
-    double time = p.t0;
-    const int n_steps = (int)p.n_steps;
-
-    // leading kinematic half step of the first step; every later one is fused with the trailing half step
-    // of the step before it (same velocities, same omega)
-#pragma unroll
-    for (int j = 0; j < C; ++j) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) th.x[j][i] = fma(hdt, th.v[j][i], th.x[j][i]);
-        th.bad |= rotate_directors_tiny(th.Q[j], th.w[j], hdt, hdt);
-    }
-    for (int step = 0; step < n_steps - 1; ++step) {
-        tile_step<C, NT, false>(p, sm, th, time + hdt);
-        time = (time + hdt) + hdt;
-    }
-    tile_step<C, NT, true>(p, sm, th, time + hdt);
-
-    // a CTA that left the series' validity range keeps its launch-start state and asks for the exact path
-    if (__syncthreads_or(th.bad)) {
-        if (t == 0) p.status[b] = 1;
-        return;
-    }
-#pragma unroll
-    for (int j = 0; j < C; ++j) {
-        const int k = k0 + j;
-        if (th.fl[j] & TILE_F_VALID) {
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                inst[i * np1 + k] = th.x[j][i];
-                inst[3 * np1 + i * np1 + k] = th.v[j][i];
             }
         }
-        if (th.fl[j] & TILE_F_ELEM) {
+        // zero the exchange arrays (the zero row stays zero for the whole chunk)
+        for (int i = t; i < L::ZERO_END; i += NT) sm[i] = 0.0;
+        __syncthreads();
+
+        double time = p.chunk_t0[chunk];
+        const double hdt = 0.5 * p.dt;
+
+        // leading kinematic half step of the first step; every later one is fused with the trailing half step
+        // of the step before it (same velocities, same omega)
 #pragma unroll
-            for (int i = 0; i < 9; ++i) inst[6 * np1 + i * n + k] = th.Q[j][i];
+        for (int j = 0; j < C; ++j) {
 #pragma unroll
-            for (int i = 0; i < 3; ++i) inst[6 * np1 + 9 * n + i * n + k] = th.w[j][i];
+            for (int i = 0; i < 3; ++i) th.x[j][i] = fma(hdt, th.v[j][i], th.x[j][i]);
+            th.bad |= rotate_directors_tiny(th.Q[j], th.w[j], hdt, hdt);
         }
+        for (int step = 0; step < n_steps - 1; ++step) {
+            tile_step<C, NT, false, false>(p, sm, th, time + hdt, b);
+            time = (time + hdt) + hdt;
+        }
+        if (final_chunk)
+            tile_step<C, NT, true, true>(p, sm, th, time + hdt, b);
+        else
+            tile_step<C, NT, true, false>(p, sm, th, time + hdt, b);
+
+        // a CTA that left the series' validity range keeps the chunk-start state and asks for the exact path, which
+        // resumes this instance from the start of this chunk (status = 1 + chunk)
+        if (__syncthreads_or(th.bad)) {
+            if (t == 0) {
+                *(volatile int *)(p.status + b) = 1 + chunk;
+                __threadfence();
+                *(volatile int *)(p.progress + b) = chunk + 1;
+            }
+            continue;
+        }
+        {
+            const TileWhere wh = tile_where<C>(p, t, b);
+            const int n = wh.n, np1 = wh.n + 1;
+            double *const inst = wh.inst;
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                const int k = wh.k0 + j;
+                if (th.fl[j] & TILE_F_VALID) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        inst[i * np1 + k] = th.x[j][i];
+                        inst[3 * np1 + i * np1 + k] = th.v[j][i];
+                    }
+                }
+                if (th.fl[j] & TILE_F_ELEM) {
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) inst[6 * np1 + i * n + k] = th.Q[j][i];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) inst[6 * np1 + 9 * n + i * n + k] = th.w[j][i];
+                }
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (t == 0) *(volatile int *)(p.progress + b) = chunk + 1;
     }
 }
 

@@ -223,14 +223,17 @@ def test_step_host_entry_point_matches_device_path():
     env.close()
 
 
-def test_fast_kernel_falls_back_to_exact_path_when_out_of_range():
-    """Absurd actuation drives strains / rotations outside the fast kernel's series range: the flagged
-    instances must be redone by the exact-path kernel, giving exactly the generic kernel's result, while
-    the well-behaved instances of the same batch keep the fast kernel's result."""
+@pytest.mark.parametrize("variant", ["fast-uniform", "tile"])
+def test_fast_kernel_falls_back_to_exact_path_when_out_of_range(variant):
+    """Absurd actuation drives strains / rotations outside the optimistic kernels' series range: the flagged
+    instances must be redone by the exact-path kernel while the well-behaved instances of the same batch keep
+    the optimistic kernel's result.  The one-slot-per-thread kernel replays the whole launch (result = the
+    generic kernel's, bit for bit); the tile kernel replays from the start of the launch chunk in which the
+    range was left (result = the generic kernel's up to the rounding noise of the chunks before)."""
     dt, n_steps = 2.0e-5, 400
     pressures = np.array([[30.0, 3.0e4, 10.0, 5.0e4], [20.0, 2.0e4, 5.0, 5.0e4], [10.0, 1.0e4, 0.0, 5.0e4]]) * PSI
     action = {name: pressures[i] for i, name in enumerate(NAMES)}
-    fast = make_env("single", 4, gravity=True)
+    fast = make_env("single", 4, variant=variant, gravity=True)
     fast.simulator._callback_ops = []
     fast.run(action, duration=n_steps * dt - 0.5 * dt, disable_progress_bar=True)
     replays = fast.engine.replay_count()
@@ -241,8 +244,13 @@ def test_fast_kernel_falls_back_to_exact_path_when_out_of_range():
     assert generic.engine.replay_count() == 0
     for rf, rg in zip(fast.simulator, generic.simulator):
         xf, xg = rf.position_collection, rg.position_collection
-        for inst in (1, 3):  # replayed from the launch start by the same generic kernel: bit-identical (NaNs included)
-            np.testing.assert_array_equal(xf[inst], xg[inst])
+        for inst in (1, 3):
+            if variant == "fast-uniform":  # replayed from the launch start by the same generic kernel (NaNs included)
+                np.testing.assert_array_equal(xf[inst], xg[inst])
+            else:
+                assert np.array_equal(np.isfinite(xf[inst]), np.isfinite(xg[inst]))
+                ok = np.isfinite(xg[inst])
+                assert np.abs(xf[inst][ok] - xg[inst][ok]).max() <= 1e-6 * max(1.0, np.abs(xg[inst][ok]).max())
         for inst in (0, 2):  # stayed on the fast kernel: equal to rounding noise only
             assert np.abs(xf[inst] - xg[inst]).max() <= POS_TOL * 0.2
             assert np.isfinite(xf[inst]).all()
