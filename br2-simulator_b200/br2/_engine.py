@@ -118,6 +118,12 @@ class Engine:
         _native.check(self.lib.br2_replay_count(self.handle, ctypes.byref(count)))
         return count.value
 
+    def replay_reasons(self):
+        """Why instances left the optimistic kernel: counts per series (rotation angle, curvature angle, strain)."""
+        vals = [ctypes.c_int64(0) for _ in range(3)]
+        _native.check(self.lib.br2_replay_reasons(self.handle, *[ctypes.byref(v) for v in vals]))
+        return dict(zip(("rotation", "curvature", "strain"), (v.value for v in vals)))
+
     def select_kernel(self, variant):
         """0 generic, 1 fast (per-slot constants), 2 fast (uniform constants), 3 tile (several slots per thread), -1 automatic."""
         _native.check(self.lib.br2_select_kernel(self.handle, int(variant)))

@@ -91,8 +91,8 @@ struct KernelChoice {
 // variant 3: tile kernel (BR2_TILE_C slots per thread, uniform constants); `threads` = CTA size
 const KernelChoice kTileKernels[] = {
     {64, br2::br2_step_tile_kernel<BR2_TILE_C, 64, BR2_TILE_MB64>},
-    {128, br2::br2_step_tile_kernel<BR2_TILE_C, 128, 2>},
-    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 1>},
+    {128, br2::br2_step_tile_kernel<BR2_TILE_C, 128, 3>},
+    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2>},
     {256, br2::br2_step_tile_kernel<BR2_TILE_C, 256, 1>},
 };
 
@@ -190,11 +190,15 @@ int validate(const br2_program *p) {
 }
 
 // Plan of the thread-coarsened kernel (br2_tile.cuh), or the reason the assembly does not qualify.
-bool make_tile_plan(const br2_program *p, bool has_extra, int C, br2::TilePlan *plan, std::string *why) {
+struct TileExtraTables {
+    std::vector<int32_t> xi, xj_i;
+    std::vector<double> xj_d;
+};
+
+bool make_tile_plan(const br2_program *p, int C, br2::TilePlan *plan, TileExtraTables *xt, std::string *why) {
     *plan = br2::TilePlan{};
     plan->C = C;
     if (!p->fast_ok || !p->fast_uniform) return *why = "assembly constants are not uniform", false;
-    if (has_extra) return *why = "joints outside the ring pattern (tip-to-base joints)", false;
     if (p->n_rods > BR2_TILE_MAX_RODS) return *why = "too many rods", false;
     const size_t S = (size_t)p->n_slots;
     int threads = 0;
@@ -245,6 +249,71 @@ bool make_tile_plan(const br2_program *p, bool has_extra, int C, br2::TilePlan *
     const double *fc = p->fast_c;
     const double l0 = fc[(size_t)BR2_FC_LN_CR * S], l1 = fc[(size_t)(BR2_FC_LN_CR + 1) * S], l2 = fc[(size_t)(BR2_FC_LN_CR + 2) * S];
     plan->round_section = (l0 == l1 && fabs(l0 - 2.0 * l2) <= 1e-13 * fabs(l0)) ? 1 : 0;
+
+    // ---- extra joints (everything that is not an owned ring joint): tip-to-base joints only ----------------
+    const int XN = BR2_TILE_XI_N(C);
+    xt->xi.assign((size_t)(threads + 128) * XN, -1);  // rows for the idle threads of the CTA too
+    for (int t = 0; t < threads + 128; ++t)
+        for (int j = 0; j < C; ++j) xt->xi[(size_t)t * XN + BR2_TILE_XI_NCNT(C, j)] = 0;
+    auto thread_of = [&](int slot, int *j) {
+        const int r = p->slot_rod[slot];
+        const int k = slot - p->rod_i[r * BR2_ROD_NI + BR2_ROD_SLOT0];
+        *j = k % C;
+        return plan->rod_t0[r] + k / C;
+    };
+    std::vector<int> xe_of_slot(S, -1);
+    auto xe_id = [&](int slot) {
+        if (xe_of_slot[slot] < 0) {
+            xe_of_slot[slot] = plan->n_xe++;
+            int j;
+            const int t = thread_of(slot, &j);
+            xt->xi[(size_t)t * XN + BR2_TILE_XI_PUB(C, j)] = xe_of_slot[slot];
+        }
+        return xe_of_slot[slot];
+    };
+    std::vector<char> owned_joint(p->n_joints, 0);
+    for (size_t sl = 0; sl < S; ++sl) {
+        const int j = p->fast_i[sl * BR2_FAST_NI + BR2_FAST_OWN_JOINT];
+        if (j >= 0) owned_joint[j] = 1;
+    }
+    for (int j = 0; j < p->n_joints; ++j) {
+        if (owned_joint[j]) continue;
+        const int32_t *ji = p->joint_i + (size_t)j * BR2_J_NI;
+        const double *jd = p->joint_d + (size_t)j * BR2_J_ND;
+        if (ji[BR2_J_TYPE] != BR2_JOINT_TIP_TO_BASE) return *why = "a surface joint outside the ring pattern", false;
+        const int xj = plan->n_xj++;
+        int j1, j2;
+        const int t1 = thread_of(ji[BR2_J_S1], &j1), t2 = thread_of(ji[BR2_J_S2], &j2);
+        const int32_t row[8] = {t1, j1, t2, j2, xe_id(ji[BR2_J_Q1]), xe_id(ji[BR2_J_Q2]), xe_id(ji[BR2_J_S1]), xe_id(ji[BR2_J_S2])};
+        xt->xj_i.insert(xt->xj_i.end(), row, row + 8);
+        const double drow[8] = {jd[0], jd[1], jd[3], jd[4], jd[5], jd[6], jd[7], jd[8]};
+        xt->xj_d.insert(xt->xj_d.end(), drow, drow + 8);
+        // the four nodes of the two elements: rod one +F/2, rod two -F/2
+        const int node_slot[4] = {ji[BR2_J_S1], ji[BR2_J_S1] + 1, ji[BR2_J_S2], ji[BR2_J_S2] + 1};
+        for (int q = 0; q < 4; ++q) {
+            int jn;
+            const int tn = thread_of(node_slot[q], &jn);
+            int32_t &cnt = xt->xi[(size_t)tn * XN + BR2_TILE_XI_NCNT(C, jn)];
+            if (cnt >= BR2_FAST_NODE_ITEMS) return *why = "a node receives too many extra joint forces", false;
+            xt->xi[(size_t)tn * XN + BR2_TILE_XI_NITEM(C, jn, cnt)] = (xj << 1) | (q >= 2 ? 1 : 0);
+            ++cnt;
+        }
+    }
+    for (size_t sl = 0; sl < S; ++sl) {
+        if (p->overwrite_src[sl] < 0) continue;
+        int j;
+        const int t = thread_of((int)sl, &j);
+        xt->xi[(size_t)t * XN + BR2_TILE_XI_OW(C, j)] = xe_id(p->overwrite_src[sl]);
+    }
+    // the extra joints are evaluated by the first n_xj threads, spread over the warps
+    if (plan->n_xj > threads) return *why = "more extra joints than threads", false;
+    {
+        const int warps = (threads + 31) / 32;
+        int xj = 0;
+        for (int lane = 0; lane < 32 && xj < plan->n_xj; ++lane)
+            for (int wp = 0; wp < warps && xj < plan->n_xj; ++wp)
+                if (wp * 32 + lane < threads) xt->xi[(size_t)(wp * 32 + lane) * XN + BR2_TILE_XI_JOINT] = xj++;
+    }
     return true;
 }
 
@@ -312,14 +381,26 @@ int br2_create(const br2_program *p, int device, br2_handle *out) {
     }
 #undef UP
     {
-        cudaError_t e = cudaMalloc((void **)&h->replays, sizeof(unsigned long long));
-        if (e == cudaSuccess) e = cudaMemset(h->replays, 0, sizeof(unsigned long long));
+        cudaError_t e = cudaMalloc((void **)&h->replays, 4 * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMemset(h->replays, 0, 4 * sizeof(unsigned long long));
         if (e != cudaSuccess) {
             br2_destroy(h);
             return fail(BR2_ECUDA, std::string("replay counter: ") + cudaGetErrorString(e));
         }
     }
-    h->tile_ok = h->fast_ok && make_tile_plan(p, h->has_extra, BR2_TILE_C, &h->tile, &h->tile_why);
+    {
+        TileExtraTables xt;
+        h->tile_ok = h->fast_ok && make_tile_plan(p, BR2_TILE_C, &h->tile, &xt, &h->tile_why);
+        if (h->tile_ok && h->tile.n_xj > 0) {
+            rc = upload(h, xt.xi.data(), xt.xi.size(), &h->tile.xi);
+            if (rc == BR2_OK) rc = upload(h, xt.xj_i.data(), xt.xj_i.size(), &h->tile.xj_i);
+            if (rc == BR2_OK) rc = upload(h, xt.xj_d.data(), xt.xj_d.size(), &h->tile.xj_d);
+            if (rc != BR2_OK) {
+                br2_destroy(h);
+                return rc;
+            }
+        }
+    }
     h->auto_variant = h->tile_ok ? 3 : h->fast_ok ? (h->fast_uniform ? 2 : 1) : 0;
     rc = br2_select_kernel(h, -1);
     if (rc != BR2_OK) {
@@ -359,7 +440,8 @@ int br2_select_kernel(br2_handle h, int32_t variant) {
     if (variant == 0)
         smem = sizeof(double) * (30 * S + 9 * (size_t)h->t.n_joints + 32);
     else if (variant == 3)
-        smem = sizeof(double) * (size_t)br2::TileSmem<BR2_TILE_C, 0>::WORDS * (size_t)(pick.threads + 1);
+        smem = sizeof(double) * ((size_t)br2::TileSmem<BR2_TILE_C, 0>::ROWS_END * (size_t)(pick.threads + 1) +
+                                 br2::TileSmem<BR2_TILE_C, 0>::TAIL + 13 * (size_t)h->tile.n_xe + 3 * (size_t)h->tile.n_xj);
     else
     {
         // fixed part: 45 T doubles + two [3][T+8] accumulators + O1 (T ints); tail (omega, extra-joint rows,
@@ -590,6 +672,17 @@ int br2_replay_count(br2_handle h, int64_t *count) {
     unsigned long long v = 0;
     CUDA_TRY(cudaMemcpy(&v, h->replays, sizeof(v), cudaMemcpyDeviceToHost));  // synchronises with prior work
     *count = (int64_t)v;
+    return BR2_OK;
+}
+
+int br2_replay_reasons(br2_handle h, int64_t *rotation, int64_t *curvature, int64_t *strain) {
+    if (!h) return fail(BR2_EINVAL, "br2_replay_reasons: NULL handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    unsigned long long v[4] = {0, 0, 0, 0};
+    CUDA_TRY(cudaMemcpy(v, h->replays, sizeof(v), cudaMemcpyDeviceToHost));
+    if (rotation) *rotation = (int64_t)v[1];
+    if (curvature) *curvature = (int64_t)v[2];
+    if (strain) *strain = (int64_t)v[3];
     return BR2_OK;
 }
 

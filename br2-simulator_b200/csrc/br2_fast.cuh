@@ -578,7 +578,26 @@ __global__ void selftest_math_kernel(int which, const double *in, double *out, l
         y = cosc;
         break;
     case 4: y = logmap_scale_small(1.0 - x); break;
-    default: y = exp_small(x); break;
+    case 5: y = exp_small(x); break;
+    // second generation (tile kernel)
+    case 6:
+        sinc_cosc_tiny(x, sinc, cosc);
+        y = sinc;
+        break;
+    case 7:
+        sinc_cosc_tiny(x, sinc, cosc);
+        y = cosc;
+        break;
+    case 8: y = -0.5 * logmap_ratio_tiny(1.0 - x); break;
+    case 9: y = exp_tiny(x); break;
+    case 10: y = sqrt_mid(x); break;
+    default: {  // 11: angle of rotate_directors_tiny for omega = (0, 0, x), half step 1e-5: atan2(R10, R00)
+        double Q[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        const double w[3] = {0.0, 0.0, x};
+        rotate_directors_tiny(Q, w, 1e-5, 1e-5);
+        y = atan2(Q[1], Q[0]);
+        break;
+    }
     }
     out[i] = y;
 }

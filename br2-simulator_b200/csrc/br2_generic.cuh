@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_generic_kernel(
 
     const double dt = p.dt, hdt = 0.5 * p.dt;
     // exact-path replay: resume at the chunk in which the optimistic kernel left its range (status = 1 + chunk)
-    const int resume_chunk = p.only_flagged ? p.status[b] - 1 : 0;
+    const int resume_chunk = p.only_flagged ? (p.status[b] & 0xFF) - 1 : 0;
     const long long first_step = (long long)resume_chunk * p.chunk_steps;
     double time = p.only_flagged ? p.chunk_t0[resume_chunk] : p.t0;
 
@@ -535,8 +535,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_generic_kernel(
         }
     }
     if (p.only_flagged && s == 0) {
+        const int why = p.status[b] >> 8;  // which series' range was left (bit 0 rotation, 1 curvature, 2 strain); 0 = not recorded
         p.status[b] = 0;
         atomicAdd(p.replays, 1ULL);
+        for (int bit = 0; bit < 3; ++bit)
+            if (why & (1 << bit)) atomicAdd(p.replays + 1 + bit, 1ULL);
     }
 #undef SCONST
 }

@@ -38,7 +38,21 @@ struct TilePlan {
     int partner[BR2_TILE_MAX_RODS];         // rod whose elements are rod one of the joints this rod's elements own, or -1
     int owner[BR2_TILE_MAX_RODS];           // rod whose elements own the joints in which this rod's elements are rod one, or -1
     double jd[BR2_TILE_MAX_RODS][8];        // {dv2[3], offset/2} of the joints the rod owns, {dv1[3], offset/2} as rod one
+    // "extra" joints: tip-to-base joints between segments (TipToTipStraightJoint).  Few per
+    // assembly; evaluated by designated threads from data their elements publish; none for single-segment assemblies.
+    int n_xe, n_xj;                         // elements that publish director / omega / radius; extra joints
+    const int *xi;                          // [threads][BR2_TILE_XI_N] per-thread bookkeeping (device)
+    const int *xj_i;                        // [n_xj][8] row1, j1, row2, j2 of the joined elements; xe of Q1, Q2, radius one, radius two
+    const double *xj_d;                     // [n_xj][8] k, nu, l1[3], l2[3]
 };
+// xi fields (C = slots per thread): joint evaluated by the thread | per slot: published xe, overwrite source xe,
+// number of node items | per slot BR2_FAST_NODE_ITEMS items (joint << 1 | sign)
+#define BR2_TILE_XI_JOINT 0
+#define BR2_TILE_XI_PUB(C, j) (1 + (j))
+#define BR2_TILE_XI_OW(C, j) (1 + (C) + (j))
+#define BR2_TILE_XI_NCNT(C, j) (1 + 2 * (C) + (j))
+#define BR2_TILE_XI_NITEM(C, j, q) (1 + 3 * (C) + (j) * BR2_FAST_NODE_ITEMS + (q))
+#define BR2_TILE_XI_N(C) (1 + 3 * (C) + (C) * BR2_FAST_NODE_ITEMS)
 
 struct StepParams {
     DevTables t;

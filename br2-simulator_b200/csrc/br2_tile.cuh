@@ -30,8 +30,8 @@
 
 namespace br2 {
 
-#ifndef BR2_TILE_JD_REGS
-#define BR2_TILE_JD_REGS 0   // joint direction vectors: 1 = registers, 0 = shared-memory rows
+#ifndef BR2_TILE_JD_MODE
+#define BR2_TILE_JD_MODE 1   // joint direction vectors: 0 = per-rod table in shared memory, 1 = constant bank (indexed by rod)
 #endif
 #ifndef BR2_TILE_TA_REGS
 #define BR2_TILE_TA_REGS 0   // actuation torques: 1 = registers, 0 = shared-memory rows
@@ -55,13 +55,17 @@ struct TileSmem {
     static constexpr int HF = PA + C * R;         // [C][3][R] half force of the joint the element owns (it is rod two)
     static constexpr int FS = HF + 3 * C * R;     // [C][3][R] spring part k d of that joint (the torques use only this)
     static constexpr int ZERO_END = FS + 3 * C * R;  // everything above is zeroed at launch
-    static constexpr int JD = ZERO_END;           // [8][R]    {dv2[3], offset/2, dv1[3], offset/2} of the thread's rod
-    static constexpr int TA = JD + 8 * R;         // [C][3][R] actuation torque at full ramp (material frame)
-    static constexpr int WORDS = TA + 3 * C * R;
+    static constexpr int TA = ZERO_END;           // [C][3][R] actuation torque at full ramp (material frame)
+    static constexpr int ROWS_END = TA + 3 * C * R;
+    // after the rows (host: TileSmem<C, 0>::ROWS_END * (threads + 1) + TAIL words, then the extra-joint area)
+    static constexpr int JD = ROWS_END;           // [8][BR2_TILE_MAX_RODS] {dv2[3], offset/2, dv1[3], offset/2} per rod
+    static constexpr int TAIL = 8 * BR2_TILE_MAX_RODS;
+    static constexpr int EX = JD + TAIL;          // extra joints: EXQ [9][n_xe], EXW [3][n_xe], EXR [n_xe], JF [3][n_xj]
 };
 
 constexpr int TILE_F_VALID = 1, TILE_F_ELEM = 2, TILE_F_VOR = 4, TILE_F_ZERO_V = 8, TILE_F_ZERO_W = 16, TILE_F_OWN = 32,
-              TILE_F_REPORT0 = 64, TILE_F_SOFTFIX = 128;
+              TILE_F_REPORT0 = 64, TILE_F_SOFTFIX = 128, TILE_F_XTRA = 256,
+              TILE_F_XJOINT = 512;  // (slot 0 only) the thread evaluates an extra joint
 
 template <int C>
 struct TileThread {
@@ -69,13 +73,11 @@ struct TileThread {
     double dtmc[C];  // dt c_t / node mass
     int fl[C];
     int t, tn, tprev, t1, to, top;
-#if BR2_TILE_JD_REGS
-    double jd[8];
-#endif
+    int rod;
 #if BR2_TILE_TA_REGS
     double ta[C][3];
 #endif
-    bool bad;
+    int bad;  // bit 0: rotation angle, bit 1: curvature angle, bit 2: strain left its series' range (or NaN)
 };
 
 // Where a thread's run sits in the assembly and in the instance's state block.  Recomputed (behind an opaque
@@ -118,10 +120,10 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
     const int n = wh.n, np1 = wh.n + 1;
     double *const inst = wh.inst;
 #define UNI(idx) p.uni[(idx)]
-#if BR2_TILE_JD_REGS
-#define JDV(i) th.jd[(i)]
+#if BR2_TILE_JD_MODE == 1
+#define JDV(i) p.tile.jd[th.rod][(i)]
 #else
-#define JDV(i) sm[L::JD + (i) * R + t]
+#define JDV(i) sm[L::JD + (i) * BR2_TILE_MAX_RODS + th.rod]
 #endif
 #if BR2_TILE_TA_REGS
 #define TAV(j, i) th.ta[(j)][(i)]
@@ -144,6 +146,25 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
     }
 #pragma unroll
     for (int i = 0; i < 9; ++i) sm[L::QF + i * R + t] = Q[0][i];
+    // extra joints (tip-to-base joints between segments): CTA-uniform branch, a handful of threads involved
+    const int n_xe = p.tile.n_xe, n_xj = p.tile.n_xj;
+    constexpr int XN = BR2_TILE_XI_N(C);
+    const int *const xi = p.tile.xi + t * XN;
+    double *const EXQ = sm + L::EX, *const EXW = EXQ + 9 * n_xe, *const EXR = EXW + 3 * n_xe, *const JF = EXR + n_xe;
+    if (n_xj > 0) {
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+            if (th.fl[j] & TILE_F_XTRA) {
+                const int pub = __ldg(xi + BR2_TILE_XI_PUB(C, j));
+                if (pub >= 0) {
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) EXQ[i * n_xe + pub] = Q[j][i];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) EXW[i * n_xe + pub] = w[j][i];
+                }
+            }
+        }
+    }
     __syncthreads();
 
     // =============================== P2: element quantities ==================================
@@ -178,6 +199,10 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
             const double inv_dil = rest_len * inv_len;
             const double rse = seed_rsqrt(dil);  // only thins the ~1e-8 m rest gap of a joint: 2^-20 relative is ample
             ra2[j] = fma(JDV(3), rse, rad);
+            if (n_xj > 0 && (th.fl[j] & TILE_F_XTRA)) {
+                const int pub = __ldg(xi + BR2_TILE_XI_PUB(C, j));
+                if (pub >= 0) EXR[pub] = rad;
+            }
             if (kLast && elem) {
                 inst[15 * np1 + 21 * n + wh.k0 + j] = len[j];
                 inst[15 * np1 + 22 * n + wh.k0 + j] = dil;
@@ -247,7 +272,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
                               fma(Qn[5], q[5], fma(Qn[6], q[6], fma(Qn[7], q[7], Qn[8] * q[8]))))))));
             // y = 1 - cos(theta) with the reference's -1e-10 guard; a benign value off the rod
             const double y = vor ? fma(-0.5, tr, kMisc[7]) : kMisc2[3];
-            th.bad |= !(y <= BR2_Y_MAX && y > 0.0);
+            th.bad |= (y <= BR2_Y_MAX && y > 0.0) ? 0 : 2;
             const double ksr = logmap_ratio_tiny(y) * (-0.5 * UNI(BR2_FC_INV_REST_VLEN));
             const double ks = vor ? ksr : 0.0;
             const double kap[3] = {w0 * ks, w1 * ks, w2 * ks};
@@ -329,6 +354,27 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
         tw[j][1] = fma(rd2[0], fs[2], -rd2[2] * fs[0]);
         tw[j][2] = fma(rd2[1], fs[0], -rd2[0] * fs[1]);
     }
+    // one tip-to-base joint per designated thread (Appendix A.8): un-rounded spring between the two element
+    // surfaces along fixed material directions, un-projected damping, no torque
+    if (n_xj > 0 && (th.fl[0] & TILE_F_XJOINT)) {
+        const int xj = __ldg(xi + BR2_TILE_XI_JOINT);
+        {
+            const int *ji = p.tile.xj_i + xj * 8;
+            const double *jd = p.tile.xj_d + xj * 8;
+            const int row1 = ji[0], j1 = ji[1], row2 = ji[2], j2 = ji[3], q1 = ji[4], q2 = ji[5];
+            const double kj = jd[0], nuj = jd[1];
+            const double r1 = EXR[ji[6]], r2 = EXR[ji[7]];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const double c1 = 0.5 * sm[L::PC + (3 * j1 + i) * R + row1], c2 = 0.5 * sm[L::PC + (3 * j2 + i) * R + row2];
+                const double vrel = 0.5 * sm[L::PV + (3 * j2 + i) * R + row2] - 0.5 * sm[L::PV + (3 * j1 + i) * R + row1];
+                const double a1 = fma(EXQ[i * n_xe + q1], jd[2], fma(EXQ[(3 + i) * n_xe + q1], jd[3], EXQ[(6 + i) * n_xe + q1] * jd[4])) * r1;
+                const double a2 = fma(EXQ[i * n_xe + q2], jd[5], fma(EXQ[(3 + i) * n_xe + q2], jd[6], EXQ[(6 + i) * n_xe + q2] * jd[7])) * r2;
+                const double gap = (c2 + a2) - (c1 + a1);
+                JF[i * n_xj + xj] = 0.5 * fma(kj, gap, -nuj * vrel);
+            }
+        }
+    }
     __syncthreads();
 
     // =============================== P4: assemble, dynamic step ==============================
@@ -374,12 +420,35 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 #pragma unroll
             for (int i = 0; i < 3; ++i)
                 text[i] = fma(TAV(j, i), ramp, fma(Q[j][3 * i], tw[j][0], fma(Q[j][3 * i + 1], tw[j][1], Q[j][3 * i + 2] * tw[j][2])));
+            if (n_xj > 0 && (th.fl[j] & TILE_F_XTRA)) {
+                // half forces of the extra joints on this node
+                const int cnt = __ldg(xi + BR2_TILE_XI_NCNT(C, j));
+                for (int q = 0; q < cnt; ++q) {
+                    const int item = __ldg(xi + BR2_TILE_XI_NITEM(C, j, q));
+                    const double sgn = (item & 1) ? -1.0 : 1.0;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const double f = sgn * JF[i * n_xj + (item >> 1)];
+                        v[j][i] = fma(th.dtmc[j], f, v[j][i]);
+                        if (kLast) r_fext[j][i] += f;
+                    }
+                }
+                // a tip-to-base joint overwrites the downstream base element's director and omega during synchronize
+                // (after the surface joints above have used the old director); sources are start-of-step values
+                const int ow = __ldg(xi + BR2_TILE_XI_OW(C, j));
+                if (ow >= 0) {
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) Q[j][i] = EXQ[i * n_xe + ow];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) w[j][i] = EXW[i * n_xe + ow];
+                }
+            }
             const double dil = len[j] * UNI(BR2_FC_INV_REST_LEN);
             const double strain = (th.fl[j] & TILE_F_ELEM) ? dil - 1.0 : 0.0;
             double damp[3];
             if (p.tile.round_section) {
                 const double e2 = strain * UNI(BR2_FC_LN_CR + 2);
-                th.bad |= !(e2 * e2 <= BR2_E2_MAX);
+                th.bad |= (e2 * e2 <= BR2_E2_MAX) ? 0 : 4;
                 const double ex = exp_tiny(e2);
                 damp[2] = UNI(BR2_FC_CR + 2) * ex;
                 damp[0] = damp[1] = UNI(BR2_FC_CR) * (ex * ex);
@@ -387,7 +456,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     const double e = strain * UNI(BR2_FC_LN_CR + i);
-                    th.bad |= !(e * e <= BR2_E2_MAX);
+                    th.bad |= (e * e <= BR2_E2_MAX) ? 0 : 4;
                     damp[i] = UNI(BR2_FC_CR + i) * exp_tiny(e);
                 }
             }
@@ -449,7 +518,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
                 v[j][i] = (th.fl[j] & TILE_F_ZERO_V) ? 0.0 : v[j][i];
                 x[j][i] = fma(hmult, v[j][i], x[j][i]);
             }
-            th.bad |= rotate_directors_tiny(Q[j], w[j], hdt, hmult);
+            th.bad |= rotate_directors_tiny(Q[j], w[j], hdt, hmult) ? 1 : 0;
         }
     }
 #undef UNI
@@ -502,7 +571,7 @@ __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __gri
 
         TileThread<C> th;
         th.t = t;
-        th.bad = false;
+        th.bad = 0;
         // ---- which run is mine -------------------------------------------------------------------
         const bool active = t < tp.rod_t0[tb.n_rods];
         const int S = tb.n_slots;
@@ -535,6 +604,11 @@ __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __gri
                 if (elem && fi[BR2_FAST_OWN_JOINT] >= 0) f |= TILE_F_OWN;
                 if (pf & BR2_FAST_ZERO_REPORTED) f |= TILE_F_REPORT0;
                 if (valid && fi[BR2_FAST_SOFTFIX_ROW] >= 0) f |= TILE_F_SOFTFIX;
+                if (tp.n_xj > 0 && active) {
+                    const int *xi = tp.xi + t * BR2_TILE_XI_N(C);
+                    if (xi[BR2_TILE_XI_PUB(C, j)] >= 0 || xi[BR2_TILE_XI_OW(C, j)] >= 0 || xi[BR2_TILE_XI_NCNT(C, j)] > 0) f |= TILE_F_XTRA;
+                    if (j == 0 && xi[BR2_TILE_XI_JOINT] >= 0) f |= TILE_F_XJOINT;
+                }
                 th.fl[j] = f;
                 th.dtmc[j] = dt * p.uni[BR2_FC_CT] / tb.slot_c[(long long)BR2_SC_MASS * S + sc];
                 double ta[3] = {0.0, 0.0, 0.0};
@@ -574,15 +648,9 @@ __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __gri
                     for (int i = 0; i < 3; ++i) th.w[j][i] = 0.0;
                 }
             }
-            // joint descriptors of my rod: as rod two of the joints I own {dv2[3], offset/2}, as rod one {dv1[3], offset/2}
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-#if BR2_TILE_JD_REGS
-                th.jd[i] = tp.jd[rod][i];
-#else
-                sm[L::JD + i * R + t] = tp.jd[rod][i];
-#endif
-            }
+            // joint descriptors per rod: as rod two of the joints it owns {dv2[3], offset/2}, as rod one {dv1[3], offset/2}
+            th.rod = rod;
+            for (int i = t; i < 8 * BR2_TILE_MAX_RODS; i += NT) sm[L::JD + i] = tp.jd[i % BR2_TILE_MAX_RODS][i / BR2_TILE_MAX_RODS];
         }
         // zero the exchange arrays (the zero row stays zero for the whole chunk)
         for (int i = t; i < L::ZERO_END; i += NT) sm[i] = 0.0;
@@ -597,7 +665,7 @@ __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __gri
         for (int j = 0; j < C; ++j) {
 #pragma unroll
             for (int i = 0; i < 3; ++i) th.x[j][i] = fma(hdt, th.v[j][i], th.x[j][i]);
-            th.bad |= rotate_directors_tiny(th.Q[j], th.w[j], hdt, hdt);
+            th.bad |= rotate_directors_tiny(th.Q[j], th.w[j], hdt, hdt) ? 1 : 0;
         }
         for (int step = 0; step < n_steps - 1; ++step) {
             tile_step<C, NT, false, false>(p, sm, th, time + hdt, b);
@@ -609,10 +677,11 @@ __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __gri
             tile_step<C, NT, true, false>(p, sm, th, time + hdt, b);
 
         // a CTA that left the series' validity range keeps the chunk-start state and asks for the exact path, which
-        // resumes this instance from the start of this chunk (status = 1 + chunk)
-        if (__syncthreads_or(th.bad)) {
+        // resumes this instance from the start of this chunk (status = 1 + chunk, reason bits from bit 8 up)
+        const int why = (__syncthreads_or(th.bad & 1) ? 1 : 0) | (__syncthreads_or(th.bad & 2) ? 2 : 0) | (__syncthreads_or(th.bad & 4) ? 4 : 0);
+        if (why) {
             if (t == 0) {
-                *(volatile int *)(p.status + b) = 1 + chunk;
+                *(volatile int *)(p.status + b) = (1 + chunk) | (why << 8);
                 __threadfence();
                 *(volatile int *)(p.progress + b) = chunk + 1;
             }

@@ -230,9 +230,16 @@ int br2_select_kernel(br2_handle h, int32_t variant);
 /* Instance-launches the exact-path (generic) kernel had to redo because the fast kernel left the validity
  * range of its series on them (normally 0).  Synchronises the device. */
 int br2_replay_count(br2_handle h, int64_t *count);
+/* Of those, how many left the range of the rotation-angle series (|omega| dt/2 too large), the curvature series
+ * (neighbouring elements rotated too far apart) and the damper's exponential (axial strain too large); only
+ * the tile kernel records reasons.  Synchronises the device. */
+int br2_replay_reasons(br2_handle h, int64_t *rotation, int64_t *curvature, int64_t *strain);
 /* Evaluate the fast kernel's fp64 helpers on device arrays of n doubles (tests only):
  * which = 0 rcp, 1 rsqrt, 2 sinc(theta) [in: theta^2 <= 0.01], 3 cosc(theta) [in: theta^2 <= 0.01],
- *         4 log-map scale [in: cos theta >= 0.875], 5 exp(d) [in: |d| <= 0.02]. */
+ *         4 log-map scale [in: cos theta >= 0.875], 5 exp(d) [in: |d| <= 0.02];
+ *         tile kernel's shorter series: 6 sinc, 7 cosc [in: theta^2 <= 2e-3], 8 log-map scale [in: cos theta >= 0.97],
+ *         9 exp(d) [in: |d| <= 0.09], 10 sqrt to 2^-40, 11 rotation angle of one half step of 1e-5 s about d3
+ *         for omega = in (checks the 1e-14 guard of the reference's axis normalisation). */
 int br2_selftest_math(int32_t which, const double *dev_in, double *dev_out, int64_t n);
 
 /* fp64 roofline denominator: runs a register-resident DFMA chain kernel on `device` and returns the

@@ -61,3 +61,52 @@ def test_exp_near_zero():
     rng = np.random.default_rng(3)
     d = np.concatenate([rng.uniform(-0.02, 0.02, 100000), 10.0 ** rng.uniform(-20, -2, 1000), [0.0, 0.02, -0.02]])
     assert relerr(run(5, d), np.exp(d)).max() <= ULP4
+
+
+# ---- second generation (tile kernel): shorter series, tighter ranges ---------------------------------
+def test_tile_sinc_cosc():
+    import mpmath as mp
+
+    rng = np.random.default_rng(4)
+    t = np.concatenate([10.0 ** rng.uniform(-40, -3, 4000), rng.uniform(0.0, 2e-3, 4000), [0.0, 2e-3]])
+    mp.mp.dps = 120
+    sinc = np.array([float(mp.sin(mp.sqrt(v)) / mp.sqrt(v)) if v > 0 else 1.0 for v in t])
+    cosc = np.array([float((1 - mp.cos(mp.sqrt(v))) / mp.mpf(v)) if v > 0 else 0.5 for v in t])
+    assert relerr(run(6, t), sinc).max() <= ULP4
+    assert relerr(run(7, t), cosc).max() <= ULP4
+
+
+def test_tile_logmap_scale():
+    import mpmath as mp
+
+    mp.mp.dps = 60
+    rng = np.random.default_rng(5)
+    theta = np.concatenate([10.0 ** rng.uniform(-5, -0.7, 4000), rng.uniform(0.0, 0.245, 2000)])
+    c = np.cos(theta)
+    c = c[(c < 1.0 - 1e-11) & (1.0 - c <= 0.03)]
+    want = np.array([float(-mp.mpf(0.5) * mp.acos(mp.mpf(v)) / mp.sin(mp.acos(mp.mpf(v)) + mp.mpf("1e-14"))) for v in c])
+    assert relerr(run(8, c), want).max() <= 8 * 2.0 ** -52
+
+
+def test_tile_exp_and_sqrt():
+    rng = np.random.default_rng(6)
+    d = np.concatenate([rng.uniform(-0.09, 0.09, 100000), 10.0 ** rng.uniform(-20, -2, 1000), [0.0, 0.09, -0.09]])
+    assert relerr(run(9, d), np.exp(d)).max() <= ULP4
+    x = np.concatenate([10.0 ** rng.uniform(-30, 2, 100000), [1.0, 4.0]])
+    assert relerr(run(10, x), np.sqrt(x)).max() <= 2.0 ** -38
+    assert run(10, np.zeros(4)).tolist() == [0.0] * 4
+
+
+def test_tile_rotation_angle_keeps_the_reference_guard():
+    """One kinematic half step rotates by |u| * |u| / (|u| + 1e-14) in the reference (axis = u / (|u| + 1e-14));
+    the tile kernel evaluates that guard from hardware-seed reciprocals."""
+    import mpmath as mp
+
+    mp.mp.dps = 50
+    omega = np.concatenate([10.0 ** np.random.default_rng(7).uniform(-9, 3.3, 4000), [0.0]])
+    u = [mp.mpf(float(w)) * mp.mpf("1e-5") for w in omega]
+    want = np.array([float(v * v / (v + mp.mpf("1e-14"))) if v > 0 else 0.0 for v in u])
+    got = run(11, omega)
+    # the seeds (2^-20 relative) only enter through the guard term 1e-14 |u| / (|u| + 1e-14) <= 1e-14 rad: an absolute
+    # error below 1e-19 rad per half step whatever the angle; the rest is rounding (atan2 of the test included)
+    assert (np.abs(got - want) <= 8 * 2.0 ** -52 * want + 1e-19).all()

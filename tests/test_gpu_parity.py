@@ -25,8 +25,8 @@ SHORT = {"position_collection": "x", "velocity_collection": "v", "director_colle
 
 
 VARIANTS = {"generic": 0, "fast": 1, "fast-uniform": 2, "tile": 3}
-TILE_ASSEMBLIES = ("single",)  # single-segment assemblies qualify for the tile kernel (no tip-to-base joints)
-AUTO_VARIANT = {"single": "tile", "double": "fast-uniform", "triple": "fast-uniform"}
+TILE_ASSEMBLIES = ("single", "double", "triple")
+AUTO_VARIANT = {"single": "tile", "double": "tile", "triple": "tile"}
 
 
 def make_env(assembly, batch, fps=25, variant=None, **kwargs):
