@@ -42,6 +42,12 @@ WORKLOADS = {
                    label="single_br2_v1 x4096/GPU, random pressures U[0,40] psi, gravity on, dt=2e-5 (BASELINE configs[1])"),
     "double": dict(assembly="assembly_double.json", elements=246, gravity=False, seed=1,
                    label="double_br2_v1 with serial joints, random pressures, gravity off, dt=2e-5 (BASELINE configs[2])"),
+    "triple": dict(assembly="assembly_triple.json", elements=369, gravity=True, seed=2,
+                   label="triple_br2_v1 (41 elements per rod), random pressures, gravity on, dt=2e-5"),
+    "triple200": dict(assembly="assembly_triple.json", elements=1800, gravity=True, seed=2, dt=5.0e-6,
+                      rod_db="rod_library_n200.json",
+                      label="triple_br2_v1 with 200 elements per rod (1809 node slots, cluster of 3 CTAs per instance), "
+                            "random pressures, gravity on, dt=5e-6 (BASELINE configs[3])"),
 }
 
 
@@ -213,14 +219,15 @@ def run_ours(args, world, rank, local):
     w = WORKLOADS[args.workload]
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
-    B, M, dt = args.batch, args.substeps, 2.0e-5
+    B, M, dt = args.batch, args.substeps, w.get("dt", 2.0e-5)
+    rod_db = os.path.join(DATA, w.get("rod_db", "rod_library.json"))
     rng = np.random.default_rng(w["seed"] + 1000 * rank)
     pressures = rng.uniform(0.0, 40.0, size=(3, B)) * PSI
 
     # Environment's batch is the GLOBAL instance count; under torchrun it keeps this rank's contiguous share (B)
-    env = Environment("bench", batch=B * world, device=device, create_dirs=False)
+    env = Environment("bench", time_step=dt, batch=B * world, device=device, create_dirs=False)
     assert env.batch == B
-    env.reset(ROD_DB, os.path.join(DATA, w["assembly"]), gravity=w["gravity"])
+    env.reset(rod_db, os.path.join(DATA, w["assembly"]), gravity=w["gravity"])
     env.simulator._callback_ops = []  # stepping only; capture is a separate (next-row) path
     engine = env.engine
     if args.variant >= 0:

@@ -118,6 +118,13 @@ class Engine:
         _native.check(self.lib.br2_replay_count(self.handle, ctypes.byref(count)))
         return count.value
 
+    def unresolved_count(self):
+        """Instances frozen because they left the optimistic kernel's range and no exact-path kernel fits the
+        assembly (cluster-sized assemblies only; synchronises)."""
+        count = ctypes.c_int64(0)
+        _native.check(self.lib.br2_unresolved_count(self.handle, ctypes.byref(count)))
+        return count.value
+
     def replay_reasons(self):
         """Why instances left the optimistic kernel: counts per series (rotation angle, curvature angle, strain)."""
         vals = [ctypes.c_int64(0) for _ in range(3)]

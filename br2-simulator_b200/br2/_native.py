@@ -46,7 +46,7 @@ EXPORTS = (
     "br2_last_error", "br2_abi_version", "br2_create", "br2_destroy", "br2_words_per_instance",
     "br2_bind_state", "br2_set_actuation", "br2_step", "br2_step_host", "br2_count_steps",
     "br2_kernel_info", "br2_fp64_peak_tflops", "br2_select_kernel", "br2_selftest_math", "br2_replay_count",
-    "br2_replay_reasons",
+    "br2_replay_reasons", "br2_unresolved_count",
 )
 
 
@@ -76,6 +76,7 @@ def load():
     lib.br2_kernel_info.argtypes = [ctypes.c_void_p] + [_i32p] * 6
     lib.br2_select_kernel.argtypes = [ctypes.c_void_p, ctypes.c_int32]
     lib.br2_replay_count.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]
+    lib.br2_unresolved_count.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]
     lib.br2_replay_reasons.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_int64)] * 3
     lib.br2_selftest_math.argtypes = [ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
     lib.br2_fp64_peak_tflops.argtypes = [ctypes.c_int, ctypes.c_int32, _f64p]

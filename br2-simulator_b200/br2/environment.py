@@ -218,6 +218,11 @@ class Environment:
                 deltas[short] = torch.nan_to_num(norms, nan=-np.inf).amax(dim=-1).cpu().numpy()
             status.steady_state_deltas = deltas
         if check_nan:
+            stuck = engine.unresolved_count()
+            if stuck:
+                raise _native.Br2Error(
+                    "%d instance(s) left the validity range of the device kernel's series (%s) and this assembly is too "
+                    "large for the exact-path kernel; they stopped advancing" % (stuck, engine.replay_reasons()))
             flags = {}
             for label, short in (("position", "x"), ("velocity", "v"), ("director", "Q"), ("omega", "w")):
                 per_instance = torch.isnan(self._state_stack(short)).flatten(1).any(dim=1)

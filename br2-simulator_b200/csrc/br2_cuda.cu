@@ -90,11 +90,18 @@ struct KernelChoice {
 #endif
 // variant 3: tile kernel (BR2_TILE_C slots per thread, uniform constants); `threads` = CTA size
 const KernelChoice kTileKernels[] = {
-    {64, br2::br2_step_tile_kernel<BR2_TILE_C, 64, BR2_TILE_MB64>},
-    {128, br2::br2_step_tile_kernel<BR2_TILE_C, 128, 3>},
-    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2>},
-    {256, br2::br2_step_tile_kernel<BR2_TILE_C, 256, 1>},
+    {64, br2::br2_step_tile_kernel<BR2_TILE_C, 64, BR2_TILE_MB64, false>},
+    {128, br2::br2_step_tile_kernel<BR2_TILE_C, 128, 3, false>},
+    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, false>},
+    {256, br2::br2_step_tile_kernel<BR2_TILE_C, 256, 1, false>},
+    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, false>},
 };
+// one CTA per group of ring-connected rods, launched as a thread-block cluster per instance
+const KernelChoice kTileClusterKernels[] = {
+    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true>},
+    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, true>},
+};
+const int kTileMaxCtaThreads = 320, kTileOneCtaThreads = 256;
 
 // variant 0: generic, 1: fast with per-slot constants, 2: fast with uniform constants
 const KernelChoice kKernels[3][6] = {
@@ -155,9 +162,9 @@ int validate(const br2_program *p) {
     if (!p) return fail(BR2_EINVAL, "program is NULL");
     if (p->abi_version != BR2_ABI_VERSION) return fail(BR2_EINVAL, "br2_program.abi_version mismatch");
     if (p->n_slots <= 0 || p->n_rods <= 0) return fail(BR2_EINVAL, "empty assembly");
-    if (p->n_slots > 1024)
-        return fail(BR2_ELIMIT, "assembly has " + std::to_string(p->n_slots) +
-                                    " node slots; one CTA integrates one assembly and holds at most 1024");
+    if (p->n_slots > 8 * 2 * kTileMaxCtaThreads)
+        return fail(BR2_ELIMIT, "assembly has " + std::to_string(p->n_slots) + " node slots; one cluster holds at most " +
+                                    std::to_string(8 * 2 * kTileMaxCtaThreads));
     if (p->n_actions > 32) return fail(BR2_ELIMIT, "more than 32 actions");
     int slots = 0;
     for (int r = 0; r < p->n_rods; ++r) {
@@ -201,13 +208,45 @@ bool make_tile_plan(const br2_program *p, int C, br2::TilePlan *plan, TileExtraT
     if (!p->fast_ok || !p->fast_uniform) return *why = "assembly constants are not uniform", false;
     if (p->n_rods > BR2_TILE_MAX_RODS) return *why = "too many rods", false;
     const size_t S = (size_t)p->n_slots;
-    int threads = 0;
+    // ring-connected rods (a segment) must share a CTA: union-find over the owned surface joints
+    int group[BR2_TILE_MAX_RODS];
+    for (int r = 0; r < p->n_rods; ++r) group[r] = r;
+    auto find = [&](int r) {
+        while (group[r] != r) r = group[r] = group[group[r]];
+        return r;
+    };
+    for (size_t sl = 0; sl < S; ++sl) {
+        const int j = p->fast_i[sl * BR2_FAST_NI + BR2_FAST_OWN_JOINT];
+        if (j < 0) continue;
+        const int a = find(p->slot_rod[p->joint_i[(size_t)j * BR2_J_NI + BR2_J_S1]]), b = find(p->slot_rod[sl]);
+        if (a != b) group[a > b ? a : b] = a > b ? b : a;
+    }
+    int total_threads = 0;
+    for (int r = 0; r < p->n_rods; ++r) total_threads += (p->rod_i[r * BR2_ROD_NI + BR2_ROD_N] + 1 + C - 1) / C;
+    int one_cta_threads = kTileOneCtaThreads;
+    if (const char *env = getenv("BR2_TILE_ONE_CTA_THREADS")) one_cta_threads = atoi(env);  // tests force the cluster path
+    const bool split = total_threads > one_cta_threads;
+    int rank_of_group[BR2_TILE_MAX_RODS];
+    for (int r = 0; r < p->n_rods; ++r) rank_of_group[r] = -1;
+    plan->n_ctas = 0;
     for (int r = 0; r < p->n_rods; ++r) {
-        plan->rod_t0[r] = threads;
-        threads += (p->rod_i[r * BR2_ROD_NI + BR2_ROD_N] + 1 + C - 1) / C;
+        const int g = find(r);
+        if (rank_of_group[g] < 0) rank_of_group[g] = split ? plan->n_ctas++ : 0;
+        if (plan->n_ctas > 8) return *why = "more than 8 groups of ring-connected rods", false;
+        const int rank = rank_of_group[g];
+        plan->rod_cta[r] = rank;
+        plan->rod_t0[r] = plan->cta_threads[rank];
+        plan->cta_threads[rank] += (p->rod_i[r * BR2_ROD_NI + BR2_ROD_N] + 1 + C - 1) / C;
         plan->partner[r] = plan->owner[r] = -1;
     }
-    for (int r = p->n_rods; r <= BR2_TILE_MAX_RODS; ++r) plan->rod_t0[r] = threads;
+    if (!split) plan->n_ctas = 1;
+    int threads = 0;  // of the largest CTA
+    for (int c = 0; c < plan->n_ctas; ++c) threads = plan->cta_threads[c] > threads ? plan->cta_threads[c] : threads;
+    if (threads > kTileMaxCtaThreads)
+        return *why = "a group of ring-connected rods needs " + std::to_string(threads) + " threads (max " +
+                      std::to_string(kTileMaxCtaThreads) + ")", false;
+    plan->rod_t0[BR2_TILE_MAX_RODS] = threads;
+    plan->xi_stride = ((threads + 63) / 64) * 64 + 64;
     auto close = [](double a, double b, double tol) { return fabs(a - b) <= tol; };
     for (int r = 0; r < p->n_rods; ++r) {
         const int32_t *ri = p->rod_i + r * BR2_ROD_NI;
@@ -252,14 +291,18 @@ bool make_tile_plan(const br2_program *p, int C, br2::TilePlan *plan, TileExtraT
 
     // ---- extra joints (everything that is not an owned ring joint): tip-to-base joints only ----------------
     const int XN = BR2_TILE_XI_N(C);
-    xt->xi.assign((size_t)(threads + 128) * XN, -1);  // rows for the idle threads of the CTA too
-    for (int t = 0; t < threads + 128; ++t)
+    const int xrows = plan->n_ctas * plan->xi_stride;  // rows for the idle threads of the CTAs too
+    xt->xi.assign((size_t)xrows * XN, -1);
+    for (int t = 0; t < xrows; ++t)
         for (int j = 0; j < C; ++j) xt->xi[(size_t)t * XN + BR2_TILE_XI_NCNT(C, j)] = 0;
-    auto thread_of = [&](int slot, int *j) {
+    int slot_rank = 0, slot_row = 0;  // set by thread_of: cluster rank and thread (= shared-memory row) of the slot
+    auto thread_of = [&](int slot, int *j) {  // row of the slot's thread in xi
         const int r = p->slot_rod[slot];
         const int k = slot - p->rod_i[r * BR2_ROD_NI + BR2_ROD_SLOT0];
         *j = k % C;
-        return plan->rod_t0[r] + k / C;
+        slot_rank = plan->rod_cta[r];
+        slot_row = plan->rod_t0[r] + k / C;
+        return slot_rank * plan->xi_stride + slot_row;
     };
     std::vector<int> xe_of_slot(S, -1);
     auto xe_id = [&](int slot) {
@@ -283,9 +326,13 @@ bool make_tile_plan(const br2_program *p, int C, br2::TilePlan *plan, TileExtraT
         if (ji[BR2_J_TYPE] != BR2_JOINT_TIP_TO_BASE) return *why = "a surface joint outside the ring pattern", false;
         const int xj = plan->n_xj++;
         int j1, j2;
-        const int t1 = thread_of(ji[BR2_J_S1], &j1), t2 = thread_of(ji[BR2_J_S2], &j2);
-        const int32_t row[8] = {t1, j1, t2, j2, xe_id(ji[BR2_J_Q1]), xe_id(ji[BR2_J_Q2]), xe_id(ji[BR2_J_S1]), xe_id(ji[BR2_J_S2])};
-        xt->xj_i.insert(xt->xj_i.end(), row, row + 8);
+        thread_of(ji[BR2_J_S1], &j1);
+        const int rank1 = slot_rank, row1 = slot_row;
+        thread_of(ji[BR2_J_S2], &j2);
+        const int rank2 = slot_rank, row2 = slot_row;
+        const int32_t row[12] = {rank1, row1, j1, rank2, row2, j2, xe_id(ji[BR2_J_Q1]), xe_id(ji[BR2_J_Q2]),
+                                 xe_id(ji[BR2_J_S1]), xe_id(ji[BR2_J_S2]), 0, 0};
+        xt->xj_i.insert(xt->xj_i.end(), row, row + 12);
         const double drow[8] = {jd[0], jd[1], jd[3], jd[4], jd[5], jd[6], jd[7], jd[8]};
         xt->xj_d.insert(xt->xj_d.end(), drow, drow + 8);
         // the four nodes of the two elements: rod one +F/2, rod two -F/2
@@ -305,14 +352,24 @@ bool make_tile_plan(const br2_program *p, int C, br2::TilePlan *plan, TileExtraT
         const int t = thread_of((int)sl, &j);
         xt->xi[(size_t)t * XN + BR2_TILE_XI_OW(C, j)] = xe_id(p->overwrite_src[sl]);
     }
-    // the extra joints are evaluated by the first n_xj threads, spread over the warps
-    if (plan->n_xj > threads) return *why = "more extra joints than threads", false;
+    // the extra joints are evaluated by the CTA of their rod-two element, spread over its warps
     {
-        const int warps = (threads + 31) / 32;
-        int xj = 0;
-        for (int lane = 0; lane < 32 && xj < plan->n_xj; ++lane)
-            for (int wp = 0; wp < warps && xj < plan->n_xj; ++wp)
-                if (wp * 32 + lane < threads) xt->xi[(size_t)(wp * 32 + lane) * XN + BR2_TILE_XI_JOINT] = xj++;
+        int next_lane[8] = {0, 0, 0, 0, 0, 0, 0, 0}, next_warp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int xj = 0; xj < plan->n_xj; ++xj) {
+            const int rank = xt->xj_i[(size_t)xj * 12 + 3];
+            const int ct = plan->cta_threads[rank], warps = (ct + 31) / 32;
+            int t = -1;
+            for (int tries = 0; tries < 32 * warps && t < 0; ++tries) {
+                const int cand = next_warp[rank] * 32 + next_lane[rank];
+                if (++next_warp[rank] == warps) {
+                    next_warp[rank] = 0;
+                    ++next_lane[rank];
+                }
+                if (cand < ct && next_lane[rank] <= 32) t = cand;
+            }
+            if (t < 0) return *why = "more extra joints than threads", false;
+            xt->xi[(size_t)(rank * plan->xi_stride + t) * XN + BR2_TILE_XI_JOINT] = xj;
+        }
     }
     return true;
 }
@@ -423,11 +480,20 @@ int br2_select_kernel(br2_handle h, int32_t variant) {
     const size_t S = (size_t)h->t.n_slots;
     KernelChoice pick{0, nullptr};
     if (variant == 3) {
-        for (const KernelChoice &kc : kTileKernels)
-            if (kc.threads >= h->tile.rod_t0[h->t.n_rods]) {
-                pick = kc;
-                break;
-            }
+        const int need = h->tile.rod_t0[BR2_TILE_MAX_RODS];  // threads of the largest CTA
+        if (h->tile.n_ctas > 1) {
+            for (const KernelChoice &kc : kTileClusterKernels)
+                if (kc.threads >= need) {
+                    pick = kc;
+                    break;
+                }
+        } else {
+            for (const KernelChoice &kc : kTileKernels)
+                if (kc.threads >= need) {
+                    pick = kc;
+                    break;
+                }
+        }
     } else {
         for (const KernelChoice &kc : kKernels[variant])
             if (kc.threads >= h->t.n_slots) {
@@ -441,7 +507,7 @@ int br2_select_kernel(br2_handle h, int32_t variant) {
         smem = sizeof(double) * (30 * S + 9 * (size_t)h->t.n_joints + 32);
     else if (variant == 3)
         smem = sizeof(double) * ((size_t)br2::TileSmem<BR2_TILE_C, 0>::ROWS_END * (size_t)(pick.threads + 1) +
-                                 br2::TileSmem<BR2_TILE_C, 0>::TAIL + 13 * (size_t)h->tile.n_xe + 3 * (size_t)h->tile.n_xj);
+                                 br2::TileSmem<BR2_TILE_C, 0>::TAIL + 25 * (size_t)h->tile.n_xe + 3 * (size_t)h->tile.n_xj);
     else
     {
         // fixed part: 45 T doubles + two [3][T+8] accumulators + O1 (T ints); tail (omega, extra-joint rows,
@@ -456,7 +522,22 @@ int br2_select_kernel(br2_handle h, int32_t variant) {
     h->kernel = pick;
     h->smem_bytes = smem;
     h->variant = variant;
-    if (variant == 3) {
+    if (variant == 3 && h->tile.n_ctas > 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)h->tile.n_ctas * 64);
+        cfg.blockDim = dim3((unsigned)pick.threads);
+        cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)h->tile.n_ctas;
+        attr[0].val.clusterDim.y = attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int clusters = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveClusters(&clusters, (const void *)pick.fn, &cfg));
+        if (clusters < 1) return fail(BR2_ELIMIT, "the tile kernel's cluster does not fit on the device");
+        h->tile_capacity = clusters;  // in clusters
+    } else if (variant == 3) {
         int blocks = 0, sms = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, (const void *)pick.fn, pick.threads, smem));
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
@@ -464,15 +545,20 @@ int br2_select_kernel(br2_handle h, int32_t variant) {
         h->tile_capacity = blocks * sms;
     }
     if (variant != 0) {
+        // exact-path replay kernel; an assembly that only fits a cluster has none (one CTA cannot hold it): instances
+        // that leave the optimistic kernel's range then stay flagged and frozen -- br2_unresolved_count reports them
+        h->replay = KernelChoice{0, nullptr};
         for (const KernelChoice &kc : kKernels[0])
             if (kc.threads >= h->t.n_slots) {
                 h->replay = kc;
                 break;
             }
         h->replay_smem = sizeof(double) * (30 * S + 9 * (size_t)h->t.n_joints + 32);
-        if (h->replay_smem > 227 * 1024) return fail(BR2_ELIMIT, "assembly too large for the replay kernel");
-        CUDA_TRY(cudaFuncSetAttribute((const void *)h->replay.fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)h->replay_smem));
+        if (h->replay_smem > 227 * 1024) h->replay = KernelChoice{0, nullptr};
+        if (!h->replay.fn && variant != 3) return fail(BR2_ELIMIT, "assembly too large for the replay kernel");
+        if (h->replay.fn)
+            CUDA_TRY(cudaFuncSetAttribute((const void *)h->replay.fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)h->replay_smem));
     }
     return BR2_OK;
 }
@@ -590,9 +676,24 @@ int br2_step(br2_handle h, int64_t n_steps, double t0, double dt, void *stream, 
         const long long items = h->batch * (long long)sp.n_chunks;
         grid = (unsigned)(items < h->tile_capacity ? items : h->tile_capacity);
     }
-    CUDA_TRY(cudaLaunchKernel((const void *)h->kernel.fn, dim3(grid), dim3((unsigned)h->kernel.threads), args,
-                              h->smem_bytes, (cudaStream_t)stream));
-    if (h->variant != 0) {
+    if (h->variant == 3 && h->tile.n_ctas > 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid * (unsigned)h->tile.n_ctas);  // `grid` clusters
+        cfg.blockDim = dim3((unsigned)h->kernel.threads);
+        cfg.dynamicSmemBytes = h->smem_bytes;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)h->tile.n_ctas;
+        attr[0].val.clusterDim.y = attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelExC(&cfg, (const void *)h->kernel.fn, args));
+    } else {
+        CUDA_TRY(cudaLaunchKernel((const void *)h->kernel.fn, dim3(grid), dim3((unsigned)h->kernel.threads), args,
+                                  h->smem_bytes, (cudaStream_t)stream));
+    }
+    if (h->variant != 0 && h->replay.fn) {
         // exact-path replay, stream-ordered behind the fast kernel: CTAs of unflagged instances exit at once
         sp.only_flagged = 1;
         CUDA_TRY(cudaLaunchKernel((const void *)h->replay.fn, dim3((unsigned)h->batch), dim3((unsigned)h->replay.threads),
@@ -672,6 +773,17 @@ int br2_replay_count(br2_handle h, int64_t *count) {
     unsigned long long v = 0;
     CUDA_TRY(cudaMemcpy(&v, h->replays, sizeof(v), cudaMemcpyDeviceToHost));  // synchronises with prior work
     *count = (int64_t)v;
+    return BR2_OK;
+}
+
+int br2_unresolved_count(br2_handle h, int64_t *count) {
+    if (!h || !count) return fail(BR2_EINVAL, "br2_unresolved_count: bad argument");
+    *count = 0;
+    if (!h->status || h->batch <= 0) return BR2_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    std::vector<int> host((size_t)h->batch);
+    CUDA_TRY(cudaMemcpy(host.data(), h->status, sizeof(int) * (size_t)h->batch, cudaMemcpyDeviceToHost));
+    for (int v : host) *count += (v != 0);
     return BR2_OK;
 }
 

@@ -34,15 +34,20 @@ struct DevTables {
 struct TilePlan {
     int C;                                  // slots per thread
     int round_section;                      // ln c_r1 = ln c_r2 = 2 ln c_r3: one exponential per element and step
-    int rod_t0[BR2_TILE_MAX_RODS + 1];      // first thread of each rod; [n_rods] = threads in use
+    int n_ctas;                             // CTAs per instance: 1, or one per group of ring-connected rods (a thread-block
+                                            // cluster) when the assembly does not fit the registers of one SM
+    int rod_cta[BR2_TILE_MAX_RODS];         // cluster rank of the CTA that integrates the rod
+    int cta_threads[8];                     // threads in use per rank
+    int xi_stride;                          // rows of `xi` per rank
+    int rod_t0[BR2_TILE_MAX_RODS + 1];      // first thread of each rod inside its CTA
     int partner[BR2_TILE_MAX_RODS];         // rod whose elements are rod one of the joints this rod's elements own, or -1
     int owner[BR2_TILE_MAX_RODS];           // rod whose elements own the joints in which this rod's elements are rod one, or -1
     double jd[BR2_TILE_MAX_RODS][8];        // {dv2[3], offset/2} of the joints the rod owns, {dv1[3], offset/2} as rod one
     // "extra" joints: tip-to-base joints between segments (TipToTipStraightJoint).  Few per
     // assembly; evaluated by designated threads from data their elements publish; none for single-segment assemblies.
     int n_xe, n_xj;                         // elements that publish director / omega / radius; extra joints
-    const int *xi;                          // [threads][BR2_TILE_XI_N] per-thread bookkeeping (device)
-    const int *xj_i;                        // [n_xj][8] row1, j1, row2, j2 of the joined elements; xe of Q1, Q2, radius one, radius two
+    const int *xi;                          // [n_ctas][xi_stride][BR2_TILE_XI_N] per-thread bookkeeping (device)
+    const int *xj_i;                        // [n_xj][12] rank1, row1, j1, rank2, row2, j2 of the joined elements; xe of Q1, Q2, radius one, radius two
     const double *xj_d;                     // [n_xj][8] k, nu, l1[3], l2[3]
 };
 // xi fields (C = slots per thread): joint evaluated by the thread | per slot: published xe, overwrite source xe,

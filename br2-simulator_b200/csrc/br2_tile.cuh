@@ -25,10 +25,26 @@
 // connects equal element indices of two rods and all joints of a rod pair share one descriptor.
 #pragma once
 
+#include <cooperative_groups.h>
+
 #include "br2_math.cuh"
 #include "br2_tables.cuh"
 
 namespace br2 {
+
+// CTA-wide or (kCluster) cluster-wide barrier, and the address of a peer CTA's copy of a shared-memory location
+template <bool kCluster>
+__device__ __forceinline__ void tile_sync() {
+    if (kCluster)
+        cooperative_groups::this_cluster().sync();
+    else
+        __syncthreads();
+}
+template <bool kCluster, typename T>
+__device__ __forceinline__ T *tile_peer(T *local, int rank) {
+    if (kCluster) return cooperative_groups::this_cluster().map_shared_rank(local, rank);
+    return local;
+}
 
 #ifndef BR2_TILE_JD_MODE
 #define BR2_TILE_JD_MODE 1   // joint direction vectors: 0 = per-rod table in shared memory, 1 = constant bank (indexed by rod)
@@ -60,7 +76,8 @@ struct TileSmem {
     // after the rows (host: TileSmem<C, 0>::ROWS_END * (threads + 1) + TAIL words, then the extra-joint area)
     static constexpr int JD = ROWS_END;           // [8][BR2_TILE_MAX_RODS] {dv2[3], offset/2, dv1[3], offset/2} per rod
     static constexpr int TAIL = 8 * BR2_TILE_MAX_RODS;
-    static constexpr int EX = JD + TAIL;          // extra joints: EXQ [9][n_xe], EXW [3][n_xe], EXR [n_xe], JF [3][n_xj]
+    static constexpr int EX = JD + TAIL;          // extra joints (rank 0's copy is the live one in a cluster):
+                                                  // EXQ [2][9][n_xe], EXW [2][3][n_xe] (by step parity), EXR [n_xe], JF [3][n_xj]
 };
 
 constexpr int TILE_F_VALID = 1, TILE_F_ELEM = 2, TILE_F_VOR = 4, TILE_F_ZERO_V = 8, TILE_F_ZERO_W = 16, TILE_F_OWN = 32,
@@ -89,17 +106,22 @@ struct TileWhere {
 };
 
 template <int C>
-__device__ __forceinline__ TileWhere tile_where(const StepParams &p, int t, long long b) {
+__device__ __forceinline__ TileWhere tile_where(const StepParams &p, int t, long long b, int rank) {
     asm volatile("" : "+r"(t));
     const DevTables &tb = p.t;
     const TilePlan &tp = p.tile;
     TileWhere wh;
-    int rod = 0;
-    for (int r = 1; r < tb.n_rods; ++r) rod = (t >= tp.rod_t0[r]) ? r : rod;
+    int rod = -1, first = 0;
+    for (int r = tb.n_rods - 1; r >= 0; --r) {
+        if (tp.rod_cta[r] != rank) continue;
+        first = r;
+        if (rod < 0 && t >= tp.rod_t0[r]) rod = r;
+    }
+    if (rod < 0) rod = first;
     const int *ri = tb.rod_i + rod * BR2_ROD_NI;
     wh.rod = rod;
     wh.n = ri[BR2_ROD_N];
-    wh.k0 = (t < tp.rod_t0[tb.n_rods]) ? C * (t - tp.rod_t0[rod]) : wh.n + 1;
+    wh.k0 = (t < tp.cta_threads[rank]) ? C * (t - tp.rod_t0[rod]) : wh.n + 1;
     wh.s0 = ri[BR2_ROD_SLOT0] + wh.k0;  // table slot of my first node (when valid)
     wh.inst = p.state + b * tb.words + ri[BR2_ROD_WOFF];
     return wh;
@@ -108,15 +130,16 @@ __device__ __forceinline__ TileWhere tile_where(const StepParams &p, int t, long
 // One PositionVerlet step of a thread's run.  kEnd: last step of a chunk (ends with a single kinematic half step
 // instead of the fused pair, so the state is a whole-step state); kLast: last step of the launch (also reports
 // the callback quantities).
-template <int C, int NT, bool kEnd, bool kLast>
-__device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileThread<C> &th, double time_mid, long long b) {
+template <int C, int NT, bool kEnd, bool kLast, bool kCluster>
+__device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileThread<C> &th, double time_mid, long long b,
+                                          int rank, int parity) {
     using L = TileSmem<C, NT>;
     constexpr int R = L::R;
     const DevTables &tb = p.t;
     const int t = th.t;
     const double dt = p.dt, hdt = 0.5 * p.dt;
     TileWhere wh{};
-    if (kLast) wh = tile_where<C>(p, t, b);
+    if (kLast) wh = tile_where<C>(p, t, b, rank);
     const int n = wh.n, np1 = wh.n + 1;
     double *const inst = wh.inst;
 #define UNI(idx) p.uni[(idx)]
@@ -149,8 +172,12 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
     // extra joints (tip-to-base joints between segments): CTA-uniform branch, a handful of threads involved
     const int n_xe = p.tile.n_xe, n_xj = p.tile.n_xj;
     constexpr int XN = BR2_TILE_XI_N(C);
-    const int *const xi = p.tile.xi + t * XN;
-    double *const EXQ = sm + L::EX, *const EXW = EXQ + 9 * n_xe, *const EXR = EXW + 3 * n_xe, *const JF = EXR + n_xe;
+    const int *const xi = p.tile.xi + (rank * p.tile.xi_stride + t) * XN;
+    // director / omega rows are double-buffered by step parity: the overwrite in P4 reads them while a faster
+    // thread may already be publishing the next step's values
+    double *const EX0 = tile_peer<kCluster>(sm + L::EX, 0);
+    double *const EXQ = EX0 + parity * 9 * n_xe, *const EXW = EX0 + 18 * n_xe + parity * 3 * n_xe;
+    double *const EXR = EX0 + 24 * n_xe, *const JF = EXR + n_xe;
     if (n_xj > 0) {
 #pragma unroll
         for (int j = 0; j < C; ++j) {
@@ -165,7 +192,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
             }
         }
     }
-    __syncthreads();
+    tile_sync<kCluster>();
 
     // =============================== P2: element quantities ==================================
     double len[C], ra2[C];
@@ -250,7 +277,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 #pragma unroll
         for (int i = 0; i < 3; ++i) sm[L::SKL + i * R + t] = skp[i];
     }
-    __syncthreads();
+    tile_sync<kCluster>();
 
     // =============================== P3: Voronoi couples and own joints ======================
     double tw[C][3];  // world-frame joint torque on my element (own joint now, rod-one joint in P4)
@@ -359,15 +386,16 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
     if (n_xj > 0 && (th.fl[0] & TILE_F_XJOINT)) {
         const int xj = __ldg(xi + BR2_TILE_XI_JOINT);
         {
-            const int *ji = p.tile.xj_i + xj * 8;
+            const int *ji = p.tile.xj_i + xj * 12;
             const double *jd = p.tile.xj_d + xj * 8;
-            const int row1 = ji[0], j1 = ji[1], row2 = ji[2], j2 = ji[3], q1 = ji[4], q2 = ji[5];
+            const double *const sm1 = tile_peer<kCluster>(sm, ji[0]), *const sm2 = tile_peer<kCluster>(sm, ji[3]);
+            const int row1 = ji[1], j1 = ji[2], row2 = ji[4], j2 = ji[5], q1 = ji[6], q2 = ji[7];
             const double kj = jd[0], nuj = jd[1];
-            const double r1 = EXR[ji[6]], r2 = EXR[ji[7]];
+            const double r1 = EXR[ji[8]], r2 = EXR[ji[9]];
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                const double c1 = 0.5 * sm[L::PC + (3 * j1 + i) * R + row1], c2 = 0.5 * sm[L::PC + (3 * j2 + i) * R + row2];
-                const double vrel = 0.5 * sm[L::PV + (3 * j2 + i) * R + row2] - 0.5 * sm[L::PV + (3 * j1 + i) * R + row1];
+                const double c1 = 0.5 * sm1[L::PC + (3 * j1 + i) * R + row1], c2 = 0.5 * sm2[L::PC + (3 * j2 + i) * R + row2];
+                const double vrel = 0.5 * sm2[L::PV + (3 * j2 + i) * R + row2] - 0.5 * sm1[L::PV + (3 * j1 + i) * R + row1];
                 const double a1 = fma(EXQ[i * n_xe + q1], jd[2], fma(EXQ[(3 + i) * n_xe + q1], jd[3], EXQ[(6 + i) * n_xe + q1] * jd[4])) * r1;
                 const double a2 = fma(EXQ[i * n_xe + q2], jd[5], fma(EXQ[(3 + i) * n_xe + q2], jd[6], EXQ[(6 + i) * n_xe + q2] * jd[7])) * r2;
                 const double gap = (c2 + a2) - (c1 + a1);
@@ -375,7 +403,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
             }
         }
     }
-    __syncthreads();
+    tile_sync<kCluster>();
 
     // =============================== P4: assemble, dynamic step ==============================
     {
@@ -531,16 +559,21 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 #else
 #define BR2_TILE_BOUNDS(NT, MB) __launch_bounds__(NT, MB)
 #endif
-template <int C, int NT, int kMinBlocks>
+template <int C, int NT, int kMinBlocks, bool kCluster>
 __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __grid_constant__ StepParams p) {
     using L = TileSmem<C, NT>;
     constexpr int R = L::R, ZR = L::ZR;
     extern __shared__ double sm[];
     __shared__ long long s_item;
+    __shared__ int s_why;
 
     const DevTables &tb = p.t;
     const TilePlan &tp = p.tile;
     const int t = threadIdx.x;
+    // kCluster: the CTAs of a thread-block cluster integrate one instance together, one group of ring-connected
+    // rods (a segment) each; they meet at the step's barriers and exchange the tip-to-base joints' data through
+    // distributed shared memory.  The cluster, not the CTA, pulls work items.
+    const int rank = kCluster ? (int)cooperative_groups::this_cluster().block_rank() : 0;
     const long long total_items = p.batch * (long long)p.n_chunks;
 
     // Persistent CTAs pull (chunk, instance) items off one queue, chunk-major: the launch is cut into n_chunks
@@ -549,20 +582,23 @@ __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __gri
     // starts when chunk c-1 of the same instance has been written back (progress[instance] == c); with the
     // chunk-major order that was `batch` items ago, so nobody actually waits unless the batch is tiny.
     for (;;) {
-        if (t == 0) s_item = (long long)atomicAdd(p.work_counter, 1ULL);
-        __syncthreads();
+        if (rank == 0 && t == 0) {
+            const long long next = (long long)atomicAdd(p.work_counter, 1ULL);
+            if (next < total_items) {
+                while (*(volatile int *)(p.progress + next % p.batch) < (int)(next / p.batch)) __nanosleep(100);
+                __threadfence();
+            }
+            for (int r = 0; r < (kCluster ? tp.n_ctas : 1); ++r) *tile_peer<kCluster>(&s_item, r) = next;
+            s_why = 0;
+        }
+        tile_sync<kCluster>();
         const long long item = s_item;
-        __syncthreads();
+        tile_sync<kCluster>();
         if (item >= total_items) break;
         const long long b = item % p.batch;
         const int chunk = (int)(item / p.batch);
-        if (t == 0) {
-            while (*(volatile int *)(p.progress + b) < chunk) __nanosleep(100);
-            __threadfence();
-        }
-        __syncthreads();
         if (*(volatile int *)(p.status + b) != 0) {  // waiting for the exact-path replay: skip the rest of the launch
-            if (t == 0) *(volatile int *)(p.progress + b) = chunk + 1;
+            if (rank == 0 && t == 0) *(volatile int *)(p.progress + b) = chunk + 1;
             continue;
         }
         const int first_step = chunk * p.chunk_steps;
@@ -573,10 +609,10 @@ __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __gri
         th.t = t;
         th.bad = 0;
         // ---- which run is mine -------------------------------------------------------------------
-        const bool active = t < tp.rod_t0[tb.n_rods];
+        const bool active = t < tp.cta_threads[rank];
         const int S = tb.n_slots;
         {
-            const TileWhere wh = tile_where<C>(p, t, b);
+            const TileWhere wh = tile_where<C>(p, t, b, rank);
             const int rod = wh.rod, n = wh.n, k0 = wh.k0;
 
             // rows I read from: next / previous run of my rod, my partner as rod one of the joints I own, the owner
@@ -605,7 +641,7 @@ __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __gri
                 if (pf & BR2_FAST_ZERO_REPORTED) f |= TILE_F_REPORT0;
                 if (valid && fi[BR2_FAST_SOFTFIX_ROW] >= 0) f |= TILE_F_SOFTFIX;
                 if (tp.n_xj > 0 && active) {
-                    const int *xi = tp.xi + t * BR2_TILE_XI_N(C);
+                    const int *xi = tp.xi + (rank * tp.xi_stride + t) * BR2_TILE_XI_N(C);
                     if (xi[BR2_TILE_XI_PUB(C, j)] >= 0 || xi[BR2_TILE_XI_OW(C, j)] >= 0 || xi[BR2_TILE_XI_NCNT(C, j)] > 0) f |= TILE_F_XTRA;
                     if (j == 0 && xi[BR2_TILE_XI_JOINT] >= 0) f |= TILE_F_XJOINT;
                 }
@@ -654,7 +690,7 @@ __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __gri
         }
         // zero the exchange arrays (the zero row stays zero for the whole chunk)
         for (int i = t; i < L::ZERO_END; i += NT) sm[i] = 0.0;
-        __syncthreads();
+        tile_sync<kCluster>();
 
         double time = p.chunk_t0[chunk];
         const double hdt = 0.5 * p.dt;
@@ -668,19 +704,25 @@ __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __gri
             th.bad |= rotate_directors_tiny(th.Q[j], th.w[j], hdt, hdt) ? 1 : 0;
         }
         for (int step = 0; step < n_steps - 1; ++step) {
-            tile_step<C, NT, false, false>(p, sm, th, time + hdt, b);
+            tile_step<C, NT, false, false, kCluster>(p, sm, th, time + hdt, b, rank, step & 1);
             time = (time + hdt) + hdt;
         }
         if (final_chunk)
-            tile_step<C, NT, true, true>(p, sm, th, time + hdt, b);
+            tile_step<C, NT, true, true, kCluster>(p, sm, th, time + hdt, b, rank, (n_steps - 1) & 1);
         else
-            tile_step<C, NT, true, false>(p, sm, th, time + hdt, b);
+            tile_step<C, NT, true, false, kCluster>(p, sm, th, time + hdt, b, rank, (n_steps - 1) & 1);
 
         // a CTA that left the series' validity range keeps the chunk-start state and asks for the exact path, which
         // resumes this instance from the start of this chunk (status = 1 + chunk, reason bits from bit 8 up)
-        const int why = (__syncthreads_or(th.bad & 1) ? 1 : 0) | (__syncthreads_or(th.bad & 2) ? 2 : 0) | (__syncthreads_or(th.bad & 4) ? 4 : 0);
+        int why = (__syncthreads_or(th.bad & 1) ? 1 : 0) | (__syncthreads_or(th.bad & 2) ? 2 : 0) | (__syncthreads_or(th.bad & 4) ? 4 : 0);
+        if (kCluster) {  // the instance fails as a whole
+            if (t == 0 && why) atomicOr(tile_peer<kCluster>(&s_why, 0), why);
+            tile_sync<kCluster>();
+            why = *tile_peer<kCluster>(&s_why, 0);
+            tile_sync<kCluster>();  // everyone has read it before rank 0 clears it for the next item
+        }
         if (why) {
-            if (t == 0) {
+            if (rank == 0 && t == 0) {
                 *(volatile int *)(p.status + b) = (1 + chunk) | (why << 8);
                 __threadfence();
                 *(volatile int *)(p.progress + b) = chunk + 1;
@@ -688,7 +730,7 @@ __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __gri
             continue;
         }
         {
-            const TileWhere wh = tile_where<C>(p, t, b);
+            const TileWhere wh = tile_where<C>(p, t, b, rank);
             const int n = wh.n, np1 = wh.n + 1;
             double *const inst = wh.inst;
 #pragma unroll
@@ -710,8 +752,8 @@ __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __gri
             }
         }
         __threadfence();
-        __syncthreads();
-        if (t == 0) *(volatile int *)(p.progress + b) = chunk + 1;
+        tile_sync<kCluster>();
+        if (rank == 0 && t == 0) *(volatile int *)(p.progress + b) = chunk + 1;
     }
 }
 

@@ -140,6 +140,61 @@ def test_batched_random_pressures_match_oracle(assembly, kwargs, seed, n_steps, 
     solo.close()
 
 
+def _cluster_case(assembly, rod_db, kwargs, seed, n_steps, dt, batch, monkeypatch=None, one_cta_threads=None):
+    """Random-pressure batch on the tile kernel vs the C oracle; returns the worst errors."""
+    from br2.environment import Environment
+    from oracle import br2_port
+    from oracle.fused import FusedOracle
+
+    if one_cta_threads is not None:
+        monkeypatch.setenv("BR2_TILE_ONE_CTA_THREADS", str(one_cta_threads))
+    rng = np.random.default_rng(seed)
+    pressures = rng.uniform(0.0, 40.0, size=(3, batch)) * PSI
+    env = Environment("gpu_test", time_step=dt, batch=batch, create_dirs=False)
+    env.reset(rod_db, ASSEMBLY[assembly], **kwargs)
+    env.simulator._callback_ops = []
+    info = env.engine.kernel_info()
+    assert info["variant_name"] == "tile"
+    status = env.run({name: pressures[i] for i, name in enumerate(NAMES)}, duration=n_steps * dt - 0.5 * dt,
+                     disable_progress_bar=True, check_nan=True)
+    assert round(env.time / dt) == n_steps
+    assert not any(status.nan_per_instance[k].any() for k in status.nan_per_instance)
+    assert env.engine.replay_count() == 0 and env.engine.unresolved_count() == 0
+    ref = br2_port.OracleEnvironment(time_step=dt)
+    ref.reset(rod_db, ASSEMBLY[assembly], **kwargs)
+    fused = FusedOracle.from_simulator(ref.simulator, NAMES)
+    W = fused.pack(batch)
+    fused.run(W, pressures, n_steps, 0.0, dt)
+    x_scale = max(np.abs(fused.view(W, r, "x")).max() for r in range(len(env.simulator)))
+    worst = {"x": 0.0, "Q": 0.0, "v": 0.0, "w": 0.0}
+    for r, rod in enumerate(env.simulator):
+        for attr, short in SHORT.items():
+            if short == "a":
+                continue
+            err = np.abs(getattr(rod, attr) - fused.view(W, r, short)).max()
+            worst[short] = max(worst[short], err / x_scale if short == "x" else err)
+    env.close()
+    return worst, info
+
+
+def test_cluster_path_on_the_sample_triple(monkeypatch):
+    """The sample triple assembly forced onto the cluster path (three CTAs of 63 threads, one per segment, tip-to-base
+    joints through distributed shared memory) gives the same answer as on one CTA."""
+    worst, info = _cluster_case("triple", ROD_DB, {"gravity": True}, 2, 2000, 2.0e-5, 16, monkeypatch, one_cta_threads=100)
+    print("cluster triple n=41", info, worst)
+    assert info["threads"] == 192
+    assert worst["x"] <= POS_TOL and worst["Q"] <= DIR_TOL and worst["v"] <= VEL_TOL and worst["w"] <= OMEGA_TOL
+
+
+def test_high_resolution_triple_baseline_config_4():
+    """BASELINE config 4: triple assembly with 200 elements per rod (1809 node slots) at dt = 5e-6 (SURVEY.md section 0.6:
+    dt = 2e-5 diverges at this resolution) -- a cluster of three 320-thread CTAs per instance."""
+    worst, info = _cluster_case("triple", os.path.join(DATA, "rod_library_n200.json"), {"gravity": True}, 2, 2000, 5.0e-6, 8)
+    print("cluster triple n=200", info, worst)
+    assert info["threads"] == 320
+    assert worst["x"] <= POS_TOL and worst["Q"] <= DIR_TOL and worst["v"] <= VEL_TOL and worst["w"] <= OMEGA_TOL
+
+
 @pytest.mark.parametrize("variant", ["generic", "fast-uniform", "tile"])
 def test_chunked_launches_equal_one_launch(variant):
     """Splitting a run into launches (as capture steps do) must not change the result: bit for bit with the

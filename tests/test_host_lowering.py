@@ -173,12 +173,23 @@ def test_unknown_operator_is_refused():
         assy.simulator.lower()
 
 
-def test_too_large_assembly_is_refused():
+def test_high_resolution_triple_lowers_and_too_large_assembly_is_refused(tmp_path):
+    """BASELINE config 4 (triple assembly, 200 elements per rod = 1809 node slots) lowers -- the library runs it
+    as a cluster of three CTAs, one per segment; an assembly beyond a cluster's capacity is refused."""
     from br2.hooks import NotLowerable
 
     assy = FreeAssembly(FakeEnv())
     assy.build(os.path.join(DATA, "rod_library_n200.json"), ASSEMBLY["triple"], verbose=False)
-    with pytest.raises(NotLowerable, match="1809 node slots"):
+    program = assy.simulator.lower()
+    assert program.n_slots == 1809 and program.fast["ok"] and program.fast["uniform"]
+
+    library = json.load(open(os.path.join(DATA, "rod_library_n200.json")))
+    library["DefaultParams"]["n_elements"] = 1000
+    path = tmp_path / "rod_library_n1000.json"
+    path.write_text(json.dumps(library))
+    assy = FreeAssembly(FakeEnv())
+    assy.build(str(path), ASSEMBLY["triple"], verbose=False)
+    with pytest.raises(NotLowerable, match="9009 node slots"):
         assy.simulator.lower()
 
 
