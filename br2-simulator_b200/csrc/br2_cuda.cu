@@ -89,17 +89,21 @@ struct KernelChoice {
 #define BR2_TILE_MIN_CHUNK_STEPS 125  // a launch is cut into at most BR2_MAX_CHUNKS chunks of at least this many steps
 #endif
 // variant 3: tile kernel (BR2_TILE_C slots per thread, uniform constants); `threads` = CTA size
-const KernelChoice kTileKernels[] = {
-    {64, br2::br2_step_tile_kernel<BR2_TILE_C, 64, BR2_TILE_MB64, false>},
-    {128, br2::br2_step_tile_kernel<BR2_TILE_C, 128, 3, false>},
-    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, false>},
-    {256, br2::br2_step_tile_kernel<BR2_TILE_C, 256, 1, false>},
-    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, false>},
+// template flags: <slots per thread, CTA threads, min CTAs per SM, extra joints, cluster>
+const KernelChoice kTileKernels[] = {  // single-segment assemblies (ring joints only)
+    {64, br2::br2_step_tile_kernel<BR2_TILE_C, 64, BR2_TILE_MB64, false, false>},
+    {128, br2::br2_step_tile_kernel<BR2_TILE_C, 128, 3, false, false>},
+    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, false, false>},
+};
+const KernelChoice kTileExtraKernels[] = {  // several segments joined tip to base, one CTA
+    {128, br2::br2_step_tile_kernel<BR2_TILE_C, 128, 3, true, false>},
+    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true, false>},
+    {256, br2::br2_step_tile_kernel<BR2_TILE_C, 256, 1, true, false>},
 };
 // one CTA per group of ring-connected rods, launched as a thread-block cluster per instance
 const KernelChoice kTileClusterKernels[] = {
-    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true>},
-    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, true>},
+    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true, true>},
+    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, true, true>},
 };
 const int kTileMaxCtaThreads = 320, kTileOneCtaThreads = 256;
 
@@ -198,7 +202,8 @@ int validate(const br2_program *p) {
 
 // Plan of the thread-coarsened kernel (br2_tile.cuh), or the reason the assembly does not qualify.
 struct TileExtraTables {
-    std::vector<int32_t> xi, xj_i;
+    std::vector<int32_t> xi, xj_i;   // xi: staging rows (BR2_TILE_XI_*), packed into xpack / xitems at the end
+    std::vector<int32_t> xpack, xitems;
     std::vector<double> xj_d;
 };
 
@@ -371,6 +376,22 @@ bool make_tile_plan(const br2_program *p, int C, br2::TilePlan *plan, TileExtraT
             xt->xi[(size_t)(rank * plan->xi_stride + t) * XN + BR2_TILE_XI_JOINT] = xj;
         }
     }
+    // pack: one int per slot + the joint id per thread; node items in one compact array
+    if (plan->n_xe > 254) return *why = "too many elements in extra joints", false;
+    xt->xpack.assign((size_t)xrows * (C + 1), 0);
+    for (int t = 0; t < xrows; ++t) {
+        const int32_t *row = &xt->xi[(size_t)t * XN];
+        for (int j = 0; j < C; ++j) {
+            const int cnt = row[BR2_TILE_XI_NCNT(C, j)];
+            const int base = (int)xt->xitems.size();
+            for (int q = 0; q < cnt; ++q) xt->xitems.push_back(row[BR2_TILE_XI_NITEM(C, j, q)]);
+            if (base + cnt > 4095) return *why = "too many extra joint forces", false;
+            xt->xpack[(size_t)t * (C + 1) + j] = (row[BR2_TILE_XI_PUB(C, j)] + 1) | ((row[BR2_TILE_XI_OW(C, j)] + 1) << 8) |
+                                                 (cnt << 16) | ((cnt ? base : 0) << 20);
+        }
+        xt->xpack[(size_t)t * (C + 1) + C] = row[BR2_TILE_XI_JOINT];
+    }
+    plan->n_xitems = (int)xt->xitems.size();
     return true;
 }
 
@@ -449,7 +470,8 @@ int br2_create(const br2_program *p, int device, br2_handle *out) {
         TileExtraTables xt;
         h->tile_ok = h->fast_ok && make_tile_plan(p, BR2_TILE_C, &h->tile, &xt, &h->tile_why);
         if (h->tile_ok && h->tile.n_xj > 0) {
-            rc = upload(h, xt.xi.data(), xt.xi.size(), &h->tile.xi);
+            rc = upload(h, xt.xpack.data(), xt.xpack.size(), &h->tile.xi);
+            if (rc == BR2_OK) rc = upload(h, xt.xitems.data(), xt.xitems.size(), &h->tile.xitems);
             if (rc == BR2_OK) rc = upload(h, xt.xj_i.data(), xt.xj_i.size(), &h->tile.xj_i);
             if (rc == BR2_OK) rc = upload(h, xt.xj_d.data(), xt.xj_d.size(), &h->tile.xj_d);
             if (rc != BR2_OK) {
@@ -487,6 +509,12 @@ int br2_select_kernel(br2_handle h, int32_t variant) {
                     pick = kc;
                     break;
                 }
+        } else if (h->tile.n_xj > 0) {
+            for (const KernelChoice &kc : kTileExtraKernels)
+                if (kc.threads >= need) {
+                    pick = kc;
+                    break;
+                }
         } else {
             for (const KernelChoice &kc : kTileKernels)
                 if (kc.threads >= need) {
@@ -507,7 +535,8 @@ int br2_select_kernel(br2_handle h, int32_t variant) {
         smem = sizeof(double) * (30 * S + 9 * (size_t)h->t.n_joints + 32);
     else if (variant == 3)
         smem = sizeof(double) * ((size_t)br2::TileSmem<BR2_TILE_C, 0>::ROWS_END * (size_t)(pick.threads + 1) +
-                                 br2::TileSmem<BR2_TILE_C, 0>::TAIL + 25 * (size_t)h->tile.n_xe + 3 * (size_t)h->tile.n_xj);
+                                 br2::TileSmem<BR2_TILE_C, 0>::TAIL + 25 * (size_t)h->tile.n_xe + (3 + 8 + 6) * (size_t)h->tile.n_xj +
+                                 ((size_t)h->tile.n_xitems + 1) / 2);
     else
     {
         // fixed part: 45 T doubles + two [3][T+8] accumulators + O1 (T ints); tail (omega, extra-joint rows,

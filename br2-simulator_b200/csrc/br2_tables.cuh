@@ -46,12 +46,16 @@ struct TilePlan {
     // "extra" joints: tip-to-base joints between segments (TipToTipStraightJoint).  Few per
     // assembly; evaluated by designated threads from data their elements publish; none for single-segment assemblies.
     int n_xe, n_xj;                         // elements that publish director / omega / radius; extra joints
-    const int *xi;                          // [n_ctas][xi_stride][BR2_TILE_XI_N] per-thread bookkeeping (device)
+    int n_xitems;                           // entries of `xitems`
+    const int *xi;                          // [n_ctas][xi_stride][C + 1] per thread: packed info of each slot (published xe + 1
+                                            // | overwrite source xe + 1 << 8 | node items << 16 | first item << 20), then the
+                                            // extra joint the thread evaluates or -1 (device)
+    const int *xitems;                      // node items (joint << 1 | sign), grouped per slot (device; copied to shared memory)
     const int *xj_i;                        // [n_xj][12] rank1, row1, j1, rank2, row2, j2 of the joined elements; xe of Q1, Q2, radius one, radius two
     const double *xj_d;                     // [n_xj][8] k, nu, l1[3], l2[3]
 };
-// xi fields (C = slots per thread): joint evaluated by the thread | per slot: published xe, overwrite source xe,
-// number of node items | per slot BR2_FAST_NODE_ITEMS items (joint << 1 | sign)
+// host-side staging of the per-thread bookkeeping before it is packed (C = slots per thread): joint evaluated by the
+// thread | per slot: published xe, overwrite source xe, number of node items | per slot BR2_FAST_NODE_ITEMS items
 #define BR2_TILE_XI_JOINT 0
 #define BR2_TILE_XI_PUB(C, j) (1 + (j))
 #define BR2_TILE_XI_OW(C, j) (1 + (C) + (j))

@@ -81,8 +81,7 @@ struct TileSmem {
 };
 
 constexpr int TILE_F_VALID = 1, TILE_F_ELEM = 2, TILE_F_VOR = 4, TILE_F_ZERO_V = 8, TILE_F_ZERO_W = 16, TILE_F_OWN = 32,
-              TILE_F_REPORT0 = 64, TILE_F_SOFTFIX = 128, TILE_F_XTRA = 256,
-              TILE_F_XJOINT = 512;  // (slot 0 only) the thread evaluates an extra joint
+              TILE_F_REPORT0 = 64, TILE_F_SOFTFIX = 128;
 
 template <int C>
 struct TileThread {
@@ -91,6 +90,9 @@ struct TileThread {
     int fl[C];
     int t, tn, tprev, t1, to, top;
     int rod;
+    // extra joints (kExtras kernels): per slot published xe + 1 | overwrite source xe + 1 << 8 | node items << 16 |
+    // first item << 20; the extra joint this thread evaluates or -1
+    int xinfo[C], xjoint;
 #if BR2_TILE_TA_REGS
     double ta[C][3];
 #endif
@@ -130,7 +132,7 @@ __device__ __forceinline__ TileWhere tile_where(const StepParams &p, int t, long
 // One PositionVerlet step of a thread's run.  kEnd: last step of a chunk (ends with a single kinematic half step
 // instead of the fused pair, so the state is a whole-step state); kLast: last step of the launch (also reports
 // the callback quantities).
-template <int C, int NT, bool kEnd, bool kLast, bool kCluster>
+template <int C, int NT, bool kEnd, bool kLast, bool kExtras, bool kCluster>
 __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileThread<C> &th, double time_mid, long long b,
                                           int rank, int parity) {
     using L = TileSmem<C, NT>;
@@ -169,26 +171,25 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
     }
 #pragma unroll
     for (int i = 0; i < 9; ++i) sm[L::QF + i * R + t] = Q[0][i];
-    // extra joints (tip-to-base joints between segments): CTA-uniform branch, a handful of threads involved
-    const int n_xe = p.tile.n_xe, n_xj = p.tile.n_xj;
-    constexpr int XN = BR2_TILE_XI_N(C);
-    const int *const xi = p.tile.xi + (rank * p.tile.xi_stride + t) * XN;
+    // extra joints (tip-to-base joints between segments; kExtras kernels only): a handful of threads involved
+    const int n_xe = kExtras ? p.tile.n_xe : 0, n_xj = kExtras ? p.tile.n_xj : 0;
     // director / omega rows are double-buffered by step parity: the overwrite in P4 reads them while a faster
     // thread may already be publishing the next step's values
     double *const EX0 = tile_peer<kCluster>(sm + L::EX, 0);
     double *const EXQ = EX0 + parity * 9 * n_xe, *const EXW = EX0 + 18 * n_xe + parity * 3 * n_xe;
     double *const EXR = EX0 + 24 * n_xe, *const JF = EXR + n_xe;
-    if (n_xj > 0) {
+    // read-only copies of the joint tables (every CTA has its own): xj_d [n_xj][8], xj_i [n_xj][12], node items
+    const double *const XJD = sm + L::EX + 25 * n_xe + 3 * n_xj;
+    const int *const XJI = (const int *)(XJD + 8 * n_xj), *const XIT = XJI + 12 * n_xj;
+    if (kExtras) {
 #pragma unroll
         for (int j = 0; j < C; ++j) {
-            if (th.fl[j] & TILE_F_XTRA) {
-                const int pub = __ldg(xi + BR2_TILE_XI_PUB(C, j));
-                if (pub >= 0) {
+            const int pub = (th.xinfo[j] & 0xFF) - 1;
+            if (pub >= 0) {
 #pragma unroll
-                    for (int i = 0; i < 9; ++i) EXQ[i * n_xe + pub] = Q[j][i];
+                for (int i = 0; i < 9; ++i) EXQ[i * n_xe + pub] = Q[j][i];
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) EXW[i * n_xe + pub] = w[j][i];
-                }
+                for (int i = 0; i < 3; ++i) EXW[i * n_xe + pub] = w[j][i];
             }
         }
     }
@@ -226,8 +227,8 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
             const double inv_dil = rest_len * inv_len;
             const double rse = seed_rsqrt(dil);  // only thins the ~1e-8 m rest gap of a joint: 2^-20 relative is ample
             ra2[j] = fma(JDV(3), rse, rad);
-            if (n_xj > 0 && (th.fl[j] & TILE_F_XTRA)) {
-                const int pub = __ldg(xi + BR2_TILE_XI_PUB(C, j));
+            if (kExtras) {
+                const int pub = (th.xinfo[j] & 0xFF) - 1;
                 if (pub >= 0) EXR[pub] = rad;
             }
             if (kLast && elem) {
@@ -383,11 +384,11 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
     }
     // one tip-to-base joint per designated thread (Appendix A.8): un-rounded spring between the two element
     // surfaces along fixed material directions, un-projected damping, no torque
-    if (n_xj > 0 && (th.fl[0] & TILE_F_XJOINT)) {
-        const int xj = __ldg(xi + BR2_TILE_XI_JOINT);
+    if (kExtras && th.xjoint >= 0) {
+        const int xj = th.xjoint;
         {
-            const int *ji = p.tile.xj_i + xj * 12;
-            const double *jd = p.tile.xj_d + xj * 8;
+            const int *ji = XJI + xj * 12;
+            const double *jd = XJD + xj * 8;
             const double *const sm1 = tile_peer<kCluster>(sm, ji[0]), *const sm2 = tile_peer<kCluster>(sm, ji[3]);
             const int row1 = ji[1], j1 = ji[2], row2 = ji[4], j2 = ji[5], q1 = ji[6], q2 = ji[7];
             const double kj = jd[0], nuj = jd[1];
@@ -448,11 +449,11 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 #pragma unroll
             for (int i = 0; i < 3; ++i)
                 text[i] = fma(TAV(j, i), ramp, fma(Q[j][3 * i], tw[j][0], fma(Q[j][3 * i + 1], tw[j][1], Q[j][3 * i + 2] * tw[j][2])));
-            if (n_xj > 0 && (th.fl[j] & TILE_F_XTRA)) {
+            if (kExtras && (th.xinfo[j] >> 8) != 0) {
                 // half forces of the extra joints on this node
-                const int cnt = __ldg(xi + BR2_TILE_XI_NCNT(C, j));
+                const int cnt = (th.xinfo[j] >> 16) & 0xF, first = th.xinfo[j] >> 20;
                 for (int q = 0; q < cnt; ++q) {
-                    const int item = __ldg(xi + BR2_TILE_XI_NITEM(C, j, q));
+                    const int item = XIT[first + q];
                     const double sgn = (item & 1) ? -1.0 : 1.0;
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
@@ -463,7 +464,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
                 }
                 // a tip-to-base joint overwrites the downstream base element's director and omega during synchronize
                 // (after the surface joints above have used the old director); sources are start-of-step values
-                const int ow = __ldg(xi + BR2_TILE_XI_OW(C, j));
+                const int ow = ((th.xinfo[j] >> 8) & 0xFF) - 1;
                 if (ow >= 0) {
 #pragma unroll
                     for (int i = 0; i < 9; ++i) Q[j][i] = EXQ[i * n_xe + ow];
@@ -559,7 +560,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 #else
 #define BR2_TILE_BOUNDS(NT, MB) __launch_bounds__(NT, MB)
 #endif
-template <int C, int NT, int kMinBlocks, bool kCluster>
+template <int C, int NT, int kMinBlocks, bool kExtras, bool kCluster>
 __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __grid_constant__ StepParams p) {
     using L = TileSmem<C, NT>;
     constexpr int R = L::R, ZR = L::ZR;
@@ -640,12 +641,8 @@ __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __gri
                 if (elem && fi[BR2_FAST_OWN_JOINT] >= 0) f |= TILE_F_OWN;
                 if (pf & BR2_FAST_ZERO_REPORTED) f |= TILE_F_REPORT0;
                 if (valid && fi[BR2_FAST_SOFTFIX_ROW] >= 0) f |= TILE_F_SOFTFIX;
-                if (tp.n_xj > 0 && active) {
-                    const int *xi = tp.xi + (rank * tp.xi_stride + t) * BR2_TILE_XI_N(C);
-                    if (xi[BR2_TILE_XI_PUB(C, j)] >= 0 || xi[BR2_TILE_XI_OW(C, j)] >= 0 || xi[BR2_TILE_XI_NCNT(C, j)] > 0) f |= TILE_F_XTRA;
-                    if (j == 0 && xi[BR2_TILE_XI_JOINT] >= 0) f |= TILE_F_XJOINT;
-                }
                 th.fl[j] = f;
+                th.xinfo[j] = (kExtras && tp.n_xj > 0 && active) ? tp.xi[(rank * tp.xi_stride + t) * (C + 1) + j] : 0;
                 th.dtmc[j] = dt * p.uni[BR2_FC_CT] / tb.slot_c[(long long)BR2_SC_MASS * S + sc];
                 double ta[3] = {0.0, 0.0, 0.0};
                 if (valid) {
@@ -684,6 +681,14 @@ __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __gri
                     for (int i = 0; i < 3; ++i) th.w[j][i] = 0.0;
                 }
             }
+            th.xjoint = (kExtras && tp.n_xj > 0 && active) ? tp.xi[(rank * tp.xi_stride + t) * (C + 1) + C] : -1;
+            if (kExtras) {  // this CTA's copy of the extra joints' tables
+                double *const XJD = sm + L::EX + 25 * tp.n_xe + 3 * tp.n_xj;
+                int *const XJI = (int *)(XJD + 8 * tp.n_xj), *const XIT = XJI + 12 * tp.n_xj;
+                for (int i = t; i < 8 * tp.n_xj; i += NT) XJD[i] = tp.xj_d[i];
+                for (int i = t; i < 12 * tp.n_xj; i += NT) XJI[i] = tp.xj_i[i];
+                for (int i = t; i < tp.n_xitems; i += NT) XIT[i] = tp.xitems[i];
+            }
             // joint descriptors per rod: as rod two of the joints it owns {dv2[3], offset/2}, as rod one {dv1[3], offset/2}
             th.rod = rod;
             for (int i = t; i < 8 * BR2_TILE_MAX_RODS; i += NT) sm[L::JD + i] = tp.jd[i % BR2_TILE_MAX_RODS][i / BR2_TILE_MAX_RODS];
@@ -704,13 +709,13 @@ __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __gri
             th.bad |= rotate_directors_tiny(th.Q[j], th.w[j], hdt, hdt) ? 1 : 0;
         }
         for (int step = 0; step < n_steps - 1; ++step) {
-            tile_step<C, NT, false, false, kCluster>(p, sm, th, time + hdt, b, rank, step & 1);
+            tile_step<C, NT, false, false, kExtras, kCluster>(p, sm, th, time + hdt, b, rank, step & 1);
             time = (time + hdt) + hdt;
         }
         if (final_chunk)
-            tile_step<C, NT, true, true, kCluster>(p, sm, th, time + hdt, b, rank, (n_steps - 1) & 1);
+            tile_step<C, NT, true, true, kExtras, kCluster>(p, sm, th, time + hdt, b, rank, (n_steps - 1) & 1);
         else
-            tile_step<C, NT, true, false, kCluster>(p, sm, th, time + hdt, b, rank, (n_steps - 1) & 1);
+            tile_step<C, NT, true, false, kExtras, kCluster>(p, sm, th, time + hdt, b, rank, (n_steps - 1) & 1);
 
         // a CTA that left the series' validity range keeps the chunk-start state and asks for the exact path, which
         // resumes this instance from the start of this chunk (status = 1 + chunk, reason bits from bit 8 up)
