@@ -37,6 +37,11 @@ DATA = os.path.join(ROOT, "tests", "data")
 ROD_DB = os.path.join(DATA, "rod_library.json")
 PSI = 6895.0
 FLOP_PER_ELEMENT_STEP = 695.0  # SURVEY.md Appendix B (single-BR2-type assembly, gravity on)
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step kernel on the default workload (4096 x
+# single_br2, 2000 steps = 8 chunks), ncu capture profiles/r01_dram_2000step_launch.csv: 122.0 MB + 511.1 MB.  The
+# algorithmic figure is 231.8 MB (state in, state + derived arrays out); the excess is the chunked work queue writing
+# the 73 MB state back after every chunk -- 19 GB/s at 33 ms per launch, 0.3 % of the HBM peak.
+NCU_DRAM_BYTES_PER_LAUNCH = {("single", 4096, 2000): 633123840.0}
 WORKLOADS = {
     "single": dict(assembly="assembly_single.json", elements=123, gravity=True, seed=0,
                    label="single_br2_v1 x4096/GPU, random pressures U[0,40] psi, gravity on, dt=2e-5 (BASELINE configs[1])"),
@@ -321,7 +326,9 @@ def run_ours(args, world, rank, local):
                    "elements_per_instance": w["elements"], "l2": "flushed between timed launches (256 MB fill)",
                    "parallelism": "batch partition x%d, no step-path collective" % world},
         "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": tf.value, "unit": "TFLOP/s",
-                     "frac": achieved_tf / tf.value if tf.value else None, "traffic": None,
+                     "frac": achieved_tf / tf.value if tf.value else None,
+                     "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((args.workload, B, M)),
+                     "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_dram_2000step_launch.csv)",
                      "flop_per_element_step": FLOP_PER_ELEMENT_STEP,
                      "peak_source": "DFMA micro-benchmark run in this process (br2_fp64_peak_tflops)",
                      "hbm": {"achieved_gbs": hbm_bytes / kernel_s / 1e9, "peak_gbs": pk["hbm_gbs"], "peak_source": pk_src,
@@ -331,7 +338,7 @@ def run_ours(args, world, rank, local):
         "gpu_launches": launches,
         "kernel": dict(info, name=("br2_step_generic_kernel", "br2_step_fast_kernel", "br2_step_fast_kernel", "br2_step_tile_kernel")[info["variant"]],
                        launch_ms=per_launch_ms, exact_path_replays=engine.replay_count(),
-                       launches_per_step="fast kernel + exact-path replay pass (exits at once unless flagged)"
+                       launches_per_step="optimistic kernel + exact-path replay pass (exits at once unless flagged)"
                        if info["variant"] else "generic kernel"),
         "clocks": clocks,
         "state_finite": state_ok,
