@@ -91,19 +91,23 @@ struct KernelChoice {
 // variant 3: tile kernel (BR2_TILE_C slots per thread, uniform constants); `threads` = CTA size
 // template flags: <slots per thread, CTA threads, min CTAs per SM, extra joints, cluster>
 const KernelChoice kTileKernels[] = {  // single-segment assemblies (ring joints only)
-    {64, br2::br2_step_tile_kernel<BR2_TILE_C, 64, BR2_TILE_MB64, false, false>},
-    {128, br2::br2_step_tile_kernel<BR2_TILE_C, 128, 3, false, false>},
-    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, false, false>},
+    {64, br2::br2_step_tile_kernel<BR2_TILE_C, 64, BR2_TILE_MB64, false, false, false>},
+    {128, br2::br2_step_tile_kernel<BR2_TILE_C, 128, 3, false, false, false>},
+    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, false, false, false>},
 };
 const KernelChoice kTileExtraKernels[] = {  // several segments joined tip to base, one CTA
-    {128, br2::br2_step_tile_kernel<BR2_TILE_C, 128, 3, true, false>},
-    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true, false>},
-    {256, br2::br2_step_tile_kernel<BR2_TILE_C, 256, 1, true, false>},
+    {128, br2::br2_step_tile_kernel<BR2_TILE_C, 128, 3, true, false, false>},
+    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true, false, false>},
+    {256, br2::br2_step_tile_kernel<BR2_TILE_C, 256, 1, true, false, false>},
 };
 // one CTA per group of ring-connected rods, launched as a thread-block cluster per instance
 const KernelChoice kTileClusterKernels[] = {
-    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true, true>},
-    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, true, true>},
+    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true, true, false>},
+    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, true, true, false>},
+};
+const KernelChoice kTileClusterExactKernels[] = {  // same, exact arithmetic: the replay path of cluster-sized assemblies
+    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true, true, true>},
+    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, true, true, true>},
 };
 const int kTileMaxCtaThreads = 320, kTileOneCtaThreads = 256;
 
@@ -132,6 +136,7 @@ struct br2_handle_s {
     KernelChoice kernel{};
     size_t smem_bytes = 0;
     KernelChoice replay{};  // generic kernel used behind the fast one
+    KernelChoice exact{};   // exact-arithmetic instantiation of the cluster tile kernel (assemblies the generic kernel cannot hold)
     size_t replay_smem = 0;
     int variant = 0;        // 0 generic, 1 fast, 2 fast uniform
     int auto_variant = 0;   // what br2_create picked
@@ -503,10 +508,12 @@ int br2_select_kernel(br2_handle h, int32_t variant) {
     KernelChoice pick{0, nullptr};
     if (variant == 3) {
         const int need = h->tile.rod_t0[BR2_TILE_MAX_RODS];  // threads of the largest CTA
+        h->exact = KernelChoice{0, nullptr};
         if (h->tile.n_ctas > 1) {
-            for (const KernelChoice &kc : kTileClusterKernels)
-                if (kc.threads >= need) {
-                    pick = kc;
+            for (size_t i = 0; i < sizeof(kTileClusterKernels) / sizeof(kTileClusterKernels[0]); ++i)
+                if (kTileClusterKernels[i].threads >= need) {
+                    pick = kTileClusterKernels[i];
+                    h->exact = kTileClusterExactKernels[i];
                     break;
                 }
         } else if (h->tile.n_xj > 0) {
@@ -548,6 +555,9 @@ int br2_select_kernel(br2_handle h, int32_t variant) {
     if (smem > 227 * 1024)
         return fail(BR2_ELIMIT, "assembly needs " + std::to_string(smem) + " B of shared memory per CTA (max 232448)");
     CUDA_TRY(cudaFuncSetAttribute((const void *)pick.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (variant == 3 && h->exact.fn)
+        CUDA_TRY(cudaFuncSetAttribute((const void *)h->exact.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (variant != 3) h->exact = KernelChoice{0, nullptr};
     h->kernel = pick;
     h->smem_bytes = smem;
     h->variant = variant;
@@ -618,7 +628,7 @@ int br2_bind_state(br2_handle h, double *dev_state, int64_t batch) {
         CUDA_TRY(cudaMalloc((void **)&h->status, sizeof(int) * (size_t)batch));
         if (h->work) cudaFree(h->work);
         h->work = nullptr;
-        CUDA_TRY(cudaMalloc((void **)&h->work, sizeof(unsigned long long) + sizeof(int) * (size_t)batch));
+        CUDA_TRY(cudaMalloc((void **)&h->work, 2 * sizeof(unsigned long long) + sizeof(int) * (size_t)batch));
         h->status_batch = batch;
     }
     CUDA_TRY(cudaMemset(h->status, 0, sizeof(int) * (size_t)batch));
@@ -674,8 +684,9 @@ int br2_step(br2_handle h, int64_t n_steps, double t0, double dt, void *stream, 
     sp.status = h->status;
     sp.replays = h->replays;
     sp.only_flagged = 0;
-    sp.work_counter = h->work;
-    sp.progress = (int *)(h->work + 1);
+    sp.fail_counter = h->work;          // work buffer: [flagged instances][queue head][progress per instance]
+    sp.work_counter = h->work + 1;
+    sp.progress = (int *)(h->work + 2);
     // chunking: the tile kernel's persistent CTAs pull (chunk, instance) items; everything else runs one chunk
     sp.n_chunks = 1;
     if (h->variant == 3) {
@@ -701,7 +712,7 @@ int br2_step(br2_handle h, int64_t n_steps, double t0, double dt, void *stream, 
     void *args[] = {&sp};
     unsigned grid = (unsigned)h->batch;
     if (h->variant == 3) {
-        CUDA_TRY(cudaMemsetAsync(h->work, 0, sizeof(unsigned long long) + sizeof(int) * (size_t)h->batch, (cudaStream_t)stream));
+        CUDA_TRY(cudaMemsetAsync(h->work, 0, 2 * sizeof(unsigned long long) + sizeof(int) * (size_t)h->batch, (cudaStream_t)stream));
         const long long items = h->batch * (long long)sp.n_chunks;
         grid = (unsigned)(items < h->tile_capacity ? items : h->tile_capacity);
     }
@@ -718,6 +729,13 @@ int br2_step(br2_handle h, int64_t n_steps, double t0, double dt, void *stream, 
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         CUDA_TRY(cudaLaunchKernelExC(&cfg, (const void *)h->kernel.fn, args));
+        if (h->exact.fn) {
+            // exact-path pass of the same kernel (IEEE division / libm, no validity ranges) for the instances the
+            // optimistic pass flagged; every CTA returns at once when there are none.  The queue restarts, the count
+            // of flagged instances stays.
+            CUDA_TRY(cudaMemsetAsync(h->work + 1, 0, sizeof(unsigned long long) + sizeof(int) * (size_t)h->batch, (cudaStream_t)stream));
+            CUDA_TRY(cudaLaunchKernelExC(&cfg, (const void *)h->exact.fn, args));
+        }
     } else {
         CUDA_TRY(cudaLaunchKernel((const void *)h->kernel.fn, dim3(grid), dim3((unsigned)h->kernel.threads), args,
                                   h->smem_bytes, (cudaStream_t)stream));
@@ -757,7 +775,7 @@ int br2_step_host(br2_handle h, double *host_state, const double *host_pressures
         CUDA_TRY(cudaMalloc((void **)&h->status, sizeof(int) * (size_t)batch));
         if (h->work) cudaFree(h->work);
         h->work = nullptr;
-        CUDA_TRY(cudaMalloc((void **)&h->work, sizeof(unsigned long long) + sizeof(int) * (size_t)batch));
+        CUDA_TRY(cudaMalloc((void **)&h->work, 2 * sizeof(unsigned long long) + sizeof(int) * (size_t)batch));
         h->status_batch = batch;
         CUDA_TRY(cudaMemset(h->status, 0, sizeof(int) * (size_t)batch));
     }

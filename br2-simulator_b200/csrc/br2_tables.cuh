@@ -79,6 +79,7 @@ struct StepParams {
     // status = 1 + chunk).  One chunk = the whole launch for the other kernels.
     int chunk_steps, n_chunks;
     double chunk_t0[BR2_MAX_CHUNKS];      // fp64-accumulated start time of each chunk
+    unsigned long long *fail_counter;     // instances flagged by the optimistic pass of this launch
     unsigned long long *work_counter;     // next item of the queue (zeroed before every launch)
     int *progress;                        // [batch] chunks of the instance already written back
 };

@@ -53,6 +53,48 @@ __device__ __forceinline__ T *tile_peer(T *local, int rank) {
 #define BR2_TILE_TA_REGS 0   // actuation torques: 1 = registers, 0 = shared-memory rows
 #endif
 
+// Arithmetic of the step: the optimistic series / hardware seeds (kExact = false), or IEEE division, sqrt and libm
+// with no validity range (kExact = true).  The exact instantiation is the replay path of assemblies that are too large
+// for the one-CTA generic kernel: it redoes, from the chunk in which it was flagged, an instance that left a series' range.
+template <bool kExact>
+struct TileMath {
+    static __device__ __forceinline__ double rsqrt(double x) { return kExact ? 1.0 / sqrt(x) : fast_rsqrt(x); }
+    static __device__ __forceinline__ double rcp(double x) { return kExact ? 1.0 / x : fast_rcp(x); }
+    static __device__ __forceinline__ double rsqrt_lo(double x) { return kExact ? 1.0 / sqrt(x) : seed_rsqrt(x); }
+    static __device__ __forceinline__ double rcp_lo(double x) { return kExact ? 1.0 / x : seed_rcp(x); }
+    static __device__ __forceinline__ double sqrt_lo(double x) { return kExact ? sqrt(x) : sqrt_mid(x); }
+    static __device__ __forceinline__ double exp(double d) { return kExact ? ::exp(d) : exp_tiny(d); }
+    // theta / sin(theta + 1e-14) from y = 1 - cos(theta)
+    static __device__ __forceinline__ double logmap_ratio(double y) {
+        if (!kExact) return logmap_ratio_tiny(y);
+        const double theta = acos(1.0 - y);
+        return theta / sin(theta + 1e-14);
+    }
+    // Q <- R Q for one (hmult == hdt) or two fused (hmult == 2 hdt) kinematic half steps; true = left the series' range
+    static __device__ __forceinline__ bool rotate(double (&Q)[9], const double (&w)[3], double hdt, double hmult) {
+        if (!kExact) return rotate_directors_tiny(Q, w, hdt, hmult);
+        const double u0 = hdt * w[0], u1 = hdt * w[1], u2 = hdt * w[2];
+        const double theta = sqrt(u0 * u0 + u1 * u1 + u2 * u2);
+        const double inv = 1.0 / (theta + 1e-14);
+        const double a0 = u0 * inv, a1 = u1 * inv, a2 = u2 * inv;   // the reference's guarded axis (Appendix A.4)
+        double sn, cs;
+        sincos((hmult > 1.5 * hdt) ? 2.0 * theta : theta, &sn, &cs);  // same axis both half steps: the angles add
+        const double q = 1.0 - cs;
+        const double R00 = 1.0 - q * (a1 * a1 + a2 * a2), R11 = 1.0 - q * (a0 * a0 + a2 * a2), R22 = 1.0 - q * (a0 * a0 + a1 * a1);
+        const double q01 = q * a0 * a1, q02 = q * a0 * a2, q12 = q * a1 * a2;
+        const double R01 = sn * a2 + q01, R10 = -sn * a2 + q01, R02 = -sn * a1 + q02, R20 = sn * a1 + q02;
+        const double R12 = sn * a0 + q12, R21 = -sn * a0 + q12;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double q0 = Q[c], q1 = Q[3 + c], q2 = Q[6 + c];
+            Q[c] = R00 * q0 + R01 * q1 + R02 * q2;
+            Q[3 + c] = R10 * q0 + R11 * q1 + R12 * q2;
+            Q[6 + c] = R20 * q0 + R21 * q1 + R22 * q2;
+        }
+        return false;
+    }
+};
+
 template <int C, int NT>
 struct TileSmem {
     static constexpr int R = NT + 1;  // rows of every exchange array; row ZR is all zeros and never written
@@ -132,11 +174,12 @@ __device__ __forceinline__ TileWhere tile_where(const StepParams &p, int t, long
 // One PositionVerlet step of a thread's run.  kEnd: last step of a chunk (ends with a single kinematic half step
 // instead of the fused pair, so the state is a whole-step state); kLast: last step of the launch (also reports
 // the callback quantities).
-template <int C, int NT, bool kEnd, bool kLast, bool kExtras, bool kCluster>
+template <int C, int NT, bool kEnd, bool kLast, bool kExtras, bool kCluster, bool kExact>
 __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileThread<C> &th, double time_mid, long long b,
                                           int rank, int parity) {
     using L = TileSmem<C, NT>;
     constexpr int R = L::R;
+    using M = TileMath<kExact>;
     const DevTables &tb = p.t;
     const int t = th.t;
     const double dt = p.dt, hdt = 0.5 * p.dt;
@@ -217,15 +260,15 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
             }
             double d2 = fma(d[0], d[0], fma(d[1], d[1], d[2] * d[2]));
             d2 = elem ? d2 : 1.0;  // keeps the node-only slot finite
-            const double rs = fast_rsqrt(d2);
+            const double rs = M::rsqrt(d2);
             len[j] = fma(d2, rs, BR2_EPS14);
             const double inv_len = rs * fma(-BR2_EPS14, rs, 1.0);  // 1/(|d| + 1e-14), second order 1e-23
             const double rest_len = UNI(BR2_FC_REST_LEN), inv_rest_len = UNI(BR2_FC_INV_REST_LEN);
             const double r2 = UNI(BR2_FC_VOL_OVER_PI) * inv_len;
-            const double rad = r2 * fast_rsqrt(r2);
+            const double rad = r2 * M::rsqrt(r2);
             const double dil = len[j] * inv_rest_len;
             const double inv_dil = rest_len * inv_len;
-            const double rse = seed_rsqrt(dil);  // only thins the ~1e-8 m rest gap of a joint: 2^-20 relative is ample
+            const double rse = M::rsqrt_lo(dil);  // only thins the ~1e-8 m rest gap of a joint: 2^-20 relative is ample
             ra2[j] = fma(JDV(3), rse, rad);
             if (kExtras) {
                 const int pub = (th.xinfo[j] & 0xFF) - 1;
@@ -300,13 +343,13 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
                               fma(Qn[5], q[5], fma(Qn[6], q[6], fma(Qn[7], q[7], Qn[8] * q[8]))))))));
             // y = 1 - cos(theta) with the reference's -1e-10 guard; a benign value off the rod
             const double y = vor ? fma(-0.5, tr, kMisc[7]) : kMisc2[3];
-            th.bad |= (y <= BR2_Y_MAX && y > 0.0) ? 0 : 2;
-            const double ksr = logmap_ratio_tiny(y) * (-0.5 * UNI(BR2_FC_INV_REST_VLEN));
+            if (!kExact) th.bad |= (y <= BR2_Y_MAX && y > 0.0) ? 0 : 2;
+            const double ksr = M::logmap_ratio(y) * (-0.5 * UNI(BR2_FC_INV_REST_VLEN));
             const double ks = vor ? ksr : 0.0;
             const double kap[3] = {w0 * ks, w1 * ks, w2 * ks};
             const double tau[3] = {UNI(BR2_FC_BEND) * kap[0], UNI(BR2_FC_BEND + 1) * kap[1], UNI(BR2_FC_BEND + 2) * kap[2]};
             const double vdil = (lenn + len[j]) * (0.5 * UNI(BR2_FC_INV_REST_VLEN));
-            const double iv = fast_rcp(vdil);
+            const double iv = M::rcp(vdil);
             const double inv3 = iv * iv * iv;
             const double dinv3 = UNI(BR2_FC_REST_VLEN) * inv3;
             double Ak[3], Ck[3];
@@ -352,14 +395,14 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
         }
         const double dist2 = fma(dvec[0], dvec[0], fma(dvec[1], dvec[1], dvec[2] * dvec[2]));
         // F = k d - nu (v_rel . d_hat) d_hat = (k - nu (v_rel . d) / |d|^2) d ; no damping below |d| = 1e-12
-        const double inv_d2 = (dist2 >= BR2_1EM24) ? seed_rcp(dist2) : 0.0;  // damping term ~1e-8 N: seed accuracy is ample
+        const double inv_d2 = (dist2 >= BR2_1EM24) ? M::rcp_lo(dist2) : 0.0;  // damping term ~1e-8 N: seed accuracy is ample
         const double jk = UNI(BR2_FC_JK);
         const double hcoef = fma((-0.25 * UNI(BR2_FC_JNU)) * proj2, inv_d2, 0.5 * jk);  // half of the bracket
         // Hertz-like repulsion when the surfaces interpenetrate: -k_rep pen^1.5 along the centre line
         const double cn2 = fma(cd2[0], cd2[0], fma(cd2[1], cd2[1], cd2[2] * cd2[2])) + BR2_TINY;  // 4 |cd|^2
-        const double rcn = fast_rsqrt(cn2);                                  // 1 / (2 |cd|)
+        const double rcn = M::rsqrt(cn2);                                 // 1 / (2 |cd|)
         const double pen = fmax(fma(-0.5 * cn2, rcn, ra1 + ra2[j]), 0.0);     // max(r1 + r2 - |cd|, 0)
-        const double hmag = (-0.5 * UNI(BR2_FC_JKREP)) * (pen * sqrt_mid(pen)) * rcn;  // times cd2 = half the repulsion
+        const double hmag = (-0.5 * UNI(BR2_FC_JKREP)) * (pen * M::sqrt_lo(pen)) * rcn;  // times cd2 = half the repulsion
         double fs[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
@@ -477,16 +520,16 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
             double damp[3];
             if (p.tile.round_section) {
                 const double e2 = strain * UNI(BR2_FC_LN_CR + 2);
-                th.bad |= (e2 * e2 <= BR2_E2_MAX) ? 0 : 4;
-                const double ex = exp_tiny(e2);
+                if (!kExact) th.bad |= (e2 * e2 <= BR2_E2_MAX) ? 0 : 4;
+                const double ex = M::exp(e2);
                 damp[2] = UNI(BR2_FC_CR + 2) * ex;
                 damp[0] = damp[1] = UNI(BR2_FC_CR) * (ex * ex);
             } else {
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     const double e = strain * UNI(BR2_FC_LN_CR + i);
-                    th.bad |= (e * e <= BR2_E2_MAX) ? 0 : 4;
-                    damp[i] = UNI(BR2_FC_CR + i) * exp_tiny(e);
+                    if (!kExact) th.bad |= (e * e <= BR2_E2_MAX) ? 0 : 4;
+                    damp[i] = UNI(BR2_FC_CR + i) * M::exp(e);
                 }
             }
             double wnew[3];
@@ -547,7 +590,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
                 v[j][i] = (th.fl[j] & TILE_F_ZERO_V) ? 0.0 : v[j][i];
                 x[j][i] = fma(hmult, v[j][i], x[j][i]);
             }
-            th.bad |= rotate_directors_tiny(Q[j], w[j], hdt, hmult) ? 1 : 0;
+            th.bad |= M::rotate(Q[j], w[j], hdt, hmult) ? 1 : 0;
         }
     }
 #undef UNI
@@ -560,7 +603,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 #else
 #define BR2_TILE_BOUNDS(NT, MB) __launch_bounds__(NT, MB)
 #endif
-template <int C, int NT, int kMinBlocks, bool kExtras, bool kCluster>
+template <int C, int NT, int kMinBlocks, bool kExtras, bool kCluster, bool kExact>
 __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __grid_constant__ StepParams p) {
     using L = TileSmem<C, NT>;
     constexpr int R = L::R, ZR = L::ZR;
@@ -576,6 +619,8 @@ __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __gri
     // distributed shared memory.  The cluster, not the CTA, pulls work items.
     const int rank = kCluster ? (int)cooperative_groups::this_cluster().block_rank() : 0;
     const long long total_items = p.batch * (long long)p.n_chunks;
+    // exact-path pass: nothing to do unless the optimistic pass just before it flagged an instance
+    if (kExact && *(volatile unsigned long long *)p.fail_counter == 0ULL) return;
 
     // Persistent CTAs pull (chunk, instance) items off one queue, chunk-major: the launch is cut into n_chunks
     // runs of chunk_steps steps so that the last wave of instances does not leave most SMs idle (4096 instances
@@ -598,9 +643,15 @@ __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __gri
         if (item >= total_items) break;
         const long long b = item % p.batch;
         const int chunk = (int)(item / p.batch);
-        if (*(volatile int *)(p.status + b) != 0) {  // waiting for the exact-path replay: skip the rest of the launch
-            if (rank == 0 && t == 0) *(volatile int *)(p.progress + b) = chunk + 1;
-            continue;
+        {
+            // optimistic pass: an instance waiting for the exact-path replay skips the rest of the launch;
+            // exact pass: only flagged instances, from the chunk in which they were flagged (status = 1 + chunk | why << 8)
+            const int st = *(volatile int *)(p.status + b);
+            const bool skip = kExact ? (st == 0 || chunk < (st & 0xFF) - 1) : (st != 0);
+            if (skip) {
+                if (rank == 0 && t == 0) *(volatile int *)(p.progress + b) = chunk + 1;
+                continue;
+            }
         }
         const int first_step = chunk * p.chunk_steps;
         const int n_steps = min(p.chunk_steps, (int)p.n_steps - first_step);
@@ -706,16 +757,16 @@ __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __gri
         for (int j = 0; j < C; ++j) {
 #pragma unroll
             for (int i = 0; i < 3; ++i) th.x[j][i] = fma(hdt, th.v[j][i], th.x[j][i]);
-            th.bad |= rotate_directors_tiny(th.Q[j], th.w[j], hdt, hdt) ? 1 : 0;
+            th.bad |= TileMath<kExact>::rotate(th.Q[j], th.w[j], hdt, hdt) ? 1 : 0;
         }
         for (int step = 0; step < n_steps - 1; ++step) {
-            tile_step<C, NT, false, false, kExtras, kCluster>(p, sm, th, time + hdt, b, rank, step & 1);
+            tile_step<C, NT, false, false, kExtras, kCluster, kExact>(p, sm, th, time + hdt, b, rank, step & 1);
             time = (time + hdt) + hdt;
         }
         if (final_chunk)
-            tile_step<C, NT, true, true, kExtras, kCluster>(p, sm, th, time + hdt, b, rank, (n_steps - 1) & 1);
+            tile_step<C, NT, true, true, kExtras, kCluster, kExact>(p, sm, th, time + hdt, b, rank, (n_steps - 1) & 1);
         else
-            tile_step<C, NT, true, false, kExtras, kCluster>(p, sm, th, time + hdt, b, rank, (n_steps - 1) & 1);
+            tile_step<C, NT, true, false, kExtras, kCluster, kExact>(p, sm, th, time + hdt, b, rank, (n_steps - 1) & 1);
 
         // a CTA that left the series' validity range keeps the chunk-start state and asks for the exact path, which
         // resumes this instance from the start of this chunk (status = 1 + chunk, reason bits from bit 8 up)
@@ -728,6 +779,7 @@ __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __gri
         }
         if (why) {
             if (rank == 0 && t == 0) {
+                atomicAdd(p.fail_counter, 1ULL);
                 *(volatile int *)(p.status + b) = (1 + chunk) | (why << 8);
                 __threadfence();
                 *(volatile int *)(p.progress + b) = chunk + 1;
@@ -758,7 +810,16 @@ __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __gri
         }
         __threadfence();
         tile_sync<kCluster>();
-        if (rank == 0 && t == 0) *(volatile int *)(p.progress + b) = chunk + 1;
+        if (rank == 0 && t == 0) {
+            if (kExact && final_chunk) {  // replay complete: count it (and why it was needed), clear the flag
+                const int st = *(volatile int *)(p.status + b) >> 8;
+                atomicAdd(p.replays, 1ULL);
+                for (int bit = 0; bit < 3; ++bit)
+                    if (st & (1 << bit)) atomicAdd(p.replays + 1 + bit, 1ULL);
+                *(volatile int *)(p.status + b) = 0;
+            }
+            *(volatile int *)(p.progress + b) = chunk + 1;
+        }
     }
 }
 

@@ -230,9 +230,10 @@ int br2_select_kernel(br2_handle h, int32_t variant);
 /* Instance-launches the exact-path (generic) kernel had to redo because the fast kernel left the validity
  * range of its series on them (normally 0).  Synchronises the device. */
 int br2_replay_count(br2_handle h, int64_t *count);
-/* Instances that left the optimistic kernel's range and could NOT be redone: assemblies that only fit a thread-block
- * cluster (more than 1024 node slots) have no exact-path kernel; such instances stop advancing and stay flagged.
- * 0 for every assembly of 1024 slots or fewer.  Synchronises the device. */
+/* Instances still flagged after the replay pass, i.e. that left the optimistic kernel's range and could NOT be redone.
+ * Expected to be 0: assemblies of up to 1024 node slots are replayed by the generic kernel, cluster-sized ones by the
+ * exact-arithmetic instantiation of the cluster kernel.  A non-zero count means an instance has stopped advancing
+ * (Environment.run(check_nan=True) raises on it).  Synchronises the device. */
 int br2_unresolved_count(br2_handle h, int64_t *count);
 /* Of the replays, how many left the range of the rotation-angle series (|omega| dt/2 too large), the curvature series
  * (neighbouring elements rotated too far apart) and the damper's exponential (axial strain too large); only

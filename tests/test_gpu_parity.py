@@ -186,6 +186,34 @@ def test_cluster_path_on_the_sample_triple(monkeypatch):
     assert worst["x"] <= POS_TOL and worst["Q"] <= DIR_TOL and worst["v"] <= VEL_TOL and worst["w"] <= OMEGA_TOL
 
 
+def test_cluster_path_replays_out_of_range_instances_exactly(monkeypatch):
+    """Cluster-sized assemblies have no one-CTA generic kernel to fall back on: the exact-arithmetic instantiation of the
+    cluster kernel redoes flagged instances from the chunk in which they left the series' range.  Forced here on the
+    sample triple assembly and compared with the generic kernel."""
+    dt, n_steps = 2.0e-5, 400
+    pressures = np.array([[30.0, 3.0e4, 10.0, 5.0e4], [20.0, 2.0e4, 5.0, 5.0e4], [10.0, 1.0e4, 0.0, 5.0e4]]) * PSI
+    action = {name: pressures[i] for i, name in enumerate(NAMES)}
+    generic = make_env("triple", 4, variant="generic", gravity=True)
+    generic.simulator._callback_ops = []
+    generic.run(action, duration=n_steps * dt - 0.5 * dt, disable_progress_bar=True)
+    monkeypatch.setenv("BR2_TILE_ONE_CTA_THREADS", "100")
+    cluster = make_env("triple", 4, gravity=True)
+    cluster.simulator._callback_ops = []
+    assert cluster.engine.kernel_info()["variant_name"] == "tile" and cluster.engine.kernel_info()["threads"] == 192
+    cluster.run(action, duration=n_steps * dt - 0.5 * dt, disable_progress_bar=True)
+    assert cluster.engine.replay_count() >= 2 and cluster.engine.unresolved_count() == 0
+    assert sum(cluster.engine.replay_reasons().values()) >= 2
+    for rc, rg in zip(cluster.simulator, generic.simulator):
+        xc, xg = rc.position_collection, rg.position_collection
+        assert np.array_equal(np.isfinite(xc), np.isfinite(xg))
+        ok = np.isfinite(xg)
+        assert np.abs(xc[ok] - xg[ok]).max() <= 1e-6 * max(1.0, np.abs(xg[ok]).max())
+        for inst in (0, 2):
+            assert np.abs(xc[inst] - xg[inst]).max() <= POS_TOL * 0.6
+    cluster.close()
+    generic.close()
+
+
 def test_high_resolution_triple_baseline_config_4():
     """BASELINE config 4: triple assembly with 200 elements per rod (1809 node slots) at dt = 5e-6 (SURVEY.md section 0.6:
     dt = 2e-5 diverges at this resolution) -- a cluster of three 320-thread CTAs per instance."""
