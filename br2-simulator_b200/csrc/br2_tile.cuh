@@ -40,6 +40,15 @@ __device__ __forceinline__ void tile_sync() {
     else
         __syncthreads();
 }
+// split-phase cluster barrier: arrive (release) ... independent work ... wait (acquire)
+template <bool kCluster>
+__device__ __forceinline__ void tile_cluster_arrive() {
+    if (kCluster) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+template <bool kCluster>
+__device__ __forceinline__ void tile_cluster_wait() {
+    if (kCluster) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 template <bool kCluster, typename T>
 __device__ __forceinline__ T *tile_peer(T *local, int rank) {
     if (kCluster) return cooperative_groups::this_cluster().map_shared_rank(local, rank);
@@ -179,6 +188,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
                                           int rank, int parity) {
     using L = TileSmem<C, NT>;
     constexpr int R = L::R;
+    static_assert(kExtras || !kCluster, "the cluster kernels carry the extra-joint code (their barrier phases live in it)");
     using M = TileMath<kExact>;
     const DevTables &tb = p.t;
     const int t = th.t;
@@ -236,7 +246,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
             }
         }
     }
-    tile_sync<kCluster>();
+    __syncthreads();  // B1 (the remote director rows become visible with the cluster barrier after P2)
 
     // =============================== P2: element quantities ==================================
     double len[C], ra2[C];
@@ -321,7 +331,9 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 #pragma unroll
         for (int i = 0; i < 3; ++i) sm[L::SKL + i * R + t] = skp[i];
     }
-    tile_sync<kCluster>();
+    __syncthreads();  // B2
+    // cluster: the other CTAs' rows are needed only by the tip-to-base joints at the end of P3 -- arrive now, wait there
+    tile_cluster_arrive<kCluster>();
 
     // =============================== P3: Voronoi couples and own joints ======================
     double tw[C][3];  // world-frame joint torque on my element (own joint now, rod-one joint in P4)
@@ -427,6 +439,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
     }
     // one tip-to-base joint per designated thread (Appendix A.8): un-rounded spring between the two element
     // surfaces along fixed material directions, un-projected damping, no torque
+    tile_cluster_wait<kCluster>();
     if (kExtras && th.xjoint >= 0) {
         const int xj = th.xjoint;
         {
@@ -447,10 +460,13 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
             }
         }
     }
-    tile_sync<kCluster>();
+    // cluster: the joint forces are gathered at the very end of P4 -- arrive now, wait there
+    tile_cluster_arrive<kCluster>();
+    __syncthreads();  // B3
 
     // =============================== P4: assemble, dynamic step ==============================
     {
+        if (kLast) tile_cluster_wait<kCluster>();  // the reporting step gathers them early (external forces are reported)
         const double ramp_raw = time_mid * tb.act_inv_ramp;
         const double ramp = (ramp_raw < 1.0) ? ramp_raw : 1.0;
         // what the previous run's last element contributes to my first node / element
@@ -493,16 +509,17 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
             for (int i = 0; i < 3; ++i)
                 text[i] = fma(TAV(j, i), ramp, fma(Q[j][3 * i], tw[j][0], fma(Q[j][3 * i + 1], tw[j][1], Q[j][3 * i + 2] * tw[j][2])));
             if (kExtras && (th.xinfo[j] >> 8) != 0) {
-                // half forces of the extra joints on this node
-                const int cnt = (th.xinfo[j] >> 16) & 0xF, first = th.xinfo[j] >> 20;
-                for (int q = 0; q < cnt; ++q) {
-                    const int item = XIT[first + q];
-                    const double sgn = (item & 1) ? -1.0 : 1.0;
+                if (kLast) {  // half forces of the extra joints on this node (every other step: after the rotation below)
+                    const int cnt = (th.xinfo[j] >> 16) & 0xF, first = th.xinfo[j] >> 20;
+                    for (int q = 0; q < cnt; ++q) {
+                        const int item = XIT[first + q];
+                        const double sgn = (item & 1) ? -1.0 : 1.0;
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        const double f = sgn * JF[i * n_xj + (item >> 1)];
-                        v[j][i] = fma(th.dtmc[j], f, v[j][i]);
-                        if (kLast) r_fext[j][i] += f;
+                        for (int i = 0; i < 3; ++i) {
+                            const double f = sgn * JF[i * n_xj + (item >> 1)];
+                            v[j][i] = fma(th.dtmc[j], f, v[j][i]);
+                            r_fext[j][i] += f;
+                        }
                     }
                 }
                 // a tip-to-base joint overwrites the downstream base element's director and omega during synchronize
@@ -584,13 +601,29 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
         // next one (unless this is the last step of the launch)
         const double hmult = kEnd ? hdt : dt;
 #pragma unroll
+        for (int j = 0; j < C; ++j) th.bad |= M::rotate(Q[j], w[j], hdt, hmult) ? 1 : 0;
+        if (kExtras && !kLast) {
+            // half forces of the tip-to-base joints on my nodes -- last, so that a cluster's other CTAs had the whole of
+            // P4 to deliver them
+            tile_cluster_wait<kCluster>();
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                const int cnt = (th.xinfo[j] >> 16) & 0xF, first = th.xinfo[j] >> 20;
+                for (int q = 0; q < cnt; ++q) {
+                    const int item = XIT[first + q];
+                    const double sgn = (item & 1) ? -1.0 : 1.0;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) v[j][i] = fma(th.dtmc[j] * sgn, JF[i * n_xj + (item >> 1)], v[j][i]);
+                }
+            }
+        }
+#pragma unroll
         for (int j = 0; j < C; ++j) {
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 v[j][i] = (th.fl[j] & TILE_F_ZERO_V) ? 0.0 : v[j][i];
                 x[j][i] = fma(hmult, v[j][i], x[j][i]);
             }
-            th.bad |= M::rotate(Q[j], w[j], hdt, hmult) ? 1 : 0;
         }
     }
 #undef UNI
