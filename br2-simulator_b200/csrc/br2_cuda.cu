@@ -298,6 +298,9 @@ bool make_tile_plan(const br2_program *p, int C, br2::TilePlan *plan, TileExtraT
     const double *fc = p->fast_c;
     const double l0 = fc[(size_t)BR2_FC_LN_CR * S], l1 = fc[(size_t)(BR2_FC_LN_CR + 1) * S], l2 = fc[(size_t)(BR2_FC_LN_CR + 2) * S];
     plan->round_section = (l0 == l1 && fabs(l0 - 2.0 * l2) <= 1e-13 * fabs(l0)) ? 1 : 0;
+    for (int r = 0; r < p->n_rods; ++r)
+        if (plan->jd[r][2] != 0.0 || plan->jd[r][6] != 0.0)
+            return *why = "a surface joint's direction vector has a component along the rod axis", false;
 
     // ---- extra joints (everything that is not an owned ring joint): tip-to-base joints only ----------------
     const int XN = BR2_TILE_XI_N(C);

@@ -22,7 +22,8 @@
 //
 // Applicability (decided on the host, br2_cuda.cu: make_tile_plan): fast-path assembly with uniform element
 // constants, no "extra" joints / director overwrites (single-segment assemblies), every surface joint
-// connects equal element indices of two rods and all joints of a rod pair share one descriptor.
+// connects equal element indices of two rods, all joints of a rod pair share one descriptor, and the joints' direction
+// vectors have no component along the rod axis d3 (rods side by side).
 #pragma once
 
 #include <cooperative_groups.h>
@@ -321,11 +322,11 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
             }
             // what the joint in which this element is rod one needs from it
             const double ra1 = fma(JDV(7), rse, rad);
-            const double a0 = JDV(4) * ra1, a1 = JDV(5) * ra1, a2 = JDV(6) * ra1;
+            const double a0 = JDV(4) * ra1, a1 = JDV(5) * ra1;  // planar arms: no d3 component (tile plan requirement)
             sm[L::PA + j * R + t] = ra1;
 #pragma unroll
             for (int i = 0; i < 3; ++i)
-                sm[L::PR + (3 * j + i) * R + t] = fma(Q[j][i], a0, fma(Q[j][3 + i], a1, Q[j][6 + i] * a2));  // Q^T dv1 (r + o)
+                sm[L::PR + (3 * j + i) * R + t] = fma(Q[j][i], a0, Q[j][3 + i] * a1);  // Q^T dv1 (r + o)
         }
         sm[L::LF + t] = len[0];
 #pragma unroll
@@ -390,13 +391,13 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 #pragma unroll
     for (int j = 0; j < C; ++j) {
         const bool own = th.fl[j] & TILE_F_OWN;
-        const double b0 = JDV(0) * ra2[j], b1 = JDV(1) * ra2[j], b2 = JDV(2) * ra2[j];
+        const double b0 = JDV(0) * ra2[j], b1 = JDV(1) * ra2[j];
         const double ra1 = sm[L::PA + j * R + th.t1];
         double rd2[3], cd2[3], dvec[3];
         double proj2 = 0.0;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            rd2[i] = fma(Q[j][i], b0, fma(Q[j][3 + i], b1, Q[j][6 + i] * b2));  // Q^T dv2 (r + o)
+            rd2[i] = fma(Q[j][i], b0, Q[j][3 + i] * b1);  // Q^T dv2 (r + o)
             const double xn = (j + 1 < C) ? x[(j + 1) % C][i] : sm[L::XF + i * R + th.tn];
             cd2[i] = (xn + x[j][i]) - sm[L::PC + (3 * j + i) * R + th.t1];       // 2 (c2 - c1)
             const double g = rd2[i] - sm[L::PR + (3 * j + i) * R + th.t1];
