@@ -359,18 +359,17 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
             if (!kExact) th.bad |= (y <= BR2_Y_MAX && y > 0.0) ? 0 : 2;
             const double ksr = M::logmap_ratio(y) * (-0.5 * UNI(BR2_FC_INV_REST_VLEN));
             const double ks = vor ? ksr : 0.0;
-            const double kap[3] = {w0 * ks, w1 * ks, w2 * ks};
-            const double tau[3] = {UNI(BR2_FC_BEND) * kap[0], UNI(BR2_FC_BEND + 1) * kap[1], UNI(BR2_FC_BEND + 2) * kap[2]};
             const double vdil = (lenn + len[j]) * (0.5 * UNI(BR2_FC_INV_REST_VLEN));
             const double iv = M::rcp(vdil);
-            const double inv3 = iv * iv * iv;
-            const double dinv3 = UNI(BR2_FC_REST_VLEN) * inv3;
+            // A = B kappa / E^3 and C = (kappa x B kappa) D / E^3 = (kappa x A) D with kappa = ks w
+            const double s3 = ks * (iv * iv * iv), cs = ks * UNI(BR2_FC_REST_VLEN);
             double Ak[3], Ck[3];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) Ak[i] = tau[i] * inv3;
-            Ck[0] = fma(kap[1], tau[2], -kap[2] * tau[1]) * dinv3;
-            Ck[1] = fma(kap[2], tau[0], -kap[0] * tau[2]) * dinv3;
-            Ck[2] = fma(kap[0], tau[1], -kap[1] * tau[0]) * dinv3;
+            Ak[0] = UNI(BR2_FC_BEND) * (w0 * s3);
+            Ak[1] = UNI(BR2_FC_BEND + 1) * (w1 * s3);
+            Ak[2] = UNI(BR2_FC_BEND + 2) * (w2 * s3);
+            Ck[0] = fma(w1, Ak[2], -w2 * Ak[1]) * cs;
+            Ck[1] = fma(w2, Ak[0], -w0 * Ak[2]) * cs;
+            Ck[2] = fma(w0, Ak[1], -w1 * Ak[0]) * cs;
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 // couple on element k: (A_k - A_{k-1}) + (C_k + C_{k-1}) / 2 + shear and transport terms
