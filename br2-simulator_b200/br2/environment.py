@@ -190,7 +190,7 @@ class Environment:
             chunk = stop - done
             if chunk > 0:
                 time = self.do_step(self.StatefulStepper, self.stages_and_updates, self.simulator, time, dt,
-                                    n_steps=chunk, callbacks=True)
+                                    n_steps=chunk, callbacks=True, push_actuation=False)
                 done = stop
                 if progress is not None:
                     progress.update(chunk * dt)

@@ -19,10 +19,16 @@ class _DeviceStages:
         self.collection = collection
 
 
-def _do_step(stepper, stages_and_updates, collection, time, dt, n_steps=1, callbacks=True):
+def _do_step(stepper, stages_and_updates, collection, time, dt, n_steps=1, callbacks=True, push_actuation=True):
     engine = collection.engine
     if engine is None:
         raise RuntimeError("finalize() the collection before stepping")
+    if push_actuation:
+        # the reference's actuation operators read their shared python lists at every step
+        # (/root/reference/br2/free_custom_systems.py:49-57, :96-101): upload the current values
+        program = getattr(collection, "program", None)
+        if program is not None and program.action_lists:
+            engine.set_pressures([shared[0] for shared in program.action_lists])
     end = engine.step(n_steps, time, dt)
     if callbacks and collection._callback_ops:
         current_step = round(end / dt)

@@ -286,6 +286,93 @@ def test_optional_ops_point_force_and_last_end_fixed():
     np.testing.assert_array_equal(rod.velocity_collection[:, -1], 0.0)
 
 
+def test_lone_rod_with_odd_slot_count_on_the_tile_kernel():
+    """Ragged case for the tile kernel: one rod, no joints (no partner / owner rows), 21 node slots = 10 full runs of two
+    slots and one half-empty run; gravity, damper, soft-fixed base and a twist actuation through the hooks, vs the
+    faithful oracle."""
+    from br2.free_custom_systems import FreeBaseEndSoftFixed, FreeTwistActuation
+    from br2.free_simulator import BR2Simulator
+    from br2.hooks import AnalyticalLinearDamper, CosseratRod, GravityForces, PositionVerlet, extend_stepper_interface
+    from oracle import br2_port, mini_elastica
+
+    spec = dict(n_elements=20, start=np.zeros(3), direction=np.array([0.0, 1.0, 0.0]), normal=np.array([0.0, 0.0, 1.0]),
+                base_length=0.2, base_radius=0.005, density=1200.0, youngs_modulus=2e6, shear_modulus=1.2e6)
+    dt, n_steps = 1.0e-5, 3000
+
+    def build(sim_cls, rod_cls, damper, gravity, fixed, twist):
+        sim = sim_cls()
+        rod = rod_cls.straight_rod(**spec)
+        sim.append(rod)
+        sim.dampen(rod).using(damper, damping_constant=2.0, time_step=dt)
+        sim.add_forcing_to(rod).using(gravity, acc_gravity=np.array([0.3, 0.0, -9.80665]))
+        pressure = [2.0e4]
+        sim.add_forcing_to(rod).using(twist, actuation_ref=pressure, scale=1.25797e-6, ramp_up_time=5e-3)
+        sim.constrain(rod).using(fixed, constrained_position_idx=(0,), constrained_director_idx=(0,), k=1e9, nu=0.0, kt=0.0)
+        sim.finalize()
+        return sim, rod
+
+    sim, rod = build(BR2Simulator, CosseratRod, AnalyticalLinearDamper, GravityForces, FreeBaseEndSoftFixed, FreeTwistActuation)
+    assert sim.engine.kernel_info()["variant_name"] == "tile"
+    do_step, stages = extend_stepper_interface(PositionVerlet(), sim)
+    do_step(PositionVerlet(), stages, sim, 0.0, dt, n_steps=n_steps)
+    assert sim.engine.replay_count() == 0
+    osim, orod = build(br2_port.BR2Simulator, mini_elastica.CosseratRod, mini_elastica.AnalyticalLinearDamper,
+                       mini_elastica.GravityForces, br2_port.FreeBaseEndSoftFixed, br2_port.FreeTwistActuation)
+    mini_elastica.timestepper.integrate(mini_elastica.PositionVerlet(), osim, n_steps * dt, n_steps)
+    assert np.abs(orod.position_collection[:, -1] - np.array([0.0, 0.2, 0.0])).max() > 1e-5  # it moved
+    scale = np.abs(orod.position_collection).max()
+    assert np.abs(rod.position_collection - orod.position_collection).max() <= POS_TOL * scale
+    assert np.abs(rod.director_collection - orod.director_collection).max() <= DIR_TOL
+    assert np.abs(rod.velocity_collection - orod.velocity_collection).max() <= VEL_TOL
+    assert np.abs(rod.omega_collection - orod.omega_collection).max() <= OMEGA_TOL
+
+
+FULL_SIZE = [
+    # BASELINE.json configs at their full batch sizes: (assembly, kwargs, batch, steps)
+    ("single", {"gravity": True}, 4096, 2000),    # configs[1]
+    ("double", {}, 16384, 500),                   # configs[2]
+    ("single", {"gravity": True}, 65536, 250),    # configs[4], one GPU's worth is the whole sweep here
+]
+
+
+@pytest.mark.parametrize("assembly,kwargs,batch,n_steps", FULL_SIZE, ids=["single-4096", "double-16384", "single-65536"])
+def test_full_size_batches_by_properties(assembly, kwargs, batch, n_steps):
+    """At the BASELINE batch sizes the oracle is too slow to redo everything, so: (1) instances are independent and
+    position-blind -- the second half of the batch repeats the first half's pressures and must reproduce it bit for bit;
+    (2) a sample of instances spread over the batch matches the C oracle; (3) directors stay orthonormal; (4) nothing
+    left the optimistic path, nothing is NaN."""
+    dt = 2.0e-5
+    rng = np.random.default_rng(batch)
+    half = batch // 2
+    first = rng.uniform(0.0, 40.0, size=(3, half)) * PSI
+    if batch == 65536:
+        first[0] = np.linspace(0.0, 40.0, half) * PSI       # configs[4]: action1 swept linearly over the instances
+    pressures = np.concatenate([first, first], axis=1)
+    env = make_env(assembly, batch, **kwargs)
+    env.simulator._callback_ops = []
+    assert env.engine.kernel_info()["variant_name"] == "tile"
+    status = env.run({name: pressures[i] for i, name in enumerate(NAMES)}, duration=n_steps * dt - 0.5 * dt,
+                     disable_progress_bar=True, check_nan=True)
+    assert not any(status.nan_per_instance[k].any() for k in status.nan_per_instance)
+    assert env.engine.replay_count() == 0
+    torch = env.engine.torch
+    state = env.engine.state
+    assert torch.equal(state[:half], state[half:])
+    sample = np.unique(np.concatenate([[0, 1, half - 1, half, batch - 1], rng.integers(0, batch, 11)]))
+    fused, W = fused_reference(assembly, kwargs, pressures[:, sample], n_steps, dt)
+    x_scale = max(np.abs(fused.view(W, r, "x")).max() for r in range(len(env.simulator)))
+    idx = torch.as_tensor(sample, device=state.device)
+    for r in range(len(env.simulator)):
+        got_x = env.engine.view(r, "x")[idx].cpu().numpy()
+        got_q = env.engine.view(r, "Q")[idx].cpu().numpy()
+        assert np.abs(got_x - fused.view(W, r, "x")).max() <= POS_TOL * x_scale
+        assert np.abs(got_q - fused.view(W, r, "Q")).max() <= DIR_TOL
+        Q = env.engine.view(r, "Q")
+        gram = torch.einsum("bijk,bljk->bilk", Q, Q)
+        assert float((gram - torch.eye(3, dtype=Q.dtype, device=Q.device)[None, :, :, None]).abs().max()) < 1e-10
+    env.close()
+
+
 def test_step_host_entry_point_matches_device_path():
     """br2_step_host (host buffers in, host buffers out) == bind + step on device buffers."""
     import ctypes
