@@ -365,21 +365,16 @@ bool make_tile_plan(const br2_program *p, int C, br2::TilePlan *plan, TileExtraT
         const int t = thread_of((int)sl, &j);
         xt->xi[(size_t)t * XN + BR2_TILE_XI_OW(C, j)] = xe_id(p->overwrite_src[sl]);
     }
-    // the extra joints are evaluated by the CTA of their rod-two element, spread over its warps
+    // the extra joints are evaluated by the CTA of their rod-two element, by consecutive threads of its LAST warps: a
+    // warp executes the joint code once whichever of its lanes take part, so packing them keeps the other warps' issue
+    // slots free (the CTA waits for the slowest warp at the next barrier either way)
     {
-        int next_lane[8] = {0, 0, 0, 0, 0, 0, 0, 0}, next_warp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int used[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int xj = 0; xj < plan->n_xj; ++xj) {
             const int rank = xt->xj_i[(size_t)xj * 12 + 3];
             const int ct = plan->cta_threads[rank], warps = (ct + 31) / 32;
-            int t = -1;
-            for (int tries = 0; tries < 32 * warps && t < 0; ++tries) {
-                const int cand = next_warp[rank] * 32 + next_lane[rank];
-                if (++next_warp[rank] == warps) {
-                    next_warp[rank] = 0;
-                    ++next_lane[rank];
-                }
-                if (cand < ct && next_lane[rank] <= 32) t = cand;
-            }
+            const int k = used[rank]++;                       // k-th joint of this CTA
+            const int t = (warps - 1 - k / 32) * 32 + k % 32;  // lanes 0.. of the last warp, then the one before, ...
             if (t < 0) return *why = "more extra joints than threads", false;
             xt->xi[(size_t)(rank * plan->xi_stride + t) * XN + BR2_TILE_XI_JOINT] = xj;
         }
