@@ -78,7 +78,9 @@ def peaks():
 
 
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """`nvidia-smi -lms 100` in the background, started BEFORE the warm-up (its start-up takes longer than a short timed
+    region); only the samples whose timestamps fall inside the timed region are reported."""
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -86,6 +88,7 @@ class ClockSampler:
         self.gpu_index = gpu_index
         self.proc = None
         self.path = None
+        self.begin = self.end = None
 
     def start(self):
         try:
@@ -97,35 +100,54 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.begin = time.time()
+
+    def mark_end(self):
+        self.end = time.time()
+
     def stop(self):
+        import datetime
+
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
+        time.sleep(0.15)  # let the sample that covers the end of the region land
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        clocks, reasons, sm_max = [], set(), None
+        rows = []
         try:
             for line in open(self.path):
                 parts = [p.strip() for p in line.split(",")]
                 if len(parts) < 9:
                     continue
                 try:
-                    clocks.append(float(parts[1]))
-                    sm_max = float(parts[2])
+                    stamp = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((stamp, float(parts[1]), float(parts[2]), parts[5:9]))
                 except ValueError:
                     continue
-                for name, flag in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
-                    if flag.lower().startswith("active"):
-                        reasons.add(name)
             os.remove(self.path)
         except Exception:
             pass
-        if clocks:
-            clocks.sort()
-            out.update(sm_mhz=clocks[len(clocks) // 2], sm_max_mhz=sm_max, reasons=sorted(reasons), samples=len(clocks))
+        begin, end = self.begin or 0.0, self.end or float("inf")
+        inside = [r for r in rows if begin <= r[0] <= end]
+        window = "timed region"
+        if not inside and rows:  # region shorter than the sampling period: the sample nearest to it (GPU busy since the warm-up)
+            mid = 0.5 * (begin + min(end, begin + 3600.0))
+            inside = [min(rows, key=lambda r: abs(r[0] - mid))]
+            window = "nearest sample to the timed region (%.2f s away)" % abs(inside[0][0] - mid)
+        if inside:
+            clocks = sorted(r[1] for r in inside)
+            reasons = set()
+            for r in inside:
+                for name, flag in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
+                    if flag.lower().startswith("active"):
+                        reasons.add(name)
+            out.update(sm_mhz=clocks[len(clocks) // 2], sm_max_mhz=inside[0][2], reasons=sorted(reasons),
+                       samples=len(inside), window=window)
         return out
 
 
@@ -253,11 +275,12 @@ def run_ours(args, world, rank, local):
 
     # ---- device-resident throughput ------------------------------------------------------
     t_sim = 0.0
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         t_sim = engine.step(M, t_sim, dt)
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     launches0 = engine.launches
@@ -267,6 +290,7 @@ def run_ours(args, world, rank, local):
         t_sim = engine.step(M, t_sim, dt)
         stops[i].record()
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop()
     launches = engine.launches - launches0
     per_launch_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
