@@ -107,8 +107,11 @@ struct TileMath {
 
 template <int C, int NT>
 struct TileSmem {
-    static constexpr int R = NT + 1;  // rows of every exchange array; row ZR is all zeros and never written
-    static constexpr int ZR = NT;
+    // rows of every exchange array: thread t owns row t + 1; row 0 is all zeros and never written.  A run without a
+    // predecessor reads row (own - 1): row 0, or the previous rod's last run, whose "last element" entries are zero because
+    // its last slot is the node-only slot.  A run without a successor reads its own row (the result is masked).  Both
+    // keep a half-warp's addresses contiguous, i.e. free of bank conflicts.
+    static constexpr int R = NT + 1;
     static constexpr int XF = 0;                  // [3][R]    position of the run's first node
     static constexpr int VF = XF + 3 * R;         // [3][R]    velocity of the run's first node
     static constexpr int QF = VF + 3 * R;         // [9][R]    director of the run's first element
@@ -140,7 +143,7 @@ struct TileThread {
     double x[C][3], v[C][3], Q[C][9], w[C][3];
     double dtmc[C];  // dt c_t / node mass
     int fl[C];
-    int t, tn, tprev, t1, to, top;
+    int t, tn, t1, to;  // rows: own, next run (or own), partner as rod one of my joints (or 0), owner of the joints in which I am rod one (or 0)
     int rod;
     // extra joints (kExtras kernels): per slot published xe + 1 | overwrite source xe + 1 << 8 | node items << 16 |
     // first item << 20; the extra joint this thread evaluates or -1
@@ -195,7 +198,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
     const int t = th.t;
     const double dt = p.dt, hdt = 0.5 * p.dt;
     TileWhere wh{};
-    if (kLast) wh = tile_where<C>(p, t, b, rank);
+    if (kLast) wh = tile_where<C>(p, t - 1, b, rank);
     const int n = wh.n, np1 = wh.n + 1;
     double *const inst = wh.inst;
 #define UNI(idx) p.uni[(idx)]
@@ -446,7 +449,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
             const int *ji = XJI + xj * 12;
             const double *jd = XJD + xj * 8;
             const double *const sm1 = tile_peer<kCluster>(sm, ji[0]), *const sm2 = tile_peer<kCluster>(sm, ji[3]);
-            const int row1 = ji[1], j1 = ji[2], row2 = ji[4], j2 = ji[5], q1 = ji[6], q2 = ji[7];
+            const int row1 = ji[1] + 1, j1 = ji[2], row2 = ji[4] + 1, j2 = ji[5], q1 = ji[6], q2 = ji[7];
             const double kj = jd[0], nuj = jd[1];
             const double r1 = EXR[ji[8]], r2 = EXR[ji[9]];
 #pragma unroll
@@ -469,13 +472,14 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
         if (kLast) tile_cluster_wait<kCluster>();  // the reporting step gathers them early (external forces are reported)
         const double ramp_raw = time_mid * tb.act_inv_ramp;
         const double ramp = (ramp_raw < 1.0) ? ramp_raw : 1.0;
-        // what the previous run's last element contributes to my first node / element
+        // what the previous run's last element contributes to my first node / element (rows: see TileSmem)
+        const int tprev = t - 1, top = (th.to > 0) ? th.to - 1 : 0;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            const double fp = sm[L::HF + (3 * (C - 1) + i) * R + th.top] - sm[L::HF + (3 * (C - 1) + i) * R + th.tprev];
-            const double sp = sm[L::SKL + i * R + th.tprev];
+            const double fp = sm[L::HF + (3 * (C - 1) + i) * R + top] - sm[L::HF + (3 * (C - 1) + i) * R + tprev];
+            const double sp = sm[L::SKL + i * R + tprev];
             v[0][i] = fma(th.dtmc[0], fp - sp, v[0][i]);
-            tint[0][i] += fma(0.5, sm[L::CL + i * R + th.tprev], -sm[L::AL + i * R + th.tprev]);
+            tint[0][i] += fma(0.5, sm[L::CL + i * R + tprev], -sm[L::AL + i * R + tprev]);
             if (kLast) {
                 r_fint[0][i] -= sp;
                 r_fext[0][i] += fp;
@@ -639,7 +643,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 template <int C, int NT, int kMinBlocks, bool kExtras, bool kCluster, bool kExact>
 __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __grid_constant__ StepParams p) {
     using L = TileSmem<C, NT>;
-    constexpr int R = L::R, ZR = L::ZR;
+    constexpr int R = L::R;
     extern __shared__ double sm[];
     __shared__ long long s_item;
     __shared__ int s_why;
@@ -691,7 +695,7 @@ __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __gri
         const bool final_chunk = (chunk == p.n_chunks - 1);
 
         TileThread<C> th;
-        th.t = t;
+        th.t = t + 1;
         th.bad = 0;
         // ---- which run is mine -------------------------------------------------------------------
         const bool active = t < tp.cta_threads[rank];
@@ -702,12 +706,10 @@ __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __gri
 
             // rows I read from: next / previous run of my rod, my partner as rod one of the joints I own, the owner
             // of the joints in which I am rod one (and the owner of my predecessor's); the zero row when there is none
-            th.tn = (active && k0 + C <= n) ? t + 1 : ZR;
-            th.tprev = (active && k0 > 0) ? t - 1 : ZR;
+            th.tn = (active && k0 + C <= n) ? t + 2 : t + 1;
             const int r1 = tp.partner[rod], ro = tp.owner[rod];
-            th.t1 = (active && r1 >= 0) ? tp.rod_t0[r1] + (t - tp.rod_t0[rod]) : ZR;
-            th.to = (active && ro >= 0) ? tp.rod_t0[ro] + (t - tp.rod_t0[rod]) : ZR;
-            th.top = (th.to != ZR && k0 > 0) ? th.to - 1 : ZR;
+            th.t1 = (active && r1 >= 0) ? 1 + tp.rod_t0[r1] + (t - tp.rod_t0[rod]) : 0;
+            th.to = (active && ro >= 0) ? 1 + tp.rod_t0[ro] + (t - tp.rod_t0[rod]) : 0;
 
             const double dt = p.dt;
             const int np1 = n + 1;
@@ -741,7 +743,7 @@ __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __gri
 #if BR2_TILE_TA_REGS
                     th.ta[j][i] = ta[i];
 #else
-                    sm[L::TA + (3 * j + i) * R + t] = ta[i];
+                    sm[L::TA + (3 * j + i) * R + t + 1] = ta[i];
 #endif
                     th.x[j][i] = valid ? __ldcg(inst + i * np1 + k) : 0.0;
                     th.v[j][i] = valid ? __ldcg(inst + 3 * np1 + i * np1 + k) : 0.0;
