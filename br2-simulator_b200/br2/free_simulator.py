@@ -87,6 +87,32 @@ class FreeCallback(CallBackBaseClass):
             sink[key].append(np.array(getattr(system, attribute), copy=True))
         sink["com"].append(system.compute_position_center_of_mass())
 
+    def make_callback_lazy(self, capture, rod_index, rod, time, current_step):
+        """Same record as ``make_callback`` from a device-side capture of the batch state (br2/_capture.py): nothing is
+        copied to the host until an entry is read.  Used when the sink is the ``CaptureSink`` this package creates."""
+        from ._capture import _Lazy
+        from .hooks.rod import DYNAMIC_FIELDS
+
+        if current_step % self.every:
+            return
+        window = self.time_interval
+        if window is not None and (time < window[0] or time > window[1]):
+            return
+        sink = self.callback_params
+        sink["time"].append(time)
+        sink["step"].append(current_step)
+        n = rod.n_elems
+        for key, attribute in _CALLBACK_ARRAYS:
+            short, shape = DYNAMIC_FIELDS[attribute]
+            sink[key].append(_Lazy(lambda short=short, shape=shape(n): capture.field(rod_index, short, shape)))
+        mass = np.asarray(rod.mass)
+
+        def com():
+            x = capture.field(rod_index, "x", (3, n + 1))
+            return (x * mass).sum(axis=-1) / mass.sum()
+
+        sink["com"].append(_Lazy(com))
+
 
 def _load_rod_library(path):
     with open(path) as handle:
@@ -258,7 +284,9 @@ class FreeAssembly:
                 self.tip_to_base_connection(self.free[upstream_name], self.free[downstream_name], **param)
 
     def add_callback(self, name, step_skip, callback=None, **kwargs):
-        sink = defaultdict(list)
+        from ._capture import CaptureSink
+
+        sink = CaptureSink()  # a defaultdict like the reference's, whose lists may hold device-side captures
         self.simulator.collect_diagnostics(self.free[name]).using(
             FreeCallback if callback is None else callback, step_skip=step_skip, callback_params=sink, **kwargs)
         return sink

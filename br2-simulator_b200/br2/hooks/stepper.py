@@ -33,9 +33,21 @@ def _do_step(stepper, stages_and_updates, collection, time, dt, n_steps=1, callb
     if callbacks and collection._callback_ops:
         current_step = round(end / dt)
         if collection.callbacks_due(current_step):
-            snap = collection.snapshot_views()
+            # collectors that can record from a device-side clone of the batch state do so (no host copy until their
+            # histories are read); any other callback object gets the reference's protocol on a host snapshot
+            from .._capture import CaptureSink, capture_state
+
+            snap = capture = None
             for rod_index, op in collection._callback_ops:
-                op.make_callback(snap[rod_index], end, current_step)
+                lazy = getattr(op, "make_callback_lazy", None)
+                if lazy is not None and isinstance(getattr(op, "callback_params", None), CaptureSink):
+                    if capture is None:
+                        capture = capture_state(engine)
+                    lazy(capture, rod_index, collection._systems[rod_index], end, current_step)
+                else:
+                    if snap is None:
+                        snap = collection.snapshot_views()
+                    op.make_callback(snap[rod_index], end, current_step)
     return end
 
 

@@ -373,6 +373,39 @@ def test_full_size_batches_by_properties(assembly, kwargs, batch, n_steps):
     env.close()
 
 
+def test_device_side_captures_equal_host_snapshots():
+    """FreeCallback histories recorded as device-side clones of the batch state (materialised on read) are identical to
+    the ones recorded through the reference's make_callback protocol on host snapshots."""
+    from br2.environment import Environment
+    from br2.free_simulator import FreeCallback
+
+    class EagerCallback(FreeCallback):
+        make_callback_lazy = None  # forces the host-snapshot path
+
+    action = {"action1": np.array([30.0, 5.0, 12.0]) * PSI, "action2": 12 * PSI, "action3": np.array([0.0, 20.0, 3.0]) * PSI}
+    histories = []
+    for callback in (None, EagerCallback):
+        env = Environment("gpu_test", rendering_fps=250, batch=3, create_dirs=False)  # step_skip = 200
+        env.reset(ROD_DB, ASSEMBLY["single"], gravity=True)
+        if callback is not None:
+            env.simulator._callback_ops = [(r, callback(op.every, op.callback_params, op.time_interval))
+                                           for r, op in env.simulator._callback_ops]
+        env.run(action, duration=1000 * 2e-5 - 1e-5, disable_progress_bar=True)
+        if callback is None:
+            series = env.data_rods[0]["position"]
+            assert "still on the device" in repr(series) and len(series) == 5
+        histories.append(env.data_rods)
+        env.close()
+    lazy, eager = histories
+    for sink_l, sink_e in zip(lazy, eager):
+        assert list(sink_l["step"]) == list(sink_e["step"]) == [200, 400, 600, 800, 1000]
+        assert set(sink_l.keys()) == set(sink_e.keys())
+        for key in sink_e:
+            np.testing.assert_array_equal(np.array(sink_l[key]), np.array(sink_e[key]), err_msg=key)
+        assert np.array(sink_l["position"]).shape == (5, 3, 3, 42)
+        np.testing.assert_array_equal(sink_l["director"][-1], np.array(sink_e["director"])[-1])
+
+
 def test_step_host_entry_point_matches_device_path():
     """br2_step_host (host buffers in, host buffers out) == bind + step on device buffers."""
     import ctypes
