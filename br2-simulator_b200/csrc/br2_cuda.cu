@@ -540,7 +540,7 @@ int br2_select_kernel(br2_handle h, int32_t variant) {
         smem = sizeof(double) * (30 * S + 9 * (size_t)h->t.n_joints + 32);
     else if (variant == 3)
         smem = sizeof(double) * ((size_t)br2::TileSmem<BR2_TILE_C, 0>::ROWS_END * (size_t)(pick.threads + 1) +
-                                 br2::TileSmem<BR2_TILE_C, 0>::TAIL + 25 * (size_t)h->tile.n_xe + (3 + 8 + 6) * (size_t)h->tile.n_xj +
+                                 25 * (size_t)h->tile.n_xe + (3 + 8 + 6) * (size_t)h->tile.n_xj +
                                  ((size_t)h->tile.n_xitems + 1) / 2);
     else
     {

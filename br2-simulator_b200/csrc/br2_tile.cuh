@@ -56,12 +56,9 @@ __device__ __forceinline__ T *tile_peer(T *local, int rank) {
     return local;
 }
 
-#ifndef BR2_TILE_JD_MODE
-#define BR2_TILE_JD_MODE 1   // joint direction vectors: 0 = per-rod table in shared memory, 1 = constant bank (indexed by rod)
-#endif
-#ifndef BR2_TILE_TA_REGS
-#define BR2_TILE_TA_REGS 0   // actuation torques: 1 = registers, 0 = shared-memory rows
-#endif
+// Where the per-thread constants live was measured (single_br2 x 4096, el-steps/s): joint direction vectors from the
+// constant bank indexed by rod 3.05e10, from a per-rod shared-memory table 2.96e10; actuation torques in shared-memory
+// rows 3.05e10, in registers 2.92e10 (every register kept across the step costs instruction-level parallelism).
 
 // Arithmetic of the step: the optimistic series / hardware seeds (kExact = false), or IEEE division, sqrt and libm
 // with no validity range (kExact = true).  The exact instantiation is the replay path of assemblies that are too large
@@ -128,10 +125,8 @@ struct TileSmem {
     static constexpr int ZERO_END = FS + 3 * C * R;  // everything above is zeroed at launch
     static constexpr int TA = ZERO_END;           // [C][3][R] actuation torque at full ramp (material frame)
     static constexpr int ROWS_END = TA + 3 * C * R;
-    // after the rows (host: TileSmem<C, 0>::ROWS_END * (threads + 1) + TAIL words, then the extra-joint area)
-    static constexpr int JD = ROWS_END;           // [8][BR2_TILE_MAX_RODS] {dv2[3], offset/2, dv1[3], offset/2} per rod
-    static constexpr int TAIL = 8 * BR2_TILE_MAX_RODS;
-    static constexpr int EX = JD + TAIL;          // extra joints (rank 0's copy is the live one in a cluster):
+    // after the rows (host: TileSmem<C, 0>::ROWS_END * (threads + 1) words), the extra-joint area
+    static constexpr int EX = ROWS_END;           // extra joints (rank 0's copy is the live one in a cluster):
                                                   // EXQ [2][9][n_xe], EXW [2][3][n_xe] (by step parity), EXR [n_xe], JF [3][n_xj]
 };
 
@@ -148,9 +143,6 @@ struct TileThread {
     // extra joints (kExtras kernels): per slot published xe + 1 | overwrite source xe + 1 << 8 | node items << 16 |
     // first item << 20; the extra joint this thread evaluates or -1
     int xinfo[C], xjoint;
-#if BR2_TILE_TA_REGS
-    double ta[C][3];
-#endif
     int bad;  // bit 0: rotation angle, bit 1: curvature angle, bit 2: strain left its series' range (or NaN)
 };
 
@@ -202,16 +194,8 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
     const int n = wh.n, np1 = wh.n + 1;
     double *const inst = wh.inst;
 #define UNI(idx) p.uni[(idx)]
-#if BR2_TILE_JD_MODE == 1
 #define JDV(i) p.tile.jd[th.rod][(i)]
-#else
-#define JDV(i) sm[L::JD + (i) * BR2_TILE_MAX_RODS + th.rod]
-#endif
-#if BR2_TILE_TA_REGS
-#define TAV(j, i) th.ta[(j)][(i)]
-#else
 #define TAV(j, i) sm[L::TA + (3 * (j) + (i)) * R + t]
-#endif
     double (&x)[C][3] = th.x;
     double (&v)[C][3] = th.v;
     double (&Q)[C][9] = th.Q;
@@ -635,13 +619,8 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 #undef TAV
 }
 
-#ifdef BR2_TILE_MAXREG
-#define BR2_TILE_BOUNDS(NT, MB) __maxnreg__(BR2_TILE_MAXREG)
-#else
-#define BR2_TILE_BOUNDS(NT, MB) __launch_bounds__(NT, MB)
-#endif
 template <int C, int NT, int kMinBlocks, bool kExtras, bool kCluster, bool kExact>
-__global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __grid_constant__ StepParams p) {
+__global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __grid_constant__ StepParams p) {
     using L = TileSmem<C, NT>;
     constexpr int R = L::R;
     extern __shared__ double sm[];
@@ -740,11 +719,7 @@ __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __gri
                 }
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
-#if BR2_TILE_TA_REGS
-                    th.ta[j][i] = ta[i];
-#else
                     sm[L::TA + (3 * j + i) * R + t + 1] = ta[i];
-#endif
                     th.x[j][i] = valid ? __ldcg(inst + i * np1 + k) : 0.0;
                     th.v[j][i] = valid ? __ldcg(inst + 3 * np1 + i * np1 + k) : 0.0;
                     th.w[j][i] = elem ? __ldcg(inst + 6 * np1 + 9 * n + i * n + k) : 0.0;
@@ -775,9 +750,7 @@ __global__ void BR2_TILE_BOUNDS(NT, kMinBlocks) br2_step_tile_kernel(const __gri
                 for (int i = t; i < 12 * tp.n_xj; i += NT) XJI[i] = tp.xj_i[i];
                 for (int i = t; i < tp.n_xitems; i += NT) XIT[i] = tp.xitems[i];
             }
-            // joint descriptors per rod: as rod two of the joints it owns {dv2[3], offset/2}, as rod one {dv1[3], offset/2}
-            th.rod = rod;
-            for (int i = t; i < 8 * BR2_TILE_MAX_RODS; i += NT) sm[L::JD + i] = tp.jd[i % BR2_TILE_MAX_RODS][i / BR2_TILE_MAX_RODS];
+            th.rod = rod;  // indexes the per-rod joint descriptors in the constant bank (TilePlan::jd)
         }
         // zero the exchange arrays (the zero row stays zero for the whole chunk)
         for (int i = t; i < L::ZERO_END; i += NT) sm[i] = 0.0;
