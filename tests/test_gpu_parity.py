@@ -286,6 +286,37 @@ def test_optional_ops_point_force_and_last_end_fixed():
     np.testing.assert_array_equal(rod.velocity_collection[:, -1], 0.0)
 
 
+def test_baseline_config_1_examples_run_script(tmp_path, monkeypatch):
+    """BASELINE configs[0]: what /root/reference/examples/run.py does -- single_br2_v1, gravity, 30 psi on action1 and
+    action2, duration 1.0 s (50001 steps from the fp64 time accumulation, 25 captures), check_nan and steady-state check,
+    save_data -- against the C oracle after all 50001 steps."""
+    from br2.environment import Environment
+
+    monkeypatch.chdir(tmp_path)
+    action = {"action1": 30 * PSI, "action2": 30 * PSI}
+    env = Environment(run_tag="c1")
+    env.reset(rod_database_path=ROD_DB, assembly_config_path=ASSEMBLY["single"], gravity=True)
+    status = env.run(action=action, duration=1.0, check_nan=True, check_steady_state=True, disable_progress_bar=True)
+    assert status.end_status and not status.position_nan_status and not status.director_nan_status
+    n_steps = 50001
+    assert round(env.time / env.time_step) == n_steps and env.step_skip == 2000
+    assert list(env.data_rods[0]["step"]) == list(range(2000, 50001, 2000))
+    assert env.engine.replay_count() == 0
+    env.save_data()
+    saved = np.load(os.path.join("result_c1", "data", "br2_data.npz"))
+    assert saved["positions"].shape == (3, 25, 3, 41) and saved["directors"].shape == (3, 25, 3, 3, 41)
+    pressures = np.array([[30 * PSI], [30 * PSI], [0.0]])
+    fused, W = fused_reference("single", {"gravity": True}, pressures, n_steps)
+    x_scale = max(np.abs(fused.view(W, r, "x")).max() for r in range(3))
+    for r, rod in enumerate(env.simulator):
+        # 5e4 steps: the rounding-noise floor has had five times longer to grow than in the 1e4-step bar
+        assert np.abs(rod.position_collection - fused.view(W, r, "x")[0]).max() <= 5 * POS_TOL * x_scale
+        assert np.abs(rod.director_collection - fused.view(W, r, "Q")[0]).max() <= 5 * DIR_TOL
+    tip = env.simulator[0].position_collection[:, -1]
+    assert abs(tip[0]) > 1e-3  # the arm really bent
+    env.close()
+
+
 def test_lone_rod_with_odd_slot_count_on_the_tile_kernel():
     """Ragged case for the tile kernel: one rod, no joints (no partner / owner rows), 21 node slots = 10 full runs of two
     slots and one half-empty run; gravity, damper, soft-fixed base and a twist actuation through the hooks, vs the
