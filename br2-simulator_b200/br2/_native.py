@@ -46,7 +46,7 @@ EXPORTS = (
     "br2_last_error", "br2_abi_version", "br2_create", "br2_destroy", "br2_words_per_instance",
     "br2_bind_state", "br2_set_actuation", "br2_step", "br2_step_host", "br2_count_steps",
     "br2_kernel_info", "br2_fp64_peak_tflops", "br2_select_kernel", "br2_selftest_math", "br2_replay_count",
-    "br2_replay_reasons", "br2_unresolved_count",
+    "br2_replay_reasons", "br2_unresolved_count", "br2_describe_plan",
 )
 
 
@@ -76,6 +76,7 @@ def load():
     lib.br2_kernel_info.argtypes = [ctypes.c_void_p] + [_i32p] * 6
     lib.br2_select_kernel.argtypes = [ctypes.c_void_p, ctypes.c_int32]
     lib.br2_replay_count.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]
+    lib.br2_describe_plan.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]
     lib.br2_unresolved_count.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]
     lib.br2_replay_reasons.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_int64)] * 3
     lib.br2_selftest_math.argtypes = [ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
@@ -102,6 +103,14 @@ def make_program(prog):
             "joint_d", "node_ptr", "node_items", "elem_ptr", "elem_items", "overwrite_src")],
         int(prog.fast["ok"]), int(prog.fast["uniform"]), int(prog.fast["n_act"]), 0, float(prog.fast["ramp_up_time"]),
         *[t[name].ctypes.data for name in ("fast_i", "fast_c", "act_i", "act_d")])
+
+
+def describe_plan(prog):
+    """Which kernel the library would pick for a lowered ``Program`` and its layout (host only, no GPU needed)."""
+    buf = ctypes.create_string_buffer(512)
+    cprog = make_program(prog)
+    check(load().br2_describe_plan(ctypes.byref(cprog), buf, len(buf)))
+    return buf.value.decode()
 
 
 def count_steps(t0, duration, dt):

@@ -130,6 +130,12 @@ class BaseSystemCollection(MutableSequence):
             self.program = lower_collection(self)
         return self.program
 
+    def kernel_plan(self):
+        """Which device kernel would integrate this collection and how (one line; needs no GPU)."""
+        from .. import _native
+
+        return _native.describe_plan(self.lower())
+
     def snapshot_views(self):
         """Host snapshot of every rod (one D2H copy of the batch state) for diagnostics callbacks."""
         from .rod import HostRodView

@@ -821,6 +821,30 @@ int br2_replay_count(br2_handle h, int64_t *count) {
     return BR2_OK;
 }
 
+int br2_describe_plan(const br2_program *p, char *buf, int64_t buf_len) {
+    if (!buf || buf_len <= 0) return fail(BR2_EINVAL, "br2_describe_plan: no buffer");
+    int rc = validate(p);
+    if (rc != BR2_OK) return rc;
+    std::string text;
+    br2::TilePlan plan{};
+    TileExtraTables xt;
+    std::string why;
+    if (p->fast_ok && p->fast_i && p->fast_c && make_tile_plan(p, BR2_TILE_C, &plan, &xt, &why)) {
+        text = "tile: " + std::to_string(plan.n_ctas) + " CTA(s) per instance";
+        for (int c = 0; c < plan.n_ctas; ++c) text += (c ? ", " : " of ") + std::to_string(plan.cta_threads[c]);
+        text += " threads (" + std::to_string(BR2_TILE_C) + " slots per thread), " + std::to_string(plan.n_xj) +
+                " tip-to-base joint(s)";
+    } else if (p->fast_ok && p->fast_i && p->fast_c) {
+        text = std::string(p->fast_uniform ? "fast-uniform" : "fast") + ": one slot per thread (tile kernel refused: " + why + ")";
+    } else {
+        text = "generic: table-interpreting kernel (the assembly is outside the BR2 fast-path pattern)";
+    }
+    if (p->n_slots > 1024 && text.compare(0, 5, "tile:") != 0)
+        return fail(BR2_ELIMIT, "assembly has " + std::to_string(p->n_slots) + " node slots and does not qualify for the cluster kernel: " + why);
+    snprintf(buf, (size_t)buf_len, "%s", text.c_str());
+    return BR2_OK;
+}
+
 int br2_unresolved_count(br2_handle h, int64_t *count) {
     if (!h || !count) return fail(BR2_EINVAL, "br2_unresolved_count: bad argument");
     *count = 0;

@@ -220,6 +220,11 @@ int br2_step_host(br2_handle h, double *host_state, const double *host_pressures
  * (environment.py:278: the count comes from fp64 accumulation, two +dt/2 per step). */
 int br2_count_steps(double t0, double duration, double dt, int64_t *n_steps, double *t_end);
 
+/* Which kernel br2_create would pick for this program and how it would lay the assembly out ("tile: 3 CTA(s) per instance
+ * of 303, 303, 303 threads ..."), or why the faster kernels refuse it.  Host only: needs no GPU.  BR2_ELIMIT if the
+ * assembly fits no kernel. */
+int br2_describe_plan(const br2_program *program, char *buf, int64_t buf_len);
+
 /* Kernel facts for measurement: registers per thread, dynamic shared memory per block, threads per
  * block, resident blocks per SM as reported by the occupancy API, SM count of the device, and which
  * kernel br2_step launches (0 generic, 1 fast per-slot constants, 2 fast uniform constants). */

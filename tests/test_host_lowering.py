@@ -197,3 +197,29 @@ def test_set_actuation_unknown_action_raises_like_reference():
     assy, _ = build_product("single")
     with pytest.raises(IndexError):
         assy.set_actuation({"no_such_action": 1.0})
+
+
+def test_kernel_plan_of_the_baseline_assemblies(tmp_path):
+    """Which kernel libbr2cuda picks and how it lays the assembly out (host-only entry point br2_describe_plan)."""
+    from br2 import _native
+
+    assert _native.describe_plan(build_product("single", gravity=True)[1]) == \
+        "tile: 1 CTA(s) per instance of 63 threads (2 slots per thread), 0 tip-to-base joint(s)"
+    assert _native.describe_plan(build_product("double")[1]) == \
+        "tile: 1 CTA(s) per instance of 126 threads (2 slots per thread), 9 tip-to-base joint(s)"
+    assert _native.describe_plan(build_product("triple")[1]) == \
+        "tile: 1 CTA(s) per instance of 189 threads (2 slots per thread), 18 tip-to-base joint(s)"
+    # BASELINE config 4: 200 elements per rod -> one CTA per segment, a cluster of three
+    assy = FreeAssembly(FakeEnv())
+    assy.build(os.path.join(DATA, "rod_library_n200.json"), ASSEMBLY["triple"], verbose=False)
+    assert _native.describe_plan(assy.simulator.lower()) == \
+        "tile: 3 CTA(s) per instance of 303, 303, 303 threads (2 slots per thread), 18 tip-to-base joint(s)"
+    # a segment too long for one CTA of the cluster kernel is refused with the reason
+    library = json.load(open(os.path.join(DATA, "rod_library_n200.json")))
+    library["DefaultParams"]["n_elements"] = 250
+    path = tmp_path / "rod_library_n250.json"
+    path.write_text(json.dumps(library))
+    assy = FreeAssembly(FakeEnv())
+    assy.build(str(path), ASSEMBLY["triple"], verbose=False)
+    with pytest.raises(_native.Br2Error, match="needs 378 threads"):
+        _native.describe_plan(assy.simulator.lower())
