@@ -303,20 +303,38 @@ def run_ours(args, world, rank, local):
     state_ok = bool(torch.isfinite(engine.state).all().item())
 
     # ---- end to end through the public API ---------------------------------------------------
-    pinned_state = torch.empty((B, engine.words), dtype=torch.float64).pin_memory()
+    # Every step: H2D of the step's pressures (inside Environment.run), the integration launch, and a D2H read of the
+    # whole batch state into pinned host memory.  The read is pipelined the way a user consuming results would do it:
+    # a device-side clone of the state (0.1 ms) is copied out on a second stream while the next step's launch runs;
+    # all copies complete inside the timed region (barrier() synchronises every stream of the device).
+    pinned = [torch.empty((B, engine.words), dtype=torch.float64).pin_memory() for _ in range(2)]
+    clones = [torch.empty_like(engine.state) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device)
+    copied = [None, None]
     e2e_steps = max(2, min(args.steps, 5))
     duration = M * dt - 0.5 * dt
+    e2e_count = [0]
 
     from br2 import _dist
 
     def e2e_once():
+        buf = e2e_count[0] % 2
+        e2e_count[0] += 1
         env.run(action_host, duration=duration, disable_progress_bar=True)  # H2D of the pressures inside
-        pinned_state.copy_(engine.state, non_blocking=True)                 # D2H of the batch state
+        if copied[buf] is not None:
+            copied[buf].synchronize()                                       # this buffer's previous read has landed
+        clones[buf].copy_(engine.state)
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ready)
+            pinned[buf].copy_(clones[buf], non_blocking=True)               # D2H of the batch state
+            copied[buf] = torch.cuda.Event()
+            copied[buf].record(copy_stream)
         if world > 1:
             # the only collective of the path: per-instance metrics of all ranks to rank 0 over NCCL
             tip = engine.view(0, "x")[:, :, -1].contiguous()
             _dist.gather_batch(tip, B * world, dst=0, device=device)
-        torch.cuda.synchronize(device)
 
     e2e_once()
     barrier()
