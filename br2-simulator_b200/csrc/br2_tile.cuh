@@ -17,13 +17,19 @@
 // profiles/probes/dfma_latency_probe.cu).
 //
 // Semantics are those of br2_fast.cuh / br2_generic.cuh; the optimistic-series
-// protocol is the same: a CTA that leaves a series' validity range flags its instance, does not write back,
-// and the generic kernel redoes the launch for it right behind on the stream.
+// protocol is the same: a CTA that leaves a series' validity range flags its instance and does not write back;
+// the exact-path pass launched right behind on the stream redoes the instance from the chunk that failed (the generic
+// kernel, or this kernel's kExact instantiation for assemblies too large for it).
+//
+// Work distribution: persistent CTAs (or clusters) pull (chunk, instance) items off one queue -- see the kernel.
+// Template flags: kExtras = tip-to-base joints between segments (director overwrites included); kCluster = one CTA per
+// group of ring-connected rods, a thread-block cluster per instance (assemblies beyond one SM's registers);
+// kExact = IEEE / libm arithmetic without validity ranges.
 //
 // Applicability (decided on the host, br2_cuda.cu: make_tile_plan): fast-path assembly with uniform element
-// constants, no "extra" joints / director overwrites (single-segment assemblies), every surface joint
-// connects equal element indices of two rods, all joints of a rod pair share one descriptor, and the joints' direction
-// vectors have no component along the rod axis d3 (rods side by side).
+// constants, every surface joint connects equal element indices of two rods, all joints of a rod pair share one
+// descriptor whose direction vectors have no component along the rod axis d3 (rods side by side), every other joint
+// is a tip-to-base joint, and each group of ring-connected rods fits one CTA (320 threads = 640 slots).
 #pragma once
 
 #include <cooperative_groups.h>
