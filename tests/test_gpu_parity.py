@@ -186,6 +186,30 @@ def test_cluster_path_on_the_sample_triple(monkeypatch):
     assert worst["x"] <= POS_TOL and worst["Q"] <= DIR_TOL and worst["v"] <= VEL_TOL and worst["w"] <= OMEGA_TOL
 
 
+def test_cluster_path_reports_the_same_callback_arrays(monkeypatch):
+    """Everything FreeCallback records (state AND the derived arrays written on a launch's last step: accelerations,
+    internal / external loads, lengths, dilatation, radius) agrees between the one-CTA and the cluster layout."""
+    from br2.environment import Environment
+
+    action = {"action1": np.array([15.0, 33.0]) * PSI, "action2": 30 * PSI, "action3": np.array([5.0, 0.0]) * PSI}
+    histories = []
+    for threads in (None, "100"):
+        if threads is not None:
+            monkeypatch.setenv("BR2_TILE_ONE_CTA_THREADS", threads)
+        env = Environment("gpu_test", rendering_fps=250, batch=2, create_dirs=False)  # step_skip = 200
+        env.reset(ROD_DB, ASSEMBLY["triple"], gravity=True)
+        assert env.engine.kernel_info()["threads"] == 192
+        env.run(action, duration=600 * 2e-5 - 1e-5, disable_progress_bar=True)
+        histories.append([{key: np.array(sink[key]) for key in sink} for sink in env.data_rods])
+        env.close()
+    one_cta, cluster = histories
+    for sink_a, sink_b in zip(one_cta, cluster):
+        assert list(sink_a["step"]) == [200, 400, 600]
+        for key in sink_a:
+            scale = max(np.abs(sink_a[key]).max(), 1e-300)
+            assert np.abs(sink_a[key] - sink_b[key]).max() <= 1e-9 * scale, key
+
+
 def test_cluster_path_replays_out_of_range_instances_exactly(monkeypatch):
     """Cluster-sized assemblies have no one-CTA generic kernel to fall back on: the exact-arithmetic instantiation of the
     cluster kernel redoes flagged instances from the chunk in which they left the series' range.  Forced here on the
