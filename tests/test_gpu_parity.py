@@ -382,6 +382,45 @@ def test_lone_rod_with_odd_slot_count_on_the_tile_kernel():
     assert np.abs(rod.omega_collection - orod.omega_collection).max() <= OMEGA_TOL
 
 
+def test_last_end_fixed_rod_on_the_tile_kernel():
+    """custom_constraint.LastEndFixedRod (/root/reference/br2/custom_constraint.py:35-88) pins the last node and element;
+    without point forces the rod stays on the tile kernel.  A cantilever hanging from its far end under gravity."""
+    from br2.custom_constraint import LastEndFixedRod
+    from br2.free_simulator import BR2Simulator
+    from br2.hooks import AnalyticalLinearDamper, CosseratRod, GravityForces, PositionVerlet, extend_stepper_interface
+    from oracle import br2_port, mini_elastica
+
+    spec = dict(n_elements=31, start=np.zeros(3), direction=np.array([0.0, 1.0, 0.0]), normal=np.array([0.0, 0.0, 1.0]),
+                base_length=0.25, base_radius=0.004, density=1100.0, youngs_modulus=3e6, shear_modulus=2e6)
+    dt, n_steps = 1.0e-5, 4000
+
+    def build(sim_cls, rod_cls, damper, gravity, pin):
+        sim = sim_cls()
+        rod = rod_cls.straight_rod(**spec)
+        sim.append(rod)
+        sim.dampen(rod).using(damper, damping_constant=1.0, time_step=dt)
+        sim.add_forcing_to(rod).using(gravity, acc_gravity=np.array([0.0, 0.0, -9.80665]))
+        sim.constrain(rod).using(pin, constrained_position_idx=(-1,), constrained_director_idx=(-1,))
+        sim.finalize()
+        return sim, rod
+
+    sim, rod = build(BR2Simulator, CosseratRod, AnalyticalLinearDamper, GravityForces, LastEndFixedRod)
+    assert sim.engine.kernel_info()["variant_name"] == "tile"
+    do_step, stages = extend_stepper_interface(PositionVerlet(), sim)
+    do_step(PositionVerlet(), stages, sim, 0.0, dt, n_steps=n_steps)
+    assert sim.engine.replay_count() == 0
+    osim, orod = build(br2_port.BR2Simulator, mini_elastica.CosseratRod, mini_elastica.AnalyticalLinearDamper,
+                       mini_elastica.GravityForces, br2_port.LastEndFixedRod)
+    mini_elastica.timestepper.integrate(mini_elastica.PositionVerlet(), osim, n_steps * dt, n_steps)
+    assert abs(orod.position_collection[2, 0]) > 1e-4  # the free end sagged
+    scale = np.abs(orod.position_collection).max()
+    assert np.abs(rod.position_collection - orod.position_collection).max() <= POS_TOL * scale
+    assert np.abs(rod.director_collection - orod.director_collection).max() <= DIR_TOL
+    np.testing.assert_array_equal(rod.position_collection[:, -1], orod.position_collection[:, -1])
+    np.testing.assert_array_equal(rod.velocity_collection[:, -1], 0.0)
+    np.testing.assert_array_equal(rod.omega_collection[:, -1], 0.0)
+
+
 FULL_SIZE = [
     # BASELINE.json configs at their full batch sizes: (assembly, kwargs, batch, steps)
     ("single", {"gravity": True}, 4096, 2000),    # configs[1]
