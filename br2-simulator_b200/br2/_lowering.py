@@ -256,7 +256,8 @@ def lower_collection(collection):
         node_items=node_items, elem_ptr=elem_ptr, elem_items=elem_items, overwrite_src=overwrite_src,
         fast_i=fast["fast_i"], fast_c=fast["fast_c"], act_i=fast["act_i"], act_d=fast["act_d"],
     )
-    prog.fast = dict(ok=fast["ok"], uniform=fast["uniform"], why=fast["why"], ramp_up_time=fast["ramp_up_time"],
+    prog.fast = dict(ok=fast["ok"], uniform=fast["uniform"], point_forces=fast["point_forces"], why=fast["why"],
+                     ramp_up_time=fast["ramp_up_time"],
                      n_act=len(fast["act_i"]))
     prog.tables = {k: np.ascontiguousarray(v) for k, v in prog.tables.items()}
     prog.counts = dict(n_slots=S, n_rods=len(rods), n_forcing=len(forcing_rows), n_constraints=len(cons_rows),
@@ -274,7 +275,7 @@ def _lower_fast(ctx, rods, rod_i, slot_c, rod_d, forcing_rows, cons_rows, node_l
     fast_i[:, FAST_ACT_END] = 0
     fast_c = np.zeros((FC_COUNT, S))
     act_i, act_d = [], []
-    out = dict(ok=False, uniform=False, why="", ramp_up_time=1.0, fast_i=fast_i, fast_c=fast_c,
+    out = dict(ok=False, uniform=False, point_forces=False, why="", ramp_up_time=1.0, fast_i=fast_i, fast_c=fast_c,
                act_i=np.zeros(0, dtype=np.int32), act_d=np.zeros((0, 3)))
 
     def refuse(reason):
@@ -284,8 +285,9 @@ def _lower_fast(ctx, rods, rod_i, slot_c, rod_d, forcing_rows, cons_rows, node_l
     if slot_c[SC_REST_SIGMA:SC_REST_SIGMA + 3].any() or slot_c[SC_REST_KAPPA:SC_REST_KAPPA + 3].any():
         return refuse("non-zero rest strains")
     ramps = {float(row[1]) for kind, _, _, row in forcing_rows if kind in (FORCE_TWIST, FORCE_BEND)}
-    if any(kind == FORCE_POINT for kind, _, _, _ in forcing_rows):
-        return refuse("point forces")
+    # point forces stay in the generic forcing table; the tile kernel serves them as "extra" forces, the
+    # one-slot-per-thread fast kernel does not know them (libbr2cuda then picks the tile or the generic kernel)
+    out["point_forces"] = any(kind == FORCE_POINT for kind, _, _, _ in forcing_rows)
     if len(ramps) > 1:
         return refuse("actuation rows with different ramp_up_time")
     out["ramp_up_time"] = ramps.pop() if ramps else 1.0

@@ -31,7 +31,7 @@ class Br2Program(ctypes.Structure):
         ("joint_d", ctypes.c_void_p), ("node_ptr", ctypes.c_void_p), ("node_items", ctypes.c_void_p),
         ("elem_ptr", ctypes.c_void_p), ("elem_items", ctypes.c_void_p), ("overwrite_src", ctypes.c_void_p),
         ("fast_ok", ctypes.c_int32), ("fast_uniform", ctypes.c_int32), ("n_act", ctypes.c_int32),
-        ("reserved", ctypes.c_int32), ("act_ramp_up_time", ctypes.c_double),
+        ("fast_point_forces", ctypes.c_int32), ("act_ramp_up_time", ctypes.c_double),
         ("fast_i", ctypes.c_void_p), ("fast_c", ctypes.c_void_p), ("act_i", ctypes.c_void_p), ("act_d", ctypes.c_void_p),
     ]
 
@@ -101,7 +101,8 @@ def make_program(prog):
         *[t[name].ctypes.data for name in (
             "slot_rod", "rod_i", "rod_d", "slot_c", "forcing_i", "forcing_d", "cons_i", "cons_d", "joint_i",
             "joint_d", "node_ptr", "node_items", "elem_ptr", "elem_items", "overwrite_src")],
-        int(prog.fast["ok"]), int(prog.fast["uniform"]), int(prog.fast["n_act"]), 0, float(prog.fast["ramp_up_time"]),
+        int(prog.fast["ok"]), int(prog.fast["uniform"]), int(prog.fast["n_act"]), int(prog.fast["point_forces"]),
+        float(prog.fast["ramp_up_time"]),
         *[t[name].ctypes.data for name in ("fast_i", "fast_c", "act_i", "act_d")])
 
 

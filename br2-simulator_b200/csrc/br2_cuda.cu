@@ -140,7 +140,7 @@ struct br2_handle_s {
     size_t replay_smem = 0;
     int variant = 0;        // 0 generic, 1 fast, 2 fast uniform
     int auto_variant = 0;   // what br2_create picked
-    bool fast_ok = false, fast_uniform = false, has_extra = false, tile_ok = false;
+    bool fast_ok = false, fast_uniform = false, has_extra = false, tile_ok = false, fast_point = false;
     br2::TilePlan tile{};
     std::string tile_why;
     double uni[BR2_FC_COUNT] = {0};
@@ -359,6 +359,28 @@ bool make_tile_plan(const br2_program *p, int C, br2::TilePlan *plan, TileExtraT
             ++cnt;
         }
     }
+    // point forces (PointForces, /root/reference/br2/custom_activation.py:46-81): an "extra joint" of type 1 that puts
+    // F min(1, t / ramp_up_time) on one node
+    for (int r = 0; r < p->n_rods; ++r) {
+        const int32_t *ri = p->rod_i + r * BR2_ROD_NI;
+        for (int f = ri[BR2_ROD_F_BEGIN]; f < ri[BR2_ROD_F_END]; ++f) {
+            const int32_t *fi = p->forcing_i + (size_t)f * BR2_F_NI;
+            const double *fd = p->forcing_d + (size_t)f * BR2_F_ND;
+            if (fi[BR2_F_TYPE] != BR2_FORCE_POINT) continue;
+            if (fi[BR2_F_NODE] < 0 || fi[BR2_F_NODE] > ri[BR2_ROD_N]) return *why = "point force on a node outside its rod", false;
+            const int xj = plan->n_xj++;
+            int jn;
+            const int tn = thread_of(ri[BR2_ROD_SLOT0] + fi[BR2_F_NODE], &jn);
+            const int32_t row[12] = {slot_rank, slot_row, jn, slot_rank, slot_row, jn, 0, 0, 0, 0, 1 /* type: point force */, 0};
+            xt->xj_i.insert(xt->xj_i.end(), row, row + 12);
+            const double drow[8] = {fd[0], fd[1], fd[2], fd[3], 0, 0, 0, 0};
+            xt->xj_d.insert(xt->xj_d.end(), drow, drow + 8);
+            int32_t &cnt = xt->xi[(size_t)tn * XN + BR2_TILE_XI_NCNT(C, jn)];
+            if (cnt >= BR2_FAST_NODE_ITEMS) return *why = "a node receives too many extra forces", false;
+            xt->xi[(size_t)tn * XN + BR2_TILE_XI_NITEM(C, jn, cnt)] = (xj << 1) | 0;
+            ++cnt;
+        }
+    }
     for (size_t sl = 0; sl < S; ++sl) {
         if (p->overwrite_src[sl] < 0) continue;
         int j;
@@ -446,6 +468,7 @@ int br2_create(const br2_program *p, int device, br2_handle *out) {
     UP(elem_items, (size_t)p->elem_ptr[S]);
     UP(overwrite_src, S);
     h->fast_ok = p->fast_ok != 0 && p->fast_i && p->fast_c;
+    h->fast_point = p->fast_point_forces != 0;
     h->fast_uniform = h->fast_ok && p->fast_uniform != 0;
     if (h->fast_ok) {
         UP(fast_i, S * BR2_FAST_NI);
@@ -483,7 +506,7 @@ int br2_create(const br2_program *p, int device, br2_handle *out) {
             }
         }
     }
-    h->auto_variant = h->tile_ok ? 3 : h->fast_ok ? (h->fast_uniform ? 2 : 1) : 0;
+    h->auto_variant = h->tile_ok ? 3 : (h->fast_ok && !h->fast_point) ? (h->fast_uniform ? 2 : 1) : 0;
     rc = br2_select_kernel(h, -1);
     if (rc != BR2_OK) {
         br2_destroy(h);
@@ -501,6 +524,8 @@ int br2_select_kernel(br2_handle h, int32_t variant) {
         return fail(BR2_EINVAL, "br2_select_kernel: assembly does not qualify for the tile kernel: " + h->tile_why);
     if (variant >= 1 && !h->fast_ok) return fail(BR2_EINVAL, "br2_select_kernel: assembly does not qualify for the fast kernel");
     if (variant == 2 && !h->fast_uniform) return fail(BR2_EINVAL, "br2_select_kernel: assembly constants are not uniform");
+    if ((variant == 1 || variant == 2) && h->fast_point)
+        return fail(BR2_EINVAL, "br2_select_kernel: the one-slot-per-thread fast kernel does not serve point forces");
     CUDA_TRY(cudaSetDevice(h->device));
     const size_t S = (size_t)h->t.n_slots;
     KernelChoice pick{0, nullptr};
@@ -833,9 +858,10 @@ int br2_describe_plan(const br2_program *p, char *buf, int64_t buf_len) {
         text = "tile: " + std::to_string(plan.n_ctas) + " CTA(s) per instance";
         for (int c = 0; c < plan.n_ctas; ++c) text += (c ? ", " : " of ") + std::to_string(plan.cta_threads[c]);
         text += " threads (" + std::to_string(BR2_TILE_C) + " slots per thread), " + std::to_string(plan.n_xj) +
-                " tip-to-base joint(s)";
+                " tip-to-base joint(s) / point force(s)";
     } else if (p->fast_ok && p->fast_i && p->fast_c) {
-        text = std::string(p->fast_uniform ? "fast-uniform" : "fast") + ": one slot per thread (tile kernel refused: " + why + ")";
+        text = p->fast_point_forces ? "generic: table-interpreting kernel (tile kernel refused: " + why + ")"
+                                    : std::string(p->fast_uniform ? "fast-uniform" : "fast") + ": one slot per thread (tile kernel refused: " + why + ")";
     } else {
         text = "generic: table-interpreting kernel (the assembly is outside the BR2 fast-path pattern)";
     }

@@ -109,7 +109,7 @@ enum {
  * The BR2 assembly structure (every operator of SURVEY.md section 8a rows A5-A12) is served by a
  * specialised kernel that keeps per-slot descriptors in registers / shared memory instead of walking
  * the generic tables every step.  finalize() fills these when the assembly qualifies (fast_ok = 1):
- *   - forcing rows are gravity / twist / bend only, all with the same ramp_up_time;
+ *   - forcing rows are gravity / twist / bend (all with the same ramp_up_time) and point forces (tile kernel only);
  *   - rest_sigma and rest_kappa are zero;
  *   - every element is "rod two" of at most one surface joint and "rod one" of at most one (those
  *     contributions are gathered implicitly); at most BR2_FAST_MAX_EXTRA further joints (tip-to-base
@@ -177,7 +177,8 @@ typedef struct br2_program {
     int32_t fast_uniform;         /* 1: every element slot has identical fast_c constants (up to 1e-13
                                      relative; kernel then reads them from the constant bank) */
     int32_t n_act;                /* actuation rows */
-    int32_t reserved;
+    int32_t fast_point_forces;    /* 1: the forcing table holds BR2_FORCE_POINT rows (served by the tile kernel as extra
+                                     forces, or by the generic kernel; the one-slot-per-thread fast kernel refuses) */
     double act_ramp_up_time;
     const int32_t *fast_i;
     const double *fast_c;

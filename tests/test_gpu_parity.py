@@ -296,6 +296,8 @@ def test_optional_ops_point_force_and_last_end_fixed():
         return sim, rod
 
     sim, rod = build(BR2Simulator, CosseratRod, AnalyticalLinearDamper, PointForces, LastEndFixedRod, None)
+    assert sim.engine.kernel_info()["variant_name"] == "tile"  # point forces ride the tile kernel as extra forces
+    assert sim.kernel_plan() == "tile: 1 CTA(s) per instance of 11 threads (2 slots per thread), 1 tip-to-base joint(s) / point force(s)"
     do_step, stages = extend_stepper_interface(PositionVerlet(), sim)
     t = do_step(PositionVerlet(), stages, sim, 0.0, dt, n_steps=n_steps)
     osim, orod = build(br2_port.BR2Simulator, mini_elastica.CosseratRod, mini_elastica.AnalyticalLinearDamper,

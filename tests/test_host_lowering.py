@@ -204,16 +204,16 @@ def test_kernel_plan_of_the_baseline_assemblies(tmp_path):
     from br2 import _native
 
     assert _native.describe_plan(build_product("single", gravity=True)[1]) == \
-        "tile: 1 CTA(s) per instance of 63 threads (2 slots per thread), 0 tip-to-base joint(s)"
+        "tile: 1 CTA(s) per instance of 63 threads (2 slots per thread), 0 tip-to-base joint(s) / point force(s)"
     assert _native.describe_plan(build_product("double")[1]) == \
-        "tile: 1 CTA(s) per instance of 126 threads (2 slots per thread), 9 tip-to-base joint(s)"
+        "tile: 1 CTA(s) per instance of 126 threads (2 slots per thread), 9 tip-to-base joint(s) / point force(s)"
     assert _native.describe_plan(build_product("triple")[1]) == \
-        "tile: 1 CTA(s) per instance of 189 threads (2 slots per thread), 18 tip-to-base joint(s)"
+        "tile: 1 CTA(s) per instance of 189 threads (2 slots per thread), 18 tip-to-base joint(s) / point force(s)"
     # BASELINE config 4: 200 elements per rod -> one CTA per segment, a cluster of three
     assy = FreeAssembly(FakeEnv())
     assy.build(os.path.join(DATA, "rod_library_n200.json"), ASSEMBLY["triple"], verbose=False)
     assert _native.describe_plan(assy.simulator.lower()) == \
-        "tile: 3 CTA(s) per instance of 303, 303, 303 threads (2 slots per thread), 18 tip-to-base joint(s)"
+        "tile: 3 CTA(s) per instance of 303, 303, 303 threads (2 slots per thread), 18 tip-to-base joint(s) / point force(s)"
     # a segment too long for one CTA of the cluster kernel is refused with the reason
     library = json.load(open(os.path.join(DATA, "rod_library_n200.json")))
     library["DefaultParams"]["n_elements"] = 250
