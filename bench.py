@@ -33,6 +33,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "br2-simulator_b200"))
 os.environ.setdefault("NUMBA_CACHE_DIR", os.path.join(ROOT, ".numba_cache"))
 
+RESULT_OUT = sys.stdout
 DATA = os.path.join(ROOT, "tests", "data")
 ROD_DB = os.path.join(DATA, "rod_library.json")
 PSI = 6895.0
@@ -231,7 +232,7 @@ def run_reference_arm(args, world, rank):
         "e2e": {"value": value, "unit": "rod-element-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -388,10 +389,15 @@ def run_ours(args, world, rank, local):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_port(args.workload)
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
 def main():
+    # stdout carries the one JSON line and nothing else: libraries that write to file descriptor 1 (NCCL prints its
+    # version there when the box sets NCCL_DEBUG) are pointed at stderr for the whole run
+    global RESULT_OUT
+    RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse_args()
     world, rank, local = dist_setup(args)
     if args.impl == "reference":
