@@ -685,6 +685,7 @@ int br2_step(br2_handle h, int64_t n_steps, double t0, double dt, void *stream, 
     if (!h->state) return fail(BR2_ESTATE, "br2_step: no state bound (call br2_bind_state)");
     if (!h->pressures && h->t.n_actions > 0) return fail(BR2_ESTATE, "br2_step: no actuation set (call br2_set_actuation)");
     if (n_steps < 0 || !(dt > 0.0)) return fail(BR2_EINVAL, "br2_step: bad n_steps / dt");
+    if (n_steps > (1LL << 30)) return fail(BR2_EINVAL, "br2_step: more than 2^30 steps in one launch; split the call");
     volatile double time = t0;
     const double half = 0.5 * dt;
     for (int64_t i = 0; i < n_steps; ++i) {
