@@ -85,13 +85,16 @@ struct KernelChoice {
 #ifndef BR2_TILE_MB64
 #define BR2_TILE_MB64 6
 #endif
+#ifndef BR2_TILE_PARK
+#define BR2_TILE_PARK 0  // 1: the 64-thread tile kernel parks x and omega in tensor memory across P3 (measured: no gain)
+#endif
 #ifndef BR2_TILE_MIN_CHUNK_STEPS
 #define BR2_TILE_MIN_CHUNK_STEPS 125  // a launch is cut into at most BR2_MAX_CHUNKS chunks of at least this many steps
 #endif
 // variant 3: tile kernel (BR2_TILE_C slots per thread, uniform constants); `threads` = CTA size
 // template flags: <slots per thread, CTA threads, min CTAs per SM, extra joints, cluster>
 const KernelChoice kTileKernels[] = {  // single-segment assemblies (ring joints only)
-    {64, br2::br2_step_tile_kernel<BR2_TILE_C, 64, BR2_TILE_MB64, false, false, false>},
+    {64, br2::br2_step_tile_kernel<BR2_TILE_C, 64, BR2_TILE_MB64, false, false, false, BR2_TILE_PARK>},
     {128, br2::br2_step_tile_kernel<BR2_TILE_C, 128, 3, false, false, false>},
     {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, false, false, false>},
 };
@@ -603,6 +606,21 @@ int br2_select_kernel(br2_handle h, int32_t variant) {
         int blocks = 0, sms = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, (const void *)pick.fn, pick.threads, smem));
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+        if (BR2_TILE_PARK && pick.threads == 64) {
+            // the occupancy calculator answers 1 for a kernel that allocates tensor memory; the hardware co-schedules as
+            // many CTAs as registers, shared memory and the 512 tensor-memory columns allow (profiles/probes/tmem_scratch_probe.cu)
+            cudaFuncAttributes fa;
+            CUDA_TRY(cudaFuncGetAttributes(&fa, (const void *)pick.fn));
+            int regs_sm = 0, smem_sm = 0;
+            CUDA_TRY(cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, h->device));
+            CUDA_TRY(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device));
+            const int warp_regs = ((fa.numRegs + 7) / 8) * 8 * 32, warps_cta = pick.threads / 32;
+            const int by_regs = 4 * ((regs_sm / 4) / warp_regs) / warps_cta;  // the register file is split over four sub-partitions
+            const int by_smem = (int)((size_t)smem_sm / (smem + fa.sharedSizeBytes + 1024));
+            const int by_tmem = 512 / br2::kTileParkCols;
+            blocks = by_regs < by_smem ? by_regs : by_smem;
+            if (by_tmem < blocks) blocks = by_tmem;
+        }
         if (blocks < 1) return fail(BR2_ELIMIT, "the tile kernel does not fit on an SM");
         h->tile_capacity = blocks * sms;
     }
@@ -829,6 +847,7 @@ int br2_kernel_info(br2_handle h, int32_t *regs, int32_t *smem_bytes, int32_t *t
                                                            h->smem_bytes));
     int sms = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    if (h->variant == 3 && h->tile.n_ctas <= 1 && sms > 0) blocks = h->tile_capacity / sms;  // as launched (see br2_select_kernel)
     if (regs) *regs = attr.numRegs;
     if (smem_bytes) *smem_bytes = (int32_t)h->smem_bytes;
     if (threads) *threads = h->kernel.threads;

@@ -62,6 +62,24 @@ __device__ __forceinline__ T *tile_peer(T *local, int rank) {
     return local;
 }
 
+
+// Tensor memory as per-thread scratch (kPark kernels).  This kernel has no use for the tensor cores, so the SM's 256 KB of
+// tensor memory is idle; tcgen05.st / tcgen05.ld (32x32b shape: thread i of a warp <-> lane 32 * (warp % 4) + i, one
+// 32-bit column per register) move registers there and back without touching the shared-memory crossbar or the L1
+// (profiles/probes/tmem_scratch_probe.cu: 39-47 cycle round trip).  Values that only cross a phase are parked there so
+// that the phase in between has their registers for instruction-level parallelism.
+__device__ __forceinline__ void tmem_park(uint32_t addr, double v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(__double2loint(v)), "r"(__double2hiint(v)) : "memory");
+}
+__device__ __forceinline__ double tmem_fetch(uint32_t addr) {
+    int lo, hi;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(addr) : "memory");
+    return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+constexpr int kTileParkCols = 64;  // 32-bit columns per CTA (power of two >= 32): 32 doubles per thread
+
 // Where the per-thread constants live was measured (single_br2 x 4096, el-steps/s): joint direction vectors from the
 // constant bank indexed by rod 3.05e10, from a per-rod shared-memory table 2.96e10; actuation torques in shared-memory
 // rows 3.05e10, in registers 2.92e10 (every register kept across the step costs instruction-level parallelism).
@@ -120,9 +138,8 @@ struct TileSmem {
     static constexpr int QF = VF + 3 * R;         // [9][R]    director of the run's first element
     static constexpr int LF = QF + 9 * R;         // [R]       length of the run's first element
     static constexpr int SKL = LF + R;            // [3][R]    Q^T n_L / e of the run's last element
-    static constexpr int AL = SKL + 3 * R;        // [3][R]    tau_L / E^3 of the run's last Voronoi cell
-    static constexpr int CL = AL + 3 * R;         // [3][R]    (kappa x tau_L) D / E^3 of the run's last Voronoi cell
-    static constexpr int PC = CL + 3 * R;         // [C][3][R] x_k + x_{k+1} of each element (twice its centre)
+    static constexpr int ML = SKL + 3 * R;        // [3][R]    C/2 - A of the run's last Voronoi cell (A = tau_L / E^3, C = (kappa x tau_L) D / E^3)
+    static constexpr int PC = ML + 3 * R;         // [C][3][R] x_k + x_{k+1} of each element (twice its centre)
     static constexpr int PR = PC + 3 * C * R;     // [C][3][R] world-frame lever arm of the element as rod one
     static constexpr int PV = PR + 3 * C * R;     // [C][3][R] v_k + v_{k+1}
     static constexpr int PA = PV + 3 * C * R;     // [C][R]    arm length as rod one (radius + its share of the rest gap)
@@ -185,9 +202,9 @@ __device__ __forceinline__ TileWhere tile_where(const StepParams &p, int t, long
 // One PositionVerlet step of a thread's run.  kEnd: last step of a chunk (ends with a single kinematic half step
 // instead of the fused pair, so the state is a whole-step state); kLast: last step of the launch (also reports
 // the callback quantities).
-template <int C, int NT, bool kEnd, bool kLast, bool kExtras, bool kCluster, bool kExact>
+template <int C, int NT, bool kEnd, bool kLast, bool kExtras, bool kCluster, bool kExact, int kPark>
 __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileThread<C> &th, double time_mid, long long b,
-                                          int rank, int parity) {
+                                          int rank, int parity, uint32_t tm) {
     using L = TileSmem<C, NT>;
     constexpr int R = L::R;
     static_assert(kExtras || !kCluster, "the cluster kernels carry the extra-joint code (their barrier phases live in it)");
@@ -272,7 +289,10 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
             const double rad = r2 * M::rsqrt(r2);
             const double dil = len[j] * inv_rest_len;
             const double inv_dil = rest_len * inv_len;
-            const double rse = M::rsqrt_lo(dil);  // only thins the ~1e-8 m rest gap of a joint: 2^-20 relative is ample
+            // only thins the ~1e-8 m rest gap of a joint: 2^-20 relative is ample.  (1 / sqrt(e) is also radius x a constant;
+            // folding it into a per-rod arm factor saves the seed and two instructions per slot and was measured SLOWER,
+            // 3.12e10 against 3.17e10 el-steps/s: ptxas' schedule, not the instruction count, sets this kernel's pace.)
+            const double rse = M::rsqrt_lo(dil);
             ra2[j] = fma(JDV(3), rse, rad);
             if (kExtras) {
                 const int pub = (th.xinfo[j] & 0xFF) - 1;
@@ -325,6 +345,15 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 #pragma unroll
         for (int i = 0; i < 3; ++i) sm[L::SKL + i * R + t] = skp[i];
     }
+    if (kPark) {  // positions and angular velocities are not needed before P4: their registers serve P3
+#pragma unroll
+        for (int j = 0; j < C; ++j)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                tmem_park(tm + 2 * (3 * j + i), x[j][i]);
+                tmem_park(tm + 2 * (3 * C + 3 * j + i), w[j][i]);
+            }
+    }
     __syncthreads();  // B2
     // cluster: the other CTAs' rows are needed only by the tip-to-base joints at the end of P3 -- arrive now, wait there
     tile_cluster_arrive<kCluster>();
@@ -339,7 +368,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
             double Qn[9];
 #pragma unroll
             for (int i = 0; i < 9; ++i) Qn[i] = (j + 1 < C) ? Q[(j + 1) % C][i] : sm[L::QF + i * R + th.tn];
-            const double lenn = (j + 1 < C) ? len[(j + 1) % C] : sm[L::LF + th.tn];
+                        const double lenn = (j + 1 < C) ? len[(j + 1) % C] : sm[L::LF + th.tn];
             const double *q = Q[j];
             // antisymmetric part and trace of Qn Q^T
             const double w0 = fma(Qn[6], q[3], fma(Qn[7], q[4], fma(Qn[8], q[5], fma(-Qn[3], q[6], fma(-Qn[4], q[7], -Qn[5] * q[8])))));
@@ -374,10 +403,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
             }
         }
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            sm[L::AL + i * R + t] = ap[i];
-            sm[L::CL + i * R + t] = cp[i];
-        }
+        for (int i = 0; i < 3; ++i) sm[L::ML + i * R + t] = fma(0.5, cp[i], -ap[i]);
     }
     // own joints (Appendix A.7): my element is rod two; rod one's contribution comes from its published rows
 #pragma unroll
@@ -390,8 +416,14 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             rd2[i] = fma(Q[j][i], b0, Q[j][3 + i] * b1);  // Q^T dv2 (r + o)
-            const double xn = (j + 1 < C) ? x[(j + 1) % C][i] : sm[L::XF + i * R + th.tn];
-            cd2[i] = (xn + x[j][i]) - sm[L::PC + (3 * j + i) * R + th.t1];       // 2 (c2 - c1)
+            double xs;  // x_k + x_{k+1} of my element
+            if (kPark) {
+                xs = sm[L::PC + (3 * j + i) * R + t];
+            } else {
+                const double xn = (j + 1 < C) ? x[(j + 1) % C][i] : sm[L::XF + i * R + th.tn];
+                xs = xn + x[j][i];
+            }
+            cd2[i] = xs - sm[L::PC + (3 * j + i) * R + th.t1];       // 2 (c2 - c1)
             const double g = rd2[i] - sm[L::PR + (3 * j + i) * R + th.t1];
             // (c2 + rd2) - (c1 + rd1), rounded to 12 decimals like np.round_(x, 12)
             dvec[i] = rint(fma(0.5, cd2[i], g) * BR2_1E12) * BR2_1EM12;
@@ -466,6 +498,17 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 
     // =============================== P4: assemble, dynamic step ==============================
     {
+        if (kPark) {
+            tmem_wait_st();
+#pragma unroll
+            for (int j = 0; j < C; ++j)
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    x[j][i] = tmem_fetch(tm + 2 * (3 * j + i));
+                    w[j][i] = tmem_fetch(tm + 2 * (3 * C + 3 * j + i));
+                }
+            tmem_wait_ld();
+        }
         if (kLast) tile_cluster_wait<kCluster>();  // the reporting step gathers them early (external forces are reported)
         const double ramp_raw = time_mid * tb.act_inv_ramp;
         const double ramp = (ramp_raw < 1.0) ? ramp_raw : 1.0;
@@ -476,7 +519,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
             const double fp = sm[L::HF + (3 * (C - 1) + i) * R + top] - sm[L::HF + (3 * (C - 1) + i) * R + tprev];
             const double sp = sm[L::SKL + i * R + tprev];
             v[0][i] = fma(th.dtmc[0], fp - sp, v[0][i]);
-            tint[0][i] += fma(0.5, sm[L::CL + i * R + tprev], -sm[L::AL + i * R + tprev]);
+            tint[0][i] += sm[L::ML + i * R + tprev];
             if (kLast) {
                 r_fint[0][i] -= sp;
                 r_fext[0][i] += fp;
@@ -632,8 +675,9 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 #undef TAV
 }
 
-template <int C, int NT, int kMinBlocks, bool kExtras, bool kCluster, bool kExact>
+template <int C, int NT, int kMinBlocks, bool kExtras, bool kCluster, bool kExact, int kPark = 0>
 __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __grid_constant__ StepParams p) {
+    static_assert(!kPark || (NT <= 128 && !kExtras), "register parking: one lane per thread, no divergent joint code");
     using L = TileSmem<C, NT>;
     constexpr int R = L::R;
     extern __shared__ double sm[];
@@ -650,6 +694,18 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
     const long long total_items = p.batch * (long long)p.n_chunks;
     // exact-path pass: nothing to do unless the optimistic pass just before it flagged an instance
     if (kExact && *(volatile unsigned long long *)p.fail_counter == 0ULL) return;
+    __shared__ uint32_t s_tmem;
+    uint32_t tm = 0;
+    if (kPark) {  // this CTA's columns of tensor memory; my warp's lane quadrant
+        if (t < 32) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"l"((uint64_t)__cvta_generic_to_shared(&s_tmem)), "n"(kTileParkCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        tm = s_tmem + ((uint32_t)(32 * ((t >> 5) & 3)) << 16);
+    }
 
     // Persistent CTAs pull (chunk, instance) items off one queue, chunk-major: the launch is cut into n_chunks
     // runs of chunk_steps steps so that the last wave of instances does not leave most SMs idle (4096 instances
@@ -781,13 +837,13 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
             th.bad |= TileMath<kExact>::rotate(th.Q[j], th.w[j], hdt, hdt) ? 1 : 0;
         }
         for (int step = 0; step < n_steps - 1; ++step) {
-            tile_step<C, NT, false, false, kExtras, kCluster, kExact>(p, sm, th, time + hdt, b, rank, step & 1);
+            tile_step<C, NT, false, false, kExtras, kCluster, kExact, kPark>(p, sm, th, time + hdt, b, rank, step & 1, tm);
             time = (time + hdt) + hdt;
         }
         if (final_chunk)
-            tile_step<C, NT, true, true, kExtras, kCluster, kExact>(p, sm, th, time + hdt, b, rank, (n_steps - 1) & 1);
+            tile_step<C, NT, true, true, kExtras, kCluster, kExact, kPark>(p, sm, th, time + hdt, b, rank, (n_steps - 1) & 1, tm);
         else
-            tile_step<C, NT, true, false, kExtras, kCluster, kExact>(p, sm, th, time + hdt, b, rank, (n_steps - 1) & 1);
+            tile_step<C, NT, true, false, kExtras, kCluster, kExact, kPark>(p, sm, th, time + hdt, b, rank, (n_steps - 1) & 1, tm);
 
         // a CTA that left the series' validity range keeps the chunk-start state and asks for the exact path, which
         // resumes this instance from the start of this chunk (status = 1 + chunk, reason bits from bit 8 up)
@@ -841,6 +897,10 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
             }
             *(volatile int *)(p.progress + b) = chunk + 1;
         }
+    }
+    if (kPark) {
+        __syncthreads();
+        if (t < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "n"(kTileParkCols));
     }
 }
 
