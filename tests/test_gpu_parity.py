@@ -601,3 +601,70 @@ def test_benchmark_workload_never_leaves_the_fast_path():
     assert env.engine.kernel_info()["variant_name"] == "tile"
     assert env.engine.replay_count() == 0
     env.close()
+
+
+@pytest.mark.gpu
+def test_cuda_path_reproduces_the_surveys_independent_probe_anchors():
+    """RodBend tip after 5000 / 10000 steps of single_br2 (gravity, 30 psi on action1 and action2),
+    from the survey's own mimic of the reference -- independent of this repository's oracle (see tests/test_oracle_fused.py)."""
+    from br2.environment import Environment
+
+    env = Environment(run_tag="anchors", create_dirs=False)
+    env.reset(rod_database_path=ROD_DB, assembly_config_path=ASSEMBLY["single"], gravity=True)
+    env.simulator._callback_ops = []
+    action = {"action1": 30 * PSI, "action2": 30 * PSI}
+    for n_steps, tip in ((5000, (-0.00470, 0.17958, 0.00057)), (10000, (-0.01113, 0.17870, 0.00216))):
+        env.run(action=action, duration=5000 * env.time_step - 0.5 * env.time_step, disable_progress_bar=True)
+        assert round(env.time / env.time_step) == n_steps
+        got = env.simulator[0].position_collection[:, -1]
+        assert np.abs(got - np.array(tip)).max() < 6e-6, (n_steps, got)
+    env.close()
+
+
+def _ragged_inputs(tmp_path):
+    """A double assembly whose second segment uses shorter rods with fewer elements (30 on 0.12 m against 41 on 0.18 m):
+    SURVEY.md section 8(f) row 4, per-rod heterogeneous n_elements across segments."""
+    import json
+
+    library = json.load(open(ROD_DB))
+    for key in ("RodBend", "RodRightTwist", "RodLeftTwist"):
+        library["Rods"][key + "Short"] = dict(library["Rods"][key], n_elements=30, base_length=0.12)
+    assembly = json.load(open(ASSEMBLY["double"]))
+    assembly["Segments"]["seg2"]["rod_order"] = ["RodRightTwistShort", "RodBendShort", "RodLeftTwistShort"]
+    rod_db, path = tmp_path / "rod_library_ragged.json", tmp_path / "assembly_ragged.json"
+    rod_db.write_text(json.dumps(library))
+    path.write_text(json.dumps(assembly))
+    return str(rod_db), str(path)
+
+
+@pytest.mark.parametrize("variant", ["generic", "fast"])
+def test_ragged_assembly_with_an_odd_batch_matches_oracle(tmp_path, variant):
+    from br2.environment import Environment
+    from oracle import br2_port
+    from oracle.fused import FusedOracle
+
+    rod_db, assembly = _ragged_inputs(tmp_path)
+    batch, n_steps, dt = 37, 3000, 2.0e-5
+    pressures = np.random.default_rng(11).uniform(0.0, 40.0, size=(3, batch)) * PSI
+    env = Environment("ragged", batch=batch, create_dirs=False)
+    env.reset(rod_db, assembly, gravity=True)
+    assert [rod.n_elems for rod in env.simulator] == [41, 41, 41, 30, 30, 30]
+    assert env.engine.kernel_info()["variant_name"] == "fast"  # per-slot constants: the tile kernel wants uniform ones
+    env.engine.select_kernel(VARIANTS[variant])
+    env.simulator._callback_ops = []
+    status = env.run({name: pressures[i] for i, name in enumerate(NAMES)}, duration=n_steps * dt - 0.5 * dt,
+                     disable_progress_bar=True, check_nan=True)
+    assert round(env.time / dt) == n_steps and not status.position_nan_status
+
+    ref = br2_port.OracleEnvironment(time_step=dt)
+    ref.reset(rod_db, assembly, gravity=True)
+    fused = FusedOracle.from_simulator(ref.simulator, NAMES)
+    W = fused.pack(batch)
+    fused.run(W, pressures, n_steps, 0.0, dt)
+    x_scale = max(np.abs(fused.view(W, r, "x")).max() for r in range(6))
+    for r, rod in enumerate(env.simulator):
+        assert np.abs(rod.position_collection - fused.view(W, r, "x")).max() <= POS_TOL * x_scale
+        assert np.abs(rod.director_collection - fused.view(W, r, "Q")).max() <= DIR_TOL
+    tips = env.simulator[3].position_collection[:, 1, -1]
+    assert 0.25 < tips.mean() < 0.31 and tips.std() > 1e-5  # second segment sits on top of the first; instances differ
+    env.close()

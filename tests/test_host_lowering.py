@@ -223,3 +223,24 @@ def test_kernel_plan_of_the_baseline_assemblies(tmp_path):
     assy.build(str(path), ASSEMBLY["triple"], verbose=False)
     with pytest.raises(_native.Br2Error, match="needs 378 threads"):
         _native.describe_plan(assy.simulator.lower())
+
+
+def test_ragged_assembly_lowers_to_the_per_slot_constant_kernel(tmp_path):
+    """Segments whose rods differ in element count and length: rest lengths are no longer
+    uniform, so the tile kernel declines and the one-slot-per-thread kernel with per-slot constants takes the assembly."""
+    from br2 import _native
+
+    library = json.load(open(ROD_DB))
+    for key in ("RodBend", "RodRightTwist", "RodLeftTwist"):
+        library["Rods"][key + "Short"] = dict(library["Rods"][key], n_elements=30, base_length=0.12)
+    assembly = json.load(open(ASSEMBLY["double"]))
+    assembly["Segments"]["seg2"]["rod_order"] = ["RodRightTwistShort", "RodBendShort", "RodLeftTwistShort"]
+    rod_db, path = tmp_path / "rod_library_ragged.json", tmp_path / "assembly_ragged.json"
+    rod_db.write_text(json.dumps(library))
+    path.write_text(json.dumps(assembly))
+    assy = FreeAssembly(FakeEnv())
+    assy.build(str(rod_db), str(path), verbose=False)
+    program = assy.simulator.lower()
+    assert program.n_slots == 3 * 42 + 3 * 31 and program.fast["ok"] and not program.fast["uniform"]
+    assert _native.describe_plan(program) == \
+        "fast: one slot per thread (tile kernel refused: assembly constants are not uniform)"

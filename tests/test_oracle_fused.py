@@ -112,3 +112,24 @@ def test_fused_c_matches_faithful_to_noise_floor(assembly, kwargs, action, n_ste
             assert err <= 1e-10, (r, short, err)
         elif short in ("len", "rad", "dil"):
             assert err / np.abs(want).max() <= 1e-11, (r, short, err)
+
+
+# tip of RodBend after 5000 / 10000 steps of single_br2 (gravity on, action1 = action2 = 30 psi,
+# dt = 2e-5), measured by the survey's own throw-away mimic of the reference -- an implementation independent of this
+# repository's oracle.  Not a golden vector of the reference (it ships none), but a second opinion: five digits agree.
+SURVEY_ANCHORS = ((5000, (-0.00470, 0.17958, 0.00057)), (10000, (-0.01113, 0.17870, 0.00216)))
+
+
+def test_oracle_reproduces_the_surveys_independent_probe_anchors():
+    ref = br2_port.OracleEnvironment()
+    ref.reset(ROD_DB, os.path.join(DATA, "assembly_single.json"), gravity=True)
+    fused = FusedOracle.from_simulator(ref.simulator, NAMES)
+    W = fused.pack(1)
+    P = np.array([[30 * PSI], [30 * PSI], [0.0]])
+    done = 0
+    for n_steps, tip in SURVEY_ANCHORS:
+        fused.run(W, P, n_steps - done, done * 2.0e-5, 2.0e-5)
+        done = n_steps
+        got = fused.view(W, 0, "x")[0][:, -1]
+        assert np.abs(got - np.array(tip)).max() < 6e-6, (n_steps, got)  # the anchors are quoted to 1e-5 m
+    assert float(np.abs(fused.view(W, 0, "v")).max()) < 0.12  # "max |v| ~ 6e-2 m/s"
