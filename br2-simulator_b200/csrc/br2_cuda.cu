@@ -390,18 +390,21 @@ bool make_tile_plan(const br2_program *p, int C, br2::TilePlan *plan, TileExtraT
         const int t = thread_of((int)sl, &j);
         xt->xi[(size_t)t * XN + BR2_TILE_XI_OW(C, j)] = xe_id(p->overwrite_src[sl]);
     }
-    // the extra joints are evaluated by the CTA of their rod-two element, by consecutive threads of its LAST warps: a
-    // warp executes the joint code once whichever of its lanes take part, so packing them keeps the other warps' issue
-    // slots free (the CTA waits for the slowest warp at the next barrier either way)
+    // the extra joints are evaluated by the CTA of their rod-two element, one COMPONENT per thread, by consecutive threads
+    // of its LAST warps: a warp executes the joint code once whichever of its lanes take part, so packing them keeps the
+    // other warps' issue slots free, and the CTA waits at the next barrier for one component's chain of loads only
     {
         int used[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int xj = 0; xj < plan->n_xj; ++xj) {
             const int rank = xt->xj_i[(size_t)xj * 12 + 3];
             const int ct = plan->cta_threads[rank], warps = (ct + 31) / 32;
-            const int k = used[rank]++;                       // k-th joint of this CTA
-            const int t = (warps - 1 - k / 32) * 32 + k % 32;  // lanes 0.. of the last warp, then the one before, ...
-            if (t < 0) return *why = "more extra joints than threads", false;
-            xt->xi[(size_t)(rank * plan->xi_stride + t) * XN + BR2_TILE_XI_JOINT] = xj;
+            const int last = ct - (warps - 1) * 32;  // threads in use in the last warp
+            for (int comp = 0; comp < 3; ++comp) {
+                const int k = used[rank]++;  // k-th (joint, component) of this CTA: lanes 0.. of the last warp, then the one before, ...
+                const int t = (k < last) ? (warps - 1) * 32 + k : (warps - 2 - (k - last) / 32) * 32 + (k - last) % 32;
+                if (t < 0) return *why = "more extra joint components than threads", false;
+                xt->xi[(size_t)(rank * plan->xi_stride + t) * XN + BR2_TILE_XI_JOINT] = (xj << 2) | comp;
+            }
         }
     }
     // pack: one int per slot + the joint id per thread; node items in one compact array

@@ -164,7 +164,7 @@ struct TileThread {
     int t, tn, t1, to;  // rows: own, next run (or own), partner as rod one of my joints (or 0), owner of the joints in which I am rod one (or 0)
     int rod;
     // extra joints (kExtras kernels): per slot published xe + 1 | overwrite source xe + 1 << 8 | node items << 16 |
-    // first item << 20; the extra joint this thread evaluates or -1
+    // first item << 20; the extra joint component this thread evaluates (joint << 2 | component) or -1
     int xinfo[C], xjoint;
     int bad;  // bit 0: rotation angle, bit 1: curvature angle, bit 2: strain left its series' range (or NaN)
 };
@@ -466,29 +466,27 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
     // surfaces along fixed material directions, un-projected damping, no torque
     tile_cluster_wait<kCluster>();
     if (kExtras && th.xjoint >= 0) {
-        const int xj = th.xjoint;
+        // one COMPONENT of one joint per thread (three consecutive lanes per joint): the warp that holds them is late at
+        // the next barrier by one component's chain of loads, not three
+        const int xj = th.xjoint >> 2, i = th.xjoint & 3;
         {
             const int *ji = XJI + xj * 12;
             const double *jd = XJD + xj * 8;
             if (ji[10] == 1) {
                 // point force (custom_activation.PointForces): F min(1, t / ramp_up_time) on one node
                 const double fac = fmin(1.0, time_mid / jd[3]);
-#pragma unroll
-                for (int i = 0; i < 3; ++i) JF[i * n_xj + xj] = jd[i] * fac;
+                JF[i * n_xj + xj] = jd[i] * fac;
             } else {
                 const double *const sm1 = tile_peer<kCluster>(sm, ji[0]), *const sm2 = tile_peer<kCluster>(sm, ji[3]);
                 const int row1 = ji[1] + 1, j1 = ji[2], row2 = ji[4] + 1, j2 = ji[5], q1 = ji[6], q2 = ji[7];
                 const double kj = jd[0], nuj = jd[1];
                 const double r1 = EXR[ji[8]], r2 = EXR[ji[9]];
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const double c1 = 0.5 * sm1[L::PC + (3 * j1 + i) * R + row1], c2 = 0.5 * sm2[L::PC + (3 * j2 + i) * R + row2];
-                    const double vrel = 0.5 * sm2[L::PV + (3 * j2 + i) * R + row2] - 0.5 * sm1[L::PV + (3 * j1 + i) * R + row1];
-                    const double a1 = fma(EXQ[i * n_xe + q1], jd[2], fma(EXQ[(3 + i) * n_xe + q1], jd[3], EXQ[(6 + i) * n_xe + q1] * jd[4])) * r1;
-                    const double a2 = fma(EXQ[i * n_xe + q2], jd[5], fma(EXQ[(3 + i) * n_xe + q2], jd[6], EXQ[(6 + i) * n_xe + q2] * jd[7])) * r2;
-                    const double gap = (c2 + a2) - (c1 + a1);
-                    JF[i * n_xj + xj] = 0.5 * fma(kj, gap, -nuj * vrel);
-                }
+                const double c1 = 0.5 * sm1[L::PC + (3 * j1 + i) * R + row1], c2 = 0.5 * sm2[L::PC + (3 * j2 + i) * R + row2];
+                const double vrel = 0.5 * sm2[L::PV + (3 * j2 + i) * R + row2] - 0.5 * sm1[L::PV + (3 * j1 + i) * R + row1];
+                const double a1 = fma(EXQ[i * n_xe + q1], jd[2], fma(EXQ[(3 + i) * n_xe + q1], jd[3], EXQ[(6 + i) * n_xe + q1] * jd[4])) * r1;
+                const double a2 = fma(EXQ[i * n_xe + q2], jd[5], fma(EXQ[(3 + i) * n_xe + q2], jd[6], EXQ[(6 + i) * n_xe + q2] * jd[7])) * r2;
+                const double gap = (c2 + a2) - (c1 + a1);
+                JF[i * n_xj + xj] = 0.5 * fma(kj, gap, -nuj * vrel);
             }
         }
     }
