@@ -93,8 +93,14 @@ struct KernelChoice {
 #endif
 // variant 3: tile kernel (BR2_TILE_C slots per thread, uniform constants); `threads` = CTA size
 // template flags: <slots per thread, CTA threads, min CTAs per SM, extra joints, cluster>
+// the 128-register kernel: eight 64-thread CTAs per SM, state parked in tensor memory between phases, lean shared-memory
+// layout (needs an idle thread in the CTA)
+#ifndef BR2_TILE_LEAN_MB
+#define BR2_TILE_LEAN_MB 8
+#endif
+const KernelChoice kTileLeanKernel = {64, br2::br2_step_tile_kernel<BR2_TILE_C, 64, BR2_TILE_LEAN_MB, false, false, false, 2>};
 const KernelChoice kTileKernels[] = {  // single-segment assemblies (ring joints only)
-    {64, br2::br2_step_tile_kernel<BR2_TILE_C, 64, BR2_TILE_MB64, false, false, false, BR2_TILE_PARK>},
+    {64, br2::br2_step_tile_kernel<BR2_TILE_C, 64, BR2_TILE_MB64, false, false, false, BR2_TILE_PARK == 2 ? 0 : BR2_TILE_PARK>},
     {128, br2::br2_step_tile_kernel<BR2_TILE_C, 128, 3, false, false, false>},
     {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, false, false, false>},
 };
@@ -557,6 +563,7 @@ int br2_select_kernel(br2_handle h, int32_t variant) {
                     pick = kc;
                     break;
                 }
+            if (BR2_TILE_PARK == 2 && need < kTileLeanKernel.threads && !getenv("BR2_TILE_NO_LEAN")) pick = kTileLeanKernel;
         }
     } else {
         for (const KernelChoice &kc : kKernels[variant])
@@ -569,6 +576,8 @@ int br2_select_kernel(br2_handle h, int32_t variant) {
     size_t smem;
     if (variant == 0)
         smem = sizeof(double) * (30 * S + 9 * (size_t)h->t.n_joints + 32);
+    else if (variant == 3 && pick.fn == kTileLeanKernel.fn)
+        smem = sizeof(double) * (size_t)br2::TileSmem<BR2_TILE_C, 1, true>::ROWS_END * (size_t)pick.threads;  // (NT = 1: rows per thread)
     else if (variant == 3)
         smem = sizeof(double) * ((size_t)br2::TileSmem<BR2_TILE_C, 0>::ROWS_END * (size_t)(pick.threads + 1) +
                                  25 * (size_t)h->tile.n_xe + (3 + 8 + 6) * (size_t)h->tile.n_xj +
@@ -609,7 +618,7 @@ int br2_select_kernel(br2_handle h, int32_t variant) {
         int blocks = 0, sms = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, (const void *)pick.fn, pick.threads, smem));
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
-        if (BR2_TILE_PARK && pick.threads == 64) {
+        if ((BR2_TILE_PARK && pick.threads == 64) || pick.fn == kTileLeanKernel.fn) {
             // the occupancy calculator answers 1 for a kernel that allocates tensor memory; the hardware co-schedules as
             // many CTAs as registers, shared memory and the 512 tensor-memory columns allow (profiles/probes/tmem_scratch_probe.cu)
             cudaFuncAttributes fa;
@@ -725,6 +734,19 @@ int br2_step(br2_handle h, int64_t n_steps, double t0, double dt, void *stream, 
     sp.t0 = t0;
     sp.dt = dt;
     memcpy(sp.uni, h->uni, sizeof(sp.uni));
+    {
+        const double *u = h->uni;
+        for (int i = 0; i < 3; ++i) {
+            sp.kd[i] = dt * u[BR2_FC_CT] * u[BR2_FC_GRAVITY + i];
+            sp.kd[8 + i] = dt * u[BR2_FC_JINV + i];
+        }
+        sp.kd[3] = 0.5 * u[BR2_FC_INV_REST_VLEN];
+        sp.kd[4] = -0.5 * u[BR2_FC_INV_REST_VLEN];
+        sp.kd[5] = -0.25 * u[BR2_FC_JNU];
+        sp.kd[6] = 0.5 * u[BR2_FC_JK];
+        sp.kd[7] = -0.5 * u[BR2_FC_JKREP];
+        sp.kd[11] = 0.5 * dt;
+    }
     sp.tile = h->tile;
     sp.status = h->status;
     sp.replays = h->replays;

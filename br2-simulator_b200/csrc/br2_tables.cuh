@@ -74,6 +74,7 @@ struct StepParams {
     int only_flagged;   // generic kernel: integrate only instances whose status is set, then clear it
     unsigned long long *replays;  // counts instance-launches redone by the exact path
     double uni[BR2_FC_COUNT];  // uniform copy of fast_c (all element slots identical), constant bank
+    double kd[12];             // loop-invariant products of uni and dt for the 128-register tile kernel (br2_step fills them)
     TilePlan tile;
     // launch chunking (tile kernel's work queue; the exact-path replay resumes at the chunk that failed:
     // status = 1 + chunk).  One chunk = the whole launch for the other kernels.

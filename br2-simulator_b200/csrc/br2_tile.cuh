@@ -79,6 +79,9 @@ __device__ __forceinline__ double tmem_fetch(uint32_t addr) {
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 constexpr int kTileParkCols = 64;  // 32-bit columns per CTA (power of two >= 32): 32 doubles per thread
+// kPark == 2 (C = 2): which double lives where.  x[0] and Q[0] are not parked: their published rows (XF, QF) are the copy.
+constexpr int kPkX1 = 0, kPkV = 3, kPkW = 9, kPkQ1 = 15, kPkTA = 24;  // x[1] 3 | v 6 | w 6 | Q[1] 9 | actuation torque 6 = 30
+#define TM_AT(idx) (tm + 2 * (idx))
 
 // Where the per-thread constants live was measured (single_br2 x 4096, el-steps/s): joint direction vectors from the
 // constant bank indexed by rod 3.05e10, from a per-rod shared-memory table 2.96e10; actuation torques in shared-memory
@@ -126,13 +129,16 @@ struct TileMath {
     }
 };
 
-template <int C, int NT>
+template <int C, int NT, bool kLean = false>
 struct TileSmem {
     // rows of every exchange array: thread t owns row t + 1; row 0 is all zeros and never written.  A run without a
     // predecessor reads row (own - 1): row 0, or the previous rod's last run, whose "last element" entries are zero because
     // its last slot is the node-only slot.  A run without a successor reads its own row (the result is masked).  Both
     // keep a half-warp's addresses contiguous, i.e. free of bank conflicts.
-    static constexpr int R = NT + 1;
+    // kLean (the 128-register kernel, eight CTAs per SM): NT rows -- the CTA's idle threads (at least one: plan requirement)
+    // take row 0 as their own, where their all-zero state publishes zeros in every array whose row 0 is read as "nothing
+    // there" -- and no actuation rows (tensor memory holds them).
+    static constexpr int R = kLean ? NT : NT + 1;
     static constexpr int XF = 0;                  // [3][R]    position of the run's first node
     static constexpr int VF = XF + 3 * R;         // [3][R]    velocity of the run's first node
     static constexpr int QF = VF + 3 * R;         // [9][R]    director of the run's first element
@@ -147,7 +153,7 @@ struct TileSmem {
     static constexpr int FS = HF + 3 * C * R;     // [C][3][R] spring part k d of that joint (the torques use only this)
     static constexpr int ZERO_END = FS + 3 * C * R;  // everything above is zeroed at launch
     static constexpr int TA = ZERO_END;           // [C][3][R] actuation torque at full ramp (material frame)
-    static constexpr int ROWS_END = TA + 3 * C * R;
+    static constexpr int ROWS_END = kLean ? TA : TA + 3 * C * R;
     // after the rows (host: TileSmem<C, 0>::ROWS_END * (threads + 1) words), the extra-joint area
     static constexpr int EX = ROWS_END;           // extra joints (rank 0's copy is the live one in a cluster):
                                                   // EXQ [2][9][n_xe], EXW [2][3][n_xe] (by step parity), EXR [n_xe], JF [3][n_xj]
@@ -205,20 +211,23 @@ __device__ __forceinline__ TileWhere tile_where(const StepParams &p, int t, long
 template <int C, int NT, bool kEnd, bool kLast, bool kExtras, bool kCluster, bool kExact, int kPark>
 __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileThread<C> &th, double time_mid, long long b,
                                           int rank, int parity, uint32_t tm) {
-    using L = TileSmem<C, NT>;
+    using L = TileSmem<C, NT, kPark == 2>;
     constexpr int R = L::R;
     static_assert(kExtras || !kCluster, "the cluster kernels carry the extra-joint code (their barrier phases live in it)");
     using M = TileMath<kExact>;
     const DevTables &tb = p.t;
     const int t = th.t;
-    const double dt = p.dt, hdt = 0.5 * p.dt;
+    const double dt = p.dt, hdt = (kPark == 2) ? p.kd[11] : 0.5 * p.dt;
+    // kPark == 2 runs at 128 registers: loop-invariant products come from the constant bank (StepParams::kd, filled by
+    // br2_step with the very same expressions) instead of being hoisted into registers that then spill
+#define KD(idx, expr) ((kPark == 2) ? p.kd[(idx)] : (expr))
     TileWhere wh{};
-    if (kLast) wh = tile_where<C>(p, t - 1, b, rank);
+    if (kLast) wh = tile_where<C>(p, (int)threadIdx.x, b, rank);
     const int n = wh.n, np1 = wh.n + 1;
     double *const inst = wh.inst;
 #define UNI(idx) p.uni[(idx)]
 #define JDV(i) p.tile.jd[th.rod][(i)]
-#define TAV(j, i) sm[L::TA + (3 * (j) + (i)) * R + t]
+#define TAV(j, i) sm[L::TA + (3 * (j) + (i)) * (kPark == 2 ? 0 : R) + t]  // (kPark == 2: unused, tensor memory holds it)
     double (&x)[C][3] = th.x;
     double (&v)[C][3] = th.v;
     double (&Q)[C][9] = th.Q;
@@ -263,8 +272,8 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
     double len[C], ra2[C];
     double tint[C][3];   // internal couple on element k (complete except for the previous run's last cell)
     {
-        const double dtg[3] = {dt * UNI(BR2_FC_CT) * UNI(BR2_FC_GRAVITY), dt * UNI(BR2_FC_CT) * UNI(BR2_FC_GRAVITY + 1),
-                               dt * UNI(BR2_FC_CT) * UNI(BR2_FC_GRAVITY + 2)};
+        const double dtg[3] = {KD(0, dt * UNI(BR2_FC_CT) * UNI(BR2_FC_GRAVITY)), KD(1, dt * UNI(BR2_FC_CT) * UNI(BR2_FC_GRAVITY + 1)),
+                               KD(2, dt * UNI(BR2_FC_CT) * UNI(BR2_FC_GRAVITY + 2))};
         double skp[3];  // the previous element's Q^T n_L / e
 #pragma unroll
         for (int j = 0; j < C; ++j) {
@@ -340,12 +349,30 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 #pragma unroll
             for (int i = 0; i < 3; ++i)
                 sm[L::PR + (3 * j + i) * R + t] = fma(Q[j][i], a0, Q[j][3 + i] * a1);  // Q^T dv1 (r + o)
+            if (kPark == 2) {
+                // done with this slot until P4: its velocity and angular velocity go to tensor memory; slot 0 makes room for
+                // slot 1's director (parked since the end of the previous step) -- Q[0] comes back from its published row in P3
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    tmem_park(TM_AT(kPkV + 3 * j + i), v[j][i]);
+                    tmem_park(TM_AT(kPkW + 3 * j + i), w[j][i]);
+                }
+                if (j == 0) {
+                    tmem_wait_st();
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) Q[1][i] = tmem_fetch(TM_AT(kPkQ1 + i));
+                    tmem_wait_ld();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) tmem_park(TM_AT(kPkX1 + i), x[1][i]);
+                }
+            }
         }
         sm[L::LF + t] = len[0];
 #pragma unroll
         for (int i = 0; i < 3; ++i) sm[L::SKL + i * R + t] = skp[i];
     }
-    if (kPark) {  // positions and angular velocities are not needed before P4: their registers serve P3
+    if (kPark == 1) {  // positions and angular velocities are not needed before P4: their registers serve P3
 #pragma unroll
         for (int j = 0; j < C; ++j)
 #pragma unroll
@@ -360,6 +387,10 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 
     // =============================== P3: Voronoi couples and own joints ======================
     double tw[C][3];  // world-frame joint torque on my element (own joint now, rod-one joint in P4)
+    if (kPark == 2) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Q[0][i] = sm[L::QF + i * R + t];  // my own published row
+    }
     {
         double ap[3], cp[3];  // previous cell's A and C
 #pragma unroll
@@ -379,9 +410,9 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
             // y = 1 - cos(theta) with the reference's -1e-10 guard; a benign value off the rod
             const double y = vor ? fma(-0.5, tr, kMisc[7]) : kMisc2[3];
             if (!kExact) th.bad |= (y <= BR2_Y_MAX && y > 0.0) ? 0 : 2;
-            const double ksr = M::logmap_ratio(y) * (-0.5 * UNI(BR2_FC_INV_REST_VLEN));
+            const double ksr = M::logmap_ratio(y) * KD(4, -0.5 * UNI(BR2_FC_INV_REST_VLEN));
             const double ks = vor ? ksr : 0.0;
-            const double vdil = (lenn + len[j]) * (0.5 * UNI(BR2_FC_INV_REST_VLEN));
+            const double vdil = (lenn + len[j]) * KD(3, 0.5 * UNI(BR2_FC_INV_REST_VLEN));
             const double iv = M::rcp(vdil);
             // A = B kappa / E^3 and C = (kappa x B kappa) D / E^3 = (kappa x A) D with kappa = ks w
             const double s3 = ks * (iv * iv * iv), cs = ks * UNI(BR2_FC_REST_VLEN);
@@ -434,12 +465,12 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
         // F = k d - nu (v_rel . d_hat) d_hat = (k - nu (v_rel . d) / |d|^2) d ; no damping below |d| = 1e-12
         const double inv_d2 = (dist2 >= BR2_1EM24) ? M::rcp_lo(dist2) : 0.0;  // damping term ~1e-8 N: seed accuracy is ample
         const double jk = UNI(BR2_FC_JK);
-        const double hcoef = fma((-0.25 * UNI(BR2_FC_JNU)) * proj2, inv_d2, 0.5 * jk);  // half of the bracket
+        const double hcoef = fma(KD(5, -0.25 * UNI(BR2_FC_JNU)) * proj2, inv_d2, KD(6, 0.5 * jk));  // half of the bracket
         // Hertz-like repulsion when the surfaces interpenetrate: -k_rep pen^1.5 along the centre line
         const double cn2 = fma(cd2[0], cd2[0], fma(cd2[1], cd2[1], cd2[2] * cd2[2])) + BR2_TINY;  // 4 |cd|^2
         const double rcn = M::rsqrt(cn2);                                 // 1 / (2 |cd|)
         const double pen = fmax(fma(-0.5 * cn2, rcn, ra1 + ra2[j]), 0.0);     // max(r1 + r2 - |cd|, 0)
-        const double hmag = (-0.5 * UNI(BR2_FC_JKREP)) * (pen * M::sqrt_lo(pen)) * rcn;  // times cd2 = half the repulsion
+        const double hmag = KD(7, -0.5 * UNI(BR2_FC_JKREP)) * (pen * M::sqrt_lo(pen)) * rcn;  // times cd2 = half the repulsion
         double fs[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
@@ -450,8 +481,10 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
             sm[L::FS + (3 * j + i) * R + t] = fs[i];
             // rod two takes -F: half on each node of the element (node k+1 of the run's last element belongs
             // to the next thread, which reads HF)
-            v[j][i] = fma(-th.dtmc[j], hf, v[j][i]);
-            if (j + 1 < C) v[(j + 1) % C][i] = fma(-th.dtmc[(j + 1) % C], hf, v[(j + 1) % C][i]);
+            if (kPark != 2) {  // (kPark == 2: the velocities are parked; P4 applies this force from the HF row)
+                v[j][i] = fma(-th.dtmc[j], hf, v[j][i]);
+                if (j + 1 < C) v[(j + 1) % C][i] = fma(-th.dtmc[(j + 1) % C], hf, v[(j + 1) % C][i]);
+            }
             if (kLast) {
                 r_fext[j][i] = (j == 0) ? -hf : r_fext[j][i] - hf;
                 if (j + 1 < C) r_fext[(j + 1) % C][i] = -hf;
@@ -496,7 +529,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 
     // =============================== P4: assemble, dynamic step ==============================
     {
-        if (kPark) {
+        if (kPark == 1) {
             tmem_wait_st();
 #pragma unroll
             for (int j = 0; j < C; ++j)
@@ -507,11 +540,35 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
                 }
             tmem_wait_ld();
         }
+        if (kPark == 2) {
+            tmem_wait_st();
+#pragma unroll
+            for (int j = 0; j < C; ++j)
+#pragma unroll
+                for (int i = 0; i < 3; ++i) v[j][i] = tmem_fetch(TM_AT(kPkV + 3 * j + i));
+            if (kLast) {  // the reporting step reads positions (soft-fix spring)
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    x[1][i] = tmem_fetch(TM_AT(kPkX1 + i));
+                    x[0][i] = sm[L::XF + i * R + t];
+                }
+            }
+            tmem_wait_ld();
+            // the force of the joints I own (rod two takes -F, half on each node of the element), deferred from P3
+#pragma unroll
+            for (int j = 0; j < C; ++j)
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const double hf = sm[L::HF + (3 * j + i) * R + t];
+                    v[j][i] = fma(-th.dtmc[j], hf, v[j][i]);
+                    if (j + 1 < C) v[(j + 1) % C][i] = fma(-th.dtmc[(j + 1) % C], hf, v[(j + 1) % C][i]);
+                }
+        }
         if (kLast) tile_cluster_wait<kCluster>();  // the reporting step gathers them early (external forces are reported)
         const double ramp_raw = time_mid * tb.act_inv_ramp;
         const double ramp = (ramp_raw < 1.0) ? ramp_raw : 1.0;
         // what the previous run's last element contributes to my first node / element (rows: see TileSmem)
-        const int tprev = t - 1, top = (th.to > 0) ? th.to - 1 : 0;
+        const int tprev = (kPark == 2) ? max(t - 1, 0) : t - 1, top = (th.to > 0) ? th.to - 1 : 0;  // (an idle thread of the lean layout sits in row 0)
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const double fp = sm[L::HF + (3 * (C - 1) + i) * R + top] - sm[L::HF + (3 * (C - 1) + i) * R + tprev];
@@ -527,6 +584,15 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
         for (int j = 0; j < C; ++j) {
             const int k = wh.k0 + j;
             double text[3];
+            double ta[3];
+            if (kPark == 2) {  // (fetching everything at the start of P4, or earlier than needed anywhere, was measured: the longer
+                               // live ranges spill, 2.94e10 against 3.00e10 el-steps/s)
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    w[j][i] = tmem_fetch(TM_AT(kPkW + 3 * j + i));
+                    ta[i] = tmem_fetch(TM_AT(kPkTA + 3 * j + i));
+                }
+            }
             {
                 double fso[3], rd1[3];
 #pragma unroll
@@ -549,7 +615,10 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
             }
 #pragma unroll
             for (int i = 0; i < 3; ++i)
-                text[i] = fma(TAV(j, i), ramp, fma(Q[j][3 * i], tw[j][0], fma(Q[j][3 * i + 1], tw[j][1], Q[j][3 * i + 2] * tw[j][2])));
+                text[i] = fma(Q[j][3 * i], tw[j][0], fma(Q[j][3 * i + 1], tw[j][1], Q[j][3 * i + 2] * tw[j][2]));
+            if (kPark == 2) tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 3; ++i) text[i] = fma((kPark == 2) ? ta[i] : TAV(j, i), ramp, text[i]);
             if (kExtras && (th.xinfo[j] >> 8) != 0) {
                 if (kLast) {  // half forces of the extra joints on this node (every other step: after the rotation below)
                     const int cnt = (th.xinfo[j] >> 16) & 0xF, first = th.xinfo[j] >> 20;
@@ -594,7 +663,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
             double wnew[3];
 #pragma unroll
             for (int i = 0; i < 3; ++i)
-                wnew[i] = fma((dt * UNI(BR2_FC_JINV + i)) * dil, tint[j][i] + text[i], w[j][i]) * damp[i];
+                wnew[i] = fma(KD(8 + i, dt * UNI(BR2_FC_JINV + i)) * dil, tint[j][i] + text[i], w[j][i]) * damp[i];
             if (kLast && (th.fl[j] & TILE_F_VALID)) {
                 // quantities the reference's callbacks report (free_simulator.py:56-72), as of this step
                 const double mass = tb.slot_c[(long long)BR2_SC_MASS * tb.n_slots + wh.s0 + j];
@@ -659,6 +728,20 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
                 }
             }
         }
+        if (kPark == 2) {
+            // the rotated director of slot 1 waits in tensor memory until P2 has finished with slot 0; the positions come
+            // back: x[1] from tensor memory, x[0] from its published row (nobody has overwritten it: P1 of the next step is mine)
+#pragma unroll
+            for (int i = 0; i < 9; ++i) tmem_park(TM_AT(kPkQ1 + i), Q[1][i]);
+            if (!kLast) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    x[1][i] = tmem_fetch(TM_AT(kPkX1 + i));
+                    x[0][i] = sm[L::XF + i * R + t];
+                }
+                tmem_wait_ld();
+            }
+        }
 #pragma unroll
         for (int j = 0; j < C; ++j) {
 #pragma unroll
@@ -669,6 +752,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
         }
     }
 #undef UNI
+#undef KD
 #undef JDV
 #undef TAV
 }
@@ -676,7 +760,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 template <int C, int NT, int kMinBlocks, bool kExtras, bool kCluster, bool kExact, int kPark = 0>
 __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __grid_constant__ StepParams p) {
     static_assert(!kPark || (NT <= 128 && !kExtras), "register parking: one lane per thread, no divergent joint code");
-    using L = TileSmem<C, NT>;
+    using L = TileSmem<C, NT, kPark == 2>;
     constexpr int R = L::R;
     extern __shared__ double sm[];
     __shared__ long long s_item;
@@ -741,7 +825,7 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
         const bool final_chunk = (chunk == p.n_chunks - 1);
 
         TileThread<C> th;
-        th.t = t + 1;
+        th.t = t + 1;  // (kPark == 2: an idle thread's own row is row 0, set below)
         th.bad = 0;
         // ---- which run is mine -------------------------------------------------------------------
         const bool active = t < tp.cta_threads[rank];
@@ -753,6 +837,7 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
             // rows I read from: next / previous run of my rod, my partner as rod one of the joints I own, the owner
             // of the joints in which I am rod one (and the owner of my predecessor's); the zero row when there is none
             th.tn = (active && k0 + C <= n) ? t + 2 : t + 1;
+            if (kPark == 2 && !active) th.t = th.tn = 0;
             const int r1 = tp.partner[rod], ro = tp.owner[rod];
             th.t1 = (active && r1 >= 0) ? 1 + tp.rod_t0[r1] + (t - tp.rod_t0[rod]) : 0;
             th.to = (active && ro >= 0) ? 1 + tp.rod_t0[ro] + (t - tp.rod_t0[rod]) : 0;
@@ -786,7 +871,10 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
                 }
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
-                    sm[L::TA + (3 * j + i) * R + t + 1] = ta[i];
+                    if (kPark == 2)
+                        tmem_park(TM_AT(kPkTA + 3 * j + i), ta[i]);
+                    else
+                        sm[L::TA + (3 * j + i) * R + t + 1] = ta[i];
                     th.x[j][i] = valid ? __ldcg(inst + i * np1 + k) : 0.0;
                     th.v[j][i] = valid ? __ldcg(inst + 3 * np1 + i * np1 + k) : 0.0;
                     th.w[j][i] = elem ? __ldcg(inst + 6 * np1 + 9 * n + i * n + k) : 0.0;
@@ -833,6 +921,10 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
 #pragma unroll
             for (int i = 0; i < 3; ++i) th.x[j][i] = fma(hdt, th.v[j][i], th.x[j][i]);
             th.bad |= TileMath<kExact>::rotate(th.Q[j], th.w[j], hdt, hdt) ? 1 : 0;
+        }
+        if (kPark == 2) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) tmem_park(TM_AT(kPkQ1 + i), th.Q[1][i]);
         }
         for (int step = 0; step < n_steps - 1; ++step) {
             tile_step<C, NT, false, false, kExtras, kCluster, kExact, kPark>(p, sm, th, time + hdt, b, rank, step & 1, tm);
