@@ -217,10 +217,11 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
     using M = TileMath<kExact>;
     const DevTables &tb = p.t;
     const int t = th.t;
-    const double dt = p.dt, hdt = (kPark == 2) ? p.kd[11] : 0.5 * p.dt;
-    // kPark == 2 runs at 128 registers: loop-invariant products come from the constant bank (StepParams::kd, filled by
-    // br2_step with the very same expressions) instead of being hoisted into registers that then spill
-#define KD(idx, expr) ((kPark == 2) ? p.kd[(idx)] : (expr))
+    const double dt = p.dt, hdt = p.kd[11];
+    // loop-invariant products of the uniform constants and dt come from the constant bank (StepParams::kd, filled by br2_step
+    // with the very expressions quoted here) instead of being hoisted into registers that then spill: +2-3 % on the
+    // multi-segment kernels, neutral on the single-segment one, and what lets the 128-register build run without spills
+#define KD(idx, expr) p.kd[(idx)]
     TileWhere wh{};
     if (kLast) wh = tile_where<C>(p, (int)threadIdx.x, b, rank);
     const int n = wh.n, np1 = wh.n + 1;
