@@ -721,11 +721,30 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 #pragma unroll
             for (int j = 0; j < C; ++j) {
                 const int cnt = (th.xinfo[j] >> 16) & 0xF, first = th.xinfo[j] >> 20;
-                for (int q = 0; q < cnt; ++q) {
-                    const int item = XIT[first + q];
-                    const double sgn = (item & 1) ? -1.0 : 1.0;
+                if (cnt) {
+                    // the first three items (a joined element's node has three: one per rod of the other segment) without a
+                    // branch between them, so that their loads are in flight together; same order of summation as the loop
+                    int item[3];
+                    double f[3][3];
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) v[j][i] = fma(th.dtmc[j] * sgn, JF[i * n_xj + (item >> 1)], v[j][i]);
+                    for (int q = 0; q < 3; ++q) item[q] = XIT[first + min(q, cnt - 1)];
+#pragma unroll
+                    for (int q = 0; q < 3; ++q)
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) f[q][i] = JF[i * n_xj + (item[q] >> 1)];
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        const double sd = (item[q] & 1) ? -th.dtmc[j] : th.dtmc[j];
+                        const double s = (q < cnt) ? sd : 0.0;
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) v[j][i] = fma(s, f[q][i], v[j][i]);
+                    }
+                    for (int q = 3; q < cnt; ++q) {
+                        const int it = XIT[first + q];
+                        const double sgn = (it & 1) ? -1.0 : 1.0;
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) v[j][i] = fma(th.dtmc[j] * sgn, JF[i * n_xj + (it >> 1)], v[j][i]);
+                    }
                 }
             }
         }
