@@ -39,10 +39,11 @@ ROD_DB = os.path.join(DATA, "rod_library.json")
 PSI = 6895.0
 FLOP_PER_ELEMENT_STEP = 695.0  # SURVEY.md Appendix B (single-BR2-type assembly, gravity on)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step kernel on the default workload (4096 x
-# single_br2, 2000 steps = 8 chunks), ncu capture profiles/r01_dram_2000step_launch.csv: 140.6 MB + 535.1 MB.  The
-# algorithmic figure is 231.8 MB (state in, state + derived arrays out); the excess is the chunked work queue writing
-# the 73 MB state back after every chunk -- 21 GB/s at 32 ms per launch, 0.3 % of the HBM peak.
-NCU_DRAM_BYTES_PER_LAUNCH = {("single", 4096, 2000): 675648768.0}
+# single_br2, 2000 steps = 8 chunks), ncu capture profiles/r01_dram_2000step_launch.csv: 76.9 MB + 168.3 MB.  The
+# algorithmic figure is 231.8 MB (state in, state + derived arrays out): the work queue hands an instance's next chunk
+# out while the state the previous one wrote back is still in the L2 (groups of ~2048 instances), so only the last
+# chunk's write-back reaches DRAM.  (Chunk-major over the whole batch it was 676 MB.)
+NCU_DRAM_BYTES_PER_LAUNCH = {("single", 4096, 2000): 245184768.0}
 WORKLOADS = {
     "single": dict(assembly="assembly_single.json", elements=123, gravity=True, seed=0,
                    label="single_br2_v1 x4096/GPU, random pressures U[0,40] psi, gravity on, dt=2e-5 (BASELINE configs[1])"),

@@ -79,6 +79,7 @@ struct StepParams {
     // launch chunking (tile kernel's work queue; the exact-path replay resumes at the chunk that failed:
     // status = 1 + chunk).  One chunk = the whole launch for the other kernels.
     int chunk_steps, n_chunks;
+    long long queue_group;                // instances per group of the tile kernel's work queue (see the kernel)
     double chunk_t0[BR2_MAX_CHUNKS];      // fp64-accumulated start time of each chunk
     unsigned long long *fail_counter;     // instances flagged by the optimistic pass of this launch
     unsigned long long *work_counter;     // next item of the queue (zeroed before every launch)

@@ -809,27 +809,36 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
         tm = s_tmem + ((uint32_t)(32 * ((t >> 5) & 3)) << 16);
     }
 
-    // Persistent CTAs pull (chunk, instance) items off one queue, chunk-major: the launch is cut into n_chunks
-    // runs of chunk_steps steps so that the last wave of instances does not leave most SMs idle (4096 instances
-    // on 888 resident CTAs would otherwise cost 5 full waves for 4.6 waves of work).  Chunk c of an instance
-    // starts when chunk c-1 of the same instance has been written back (progress[instance] == c); with the
-    // chunk-major order that was `batch` items ago, so nobody actually waits unless the batch is tiny.
+    // Persistent CTAs pull (chunk, instance) items off one queue: the launch is cut into n_chunks runs of chunk_steps
+    // steps so that the last wave of instances does not leave most SMs idle (4096 instances on 888 resident CTAs would
+    // otherwise cost 5 full waves for 4.6 waves of work).  Order: instances in groups of p.queue_group (about two waves of
+    // CTAs), chunk-major inside a group, group after group -- so the state a chunk writes back is read again `queue_group`
+    // items later, while it still sits in the L2 (a group's state is ~32 MB), instead of a whole batch later.  Chunk c of an
+    // instance starts when chunk c-1 of the same instance has been written back (progress[instance] == c); that was two
+    // waves ago, so nobody actually waits unless the batch is tiny.
     for (;;) {
         if (rank == 0 && t == 0) {
             const long long next = (long long)atomicAdd(p.work_counter, 1ULL);
+            long long packed = -1;
             if (next < total_items) {
-                while (*(volatile int *)(p.progress + next % p.batch) < (int)(next / p.batch)) __nanosleep(100);
+                const long long per_group = p.queue_group * (long long)p.n_chunks;
+                const long long g = next / per_group, r = next - g * per_group;
+                const long long first = g * p.queue_group;
+                const long long size = (p.batch - first < p.queue_group) ? p.batch - first : p.queue_group;  // the last group may be short
+                const long long c = r / size, bb = first + (r - c * size);
+                while (*(volatile int *)(p.progress + bb) < (int)c) __nanosleep(100);
                 __threadfence();
+                packed = bb | (c << 48);
             }
-            for (int r = 0; r < (kCluster ? tp.n_ctas : 1); ++r) *tile_peer<kCluster>(&s_item, r) = next;
+            for (int r = 0; r < (kCluster ? tp.n_ctas : 1); ++r) *tile_peer<kCluster>(&s_item, r) = packed;
             s_why = 0;
         }
         tile_sync<kCluster>();
         const long long item = s_item;
         tile_sync<kCluster>();
-        if (item >= total_items) break;
-        const long long b = item % p.batch;
-        const int chunk = (int)(item / p.batch);
+        if (item < 0) break;
+        const long long b = item & ((1LL << 48) - 1);
+        const int chunk = (int)(item >> 48);
         {
             // optimistic pass: an instance waiting for the exact-path replay skips the rest of the launch;
             // exact pass: only flagged instances, from the chunk in which they were flagged (status = 1 + chunk | why << 8)
