@@ -668,3 +668,26 @@ def test_ragged_assembly_with_an_odd_batch_matches_oracle(tmp_path, variant):
     tips = env.simulator[3].position_collection[:, 1, -1]
     assert 0.25 < tips.mean() < 0.31 and tips.std() > 1e-5  # second segment sits on top of the first; instances differ
     env.close()
+
+
+@pytest.mark.parametrize("assembly", ["single", "double"])
+def test_work_queue_grouping_does_not_change_a_bit(assembly, monkeypatch):
+    """The tile kernel's persistent CTAs pull (chunk, instance) items in groups of instances (csrc/br2_tile.cuh).  The order
+    items are handed out in is scheduling only: tiny groups -- where a chunk IS handed out before the previous chunk of the
+    same instance has been written back, so the progress wait really waits -- a short last group, and one group for the
+    whole batch must produce identical bits."""
+    batch, n_steps, dt = 200, 1000, 2.0e-5  # 8 chunks of 125 steps
+    pressures = np.random.default_rng(21).uniform(0.0, 40.0, size=(3, batch)) * PSI
+    action = {name: pressures[i] for i, name in enumerate(NAMES)}
+    states = []
+    for group in ("0", "64", "7"):
+        monkeypatch.setenv("BR2_TILE_QUEUE_GROUP", group)
+        env = make_env(assembly, batch, variant="tile", gravity=True)
+        env.simulator._callback_ops = []
+        env.run(action, duration=n_steps * dt - 0.5 * dt, disable_progress_bar=True)
+        assert env.engine.replay_count() == 0
+        states.append(env.engine.state.cpu().numpy().copy())  # the whole state block, derived arrays included
+        env.close()
+    assert np.isfinite(states[0]).all()
+    np.testing.assert_array_equal(states[0], states[1])
+    np.testing.assert_array_equal(states[0], states[2])
