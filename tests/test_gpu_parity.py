@@ -670,13 +670,16 @@ def test_ragged_assembly_with_an_odd_batch_matches_oracle(tmp_path, variant):
     env.close()
 
 
-@pytest.mark.parametrize("assembly", ["single", "double"])
+@pytest.mark.parametrize("assembly", ["single", "double", "triple-as-cluster"])
 def test_work_queue_grouping_does_not_change_a_bit(assembly, monkeypatch):
     """The tile kernel's persistent CTAs pull (chunk, instance) items in groups of instances (csrc/br2_tile.cuh).  The order
     items are handed out in is scheduling only: tiny groups -- where a chunk IS handed out before the previous chunk of the
     same instance has been written back, so the progress wait really waits -- a short last group, and one group for the
     whole batch must produce identical bits."""
     batch, n_steps, dt = 200, 1000, 2.0e-5  # 8 chunks of 125 steps
+    if assembly == "triple-as-cluster":  # three CTAs per instance: the cluster pulls the items
+        monkeypatch.setenv("BR2_TILE_ONE_CTA_THREADS", "100")
+        assembly = "triple"
     pressures = np.random.default_rng(21).uniform(0.0, 40.0, size=(3, batch)) * PSI
     action = {name: pressures[i] for i, name in enumerate(NAMES)}
     states = []
