@@ -400,7 +400,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
             double Qn[9];
 #pragma unroll
             for (int i = 0; i < 9; ++i) Qn[i] = (j + 1 < C) ? Q[(j + 1) % C][i] : sm[L::QF + i * R + th.tn];
-                        const double lenn = (j + 1 < C) ? len[(j + 1) % C] : sm[L::LF + th.tn];
+            const double lenn = (j + 1 < C) ? len[(j + 1) % C] : sm[L::LF + th.tn];
             const double *q = Q[j];
             // antisymmetric part and trace of Qn Q^T
             const double w0 = fma(Qn[6], q[3], fma(Qn[7], q[4], fma(Qn[8], q[5], fma(-Qn[3], q[6], fma(-Qn[4], q[7], -Qn[5] * q[8])))));
