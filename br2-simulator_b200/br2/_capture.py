@@ -18,10 +18,10 @@ import numpy as np
 class StateCapture:
     """One snapshot of the batch state ``[batch, words]``: a device clone until first read, then a host array."""
 
-    def __init__(self, engine, tensor=None, host=None):
+    def __init__(self, engine, tensor=None, host=None, batch=None):
         self.layout = engine.program.layout
         self.n_elems = engine.program.n_elems
-        self.batch = engine.batch
+        self.batch = engine.batch if batch is None else int(batch)  # (a gathered capture holds the global batch)
         self._tensor = tensor
         self._host = host
 
@@ -42,11 +42,19 @@ class StateCapture:
 
 
 class _Lazy:
-    """Entry of a CaptureSeries that is still a reference into a StateCapture."""
-    __slots__ = ("make",)
+    """Entry of a CaptureSeries that is still a reference into a StateCapture: one field of one rod, optionally passed
+    through ``post`` (centre of mass).  ``rebind`` points the same entry at another capture (the gathered one)."""
+    __slots__ = ("capture", "rod_index", "short", "shape", "post")
 
-    def __init__(self, make):
-        self.make = make
+    def __init__(self, capture, rod_index, short, shape, post=None):
+        self.capture, self.rod_index, self.short, self.shape, self.post = capture, rod_index, short, tuple(shape), post
+
+    def make(self):
+        value = self.capture.field(self.rod_index, self.short, self.shape)
+        return value if self.post is None else self.post(value)
+
+    def rebind(self, capture):
+        return _Lazy(capture, self.rod_index, self.short, self.shape, self.post)
 
 
 class CaptureSeries:

@@ -71,20 +71,105 @@ def gather_batch(local, total, dst=None, device=None):
     return full.cpu().numpy() if as_numpy else full
 
 
-def gather_history(sink, total, dst=0):
-    """Gather one rod's callback dictionary (lists of per-capture arrays with a leading local-batch axis)
-    into the global-batch layout on ``dst``.  ``time`` / ``step`` are identical on every rank."""
+def gather_block(block, total, dst=0):
+    """``[local_batch, ...]`` torch tensor of every rank -> ``[total, ...]`` on ``dst`` (``None`` elsewhere), in rank
+    order, on the device the blocks live on: point-to-point sends straight into the right rows of the output (NCCL over
+    NVLink on GPUs, gloo on CPU tensors), so uneven shares need no padding and nothing is staged through the host."""
+    dist = _dist()
+    if dist is None or dist.get_world_size() == 1:
+        return block
+    world, rank = dist.get_world_size(), dist.get_rank()
+    shares = [partition(total, world, r) for r in range(world)]
+    block = block.contiguous()
+    if block.shape[0] != shares[rank][1] - shares[rank][0]:
+        raise ValueError("rank %d holds %d instances, its share of %d is %d" % (rank, block.shape[0], total, shares[rank][1] - shares[rank][0]))
+    if rank != dst:
+        for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, block, dst)]):
+            req.wait()
+        return None
+    out = block.new_empty((total,) + tuple(block.shape[1:]))
+    ops = []
+    for r, (start, stop) in enumerate(shares):
+        if r == rank:
+            out[start:stop].copy_(block)
+        else:
+            ops.append(dist.P2POp(dist.irecv, out[start:stop], r))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    return out
+
+
+def gather_history(sink, total, dst=0, local_batch=None, gathered_captures=None):
+    """Gather one rod's callback dictionary into the global-batch layout on ``dst`` (``None`` elsewhere).  ``time`` /
+    ``step`` are identical on every rank.  Entries that are still references into a device-side capture
+    (br2/_capture.py) are re-pointed at the gathered capture -- ``gathered_captures`` maps ``id(local capture)`` to the
+    global one, filled by ``gather_captures`` with ONE device-to-device gather per capture for all rods and fields --
+    and stay lazy; entries that already are host arrays (callback classes on the reference's host protocol) are gathered
+    per field.  ``local_batch``: this rank's instance count (a rank that holds ONE instance stores its arrays without a
+    batch axis, like the reference; the axis is put back before gathering)."""
+    from ._capture import CaptureSeries, _Lazy
+
+    rank = _dist().get_rank() if _dist() is not None else 0
     out = {}
     for key, series in sink.items():
         if key in ("time", "step"):
             out[key] = list(series)
             continue
-        stacked = np.stack(series, axis=1) if len(series) else np.zeros((0, 0))  # [local_batch, T, ...]
+        items = list(series._items) if isinstance(series, CaptureSeries) else list(series)
+        if items and all(isinstance(v, _Lazy) for v in items) and gathered_captures is not None:
+            if rank == dst:
+                merged = CaptureSeries()
+                for v in items:
+                    merged.append(v.rebind(gathered_captures[id(v.capture)]))
+                out[key] = merged
+            continue
+        arrays = [v.make() if isinstance(v, _Lazy) else np.asarray(v) for v in items]
+        stacked = np.stack(arrays, axis=0) if arrays else np.zeros((0,))  # [T, (local_batch,) ...]
+        if local_batch == 1 and arrays:
+            stacked = stacked[:, None]
+        if arrays:
+            stacked = np.ascontiguousarray(np.moveaxis(stacked, 1, 0))      # [local_batch, T, ...]
         merged = gather_batch(stacked, total, dst=dst)
         if merged is not None:
             out[key] = [merged[:, t] for t in range(merged.shape[1])]
-    rank = _dist().get_rank() if _dist() is not None else 0
     return out if rank == dst else None
+
+
+def gather_captures(sinks, engine, total, dst=0):
+    """Every device-side capture referenced by the callback dictionaries ``sinks``, gathered once: returns
+    ``{id(local capture): global capture}`` on ``dst`` (values ``None`` elsewhere).  A capture that is still a device
+    clone travels device to device (``gather_block``); one that was already read moves from its host copy."""
+    from ._capture import CaptureSeries, StateCapture, _Lazy
+
+    import torch
+
+    dist = _dist()
+    rank = dist.get_rank() if dist is not None else 0
+    seen, order = set(), []
+    for sink in sinks:
+        for key, series in sink.items():
+            if isinstance(series, CaptureSeries):
+                for v in series._items:
+                    if isinstance(v, _Lazy) and id(v.capture) not in seen:
+                        seen.add(id(v.capture))
+                        order.append(v.capture)
+    on_gpu = dist is not None and dist.get_backend() == "nccl"
+    out = {}
+    for capture in order:
+        if capture.on_device:
+            block = capture._tensor
+        else:
+            block = torch.from_numpy(capture.host())
+            if on_gpu:
+                block = block.to(engine.device)
+        merged = gather_block(block, total, dst=dst)
+        if rank != dst:
+            out[id(capture)] = None
+        elif merged.is_cuda:
+            out[id(capture)] = StateCapture(engine, tensor=merged, batch=total)
+        else:
+            out[id(capture)] = StateCapture(engine, host=merged.numpy(), batch=total)
+    return out
 
 
 def reduce_flags(local_flags):

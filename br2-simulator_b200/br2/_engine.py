@@ -27,11 +27,13 @@ class Engine:
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
         self.device = torch.device(device)
+        if self.device.index is None:  # "cuda": the current device, not device 0
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.words = program.words
 
         self._cprog = _native.make_program(program)
         handle = ctypes.c_void_p()
-        _native.check(self.lib.br2_create(ctypes.byref(self._cprog), self.device.index or 0, ctypes.byref(handle)))
+        _native.check(self.lib.br2_create(ctypes.byref(self._cprog), self.device.index, ctypes.byref(handle)))
         self.handle = handle
 
         template = np.zeros(self.words)

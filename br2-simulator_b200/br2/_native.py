@@ -46,7 +46,7 @@ EXPORTS = (
     "br2_last_error", "br2_abi_version", "br2_create", "br2_destroy", "br2_words_per_instance",
     "br2_bind_state", "br2_set_actuation", "br2_step", "br2_step_host", "br2_count_steps",
     "br2_kernel_info", "br2_fp64_peak_tflops", "br2_select_kernel", "br2_selftest_math", "br2_replay_count",
-    "br2_replay_reasons", "br2_unresolved_count", "br2_describe_plan",
+    "br2_replay_reasons", "br2_unresolved_count", "br2_describe_plan", "br2_capture_plan",
 )
 
 
@@ -73,6 +73,8 @@ def load():
                                   ctypes.c_int64, ctypes.c_double, ctypes.c_double, _f64p]
     lib.br2_count_steps.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                     ctypes.POINTER(ctypes.c_int64), _f64p]
+    lib.br2_capture_plan.argtypes = [ctypes.c_double, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p, ctypes.c_int32,
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]
     lib.br2_kernel_info.argtypes = [ctypes.c_void_p] + [_i32p] * 6
     lib.br2_select_kernel.argtypes = [ctypes.c_void_p, ctypes.c_int32]
     lib.br2_replay_count.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]
@@ -121,3 +123,22 @@ def count_steps(t0, duration, dt):
     t_end = ctypes.c_double(0.0)
     check(load().br2_count_steps(float(t0), float(duration), float(dt), ctypes.byref(n), ctypes.byref(t_end)))
     return n.value, t_end.value
+
+
+def capture_plan(t0, n_steps, dt, every):
+    """[(ordinal, time)] of the steps of a run after which a diagnostics collector fires (``every``: the collectors'
+    step_skip values; ``None`` = every step): `round(time / dt) % every == 0` on the fp64-accumulated time,
+    /root/reference/br2/free_simulator.py:49-51."""
+    every = np.asarray([1 if e is None else int(e) for e in every], dtype=np.int64)
+    if every.size == 0 or n_steps <= 0:
+        return []
+    smallest = max(int(every.min()), 1)
+    capacity = n_steps // smallest + 2
+    ordinals = np.zeros(capacity, dtype=np.int64)
+    times = np.zeros(capacity, dtype=np.float64)
+    count = ctypes.c_int64(0)
+    check(load().br2_capture_plan(float(t0), int(n_steps), float(dt), every.ctypes.data, int(every.size),
+                                  ordinals.ctypes.data, times.ctypes.data, capacity, ctypes.byref(count)))
+    if count.value > capacity:  # (cannot happen: at most one stop per `smallest` steps, plus the ends)
+        raise Br2Error("br2_capture_plan: %d stops, room for %d" % (count.value, capacity))
+    return [(int(o), float(t)) for o, t in zip(ordinals[:count.value], times[:count.value])]

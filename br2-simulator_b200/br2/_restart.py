@@ -26,13 +26,25 @@ def save_state(simulator, directory="", time=0.0, verbose=False):
 
 
 def load_state(simulator, directory="", verbose=False):
+    """Every dynamic array of the file goes back into the rod, like upstream's ``load_state`` restores every non-time key
+    in place; shapes are checked against the engine's batch first (a ``[batch, ...]`` checkpoint only fits the same
+    batch; an unbatched one is broadcast to every instance on purpose -- that is how a batch is seeded from a
+    reference checkpoint)."""
     times = []
     for idx, rod in enumerate(simulator):
-        data = np.load(os.path.join(directory, "system_%d.npz" % idx))
+        path = os.path.join(directory, "system_%d.npz" % idx)
+        data = np.load(path)
         times.append(float(data["time"]))
-        for name in ("position_collection", "velocity_collection", "director_collection", "omega_collection",
-                     "acceleration_collection", "alpha_collection"):
-            setattr(rod, name, data[name])
+        batch = rod._engine.batch if getattr(rod, "_engine", None) is not None else 1
+        for name, (short, shape) in DYNAMIC_FIELDS.items():
+            if name not in data.files:
+                continue
+            value = data[name]
+            per_rod = tuple(shape(rod.n_elems))
+            if value.shape != per_rod and value.shape != (batch,) + per_rod:
+                raise ValueError("%s: %s has shape %s; this rod expects %s or %s (batch %d)"
+                                 % (path, name, value.shape, per_rod, (batch,) + per_rod, batch))
+            setattr(rod, name, value)
     if any(t != times[0] for t in times):
         raise ValueError("Restart time of loaded rods are different, check your inputs!")
     if verbose:

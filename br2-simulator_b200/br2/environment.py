@@ -11,7 +11,6 @@ The reference's hot loop (``while time < self.time + duration: time = self.do_st
 same fp64 accumulation the loop performs, and launches are split only where a diagnostics callback
 has to fire (every ``step_skip`` steps, ``current_step = round(time / dt)``).
 """
-import logging
 import os
 from dataclasses import dataclass
 from typing import Optional
@@ -76,18 +75,10 @@ class TerminalInfo:
 
 def _capture_plan(collection, start_time, n_steps, dt):
     """Ordinals (1-based, within this run) of the steps after which some callback fires, using the
-    reference's own step index ``round(time / dt)`` on the fp64-accumulated time."""
+    reference's own step index ``round(time / dt)`` on the fp64-accumulated time (one C loop: br2_capture_plan)."""
     if not collection._callback_ops:
         return []
-    plan = []
-    time = start_time
-    half = 0.5 * dt
-    for ordinal in range(1, n_steps + 1):
-        time += half
-        time += half
-        if collection.callbacks_due(round(time / dt)):
-            plan.append((ordinal, time))
-    return plan
+    return _native.capture_plan(start_time, n_steps, dt, [op.capture_steps() for _, op in collection._callback_ops])
 
 
 class Environment:
@@ -217,12 +208,19 @@ class Environment:
                 norms = torch.linalg.vector_norm(diff, dim=dims)
                 deltas[short] = torch.nan_to_num(norms, nan=-np.inf).amax(dim=-1).cpu().numpy()
             status.steady_state_deltas = deltas
+        # instances that left the optimistic kernel's range with no exact-path kernel to redo them stop advancing
+        # (br2_cuda.cu: br2_select_kernel): never silently -- checked after every run (one small device-to-host copy).
+        # With a collective check requested below every rank must fail together, so the flag is reduced first.
+        stuck = engine.unresolved_count()
+        if self.world_size > 1 and (check_nan or check_steady_state == 1):
+            stuck_anywhere = _dist.reduce_flags(stuck > 0)
+        else:
+            stuck_anywhere = stuck > 0
+        if stuck_anywhere:
+            raise _native.Br2Error(
+                "%d instance(s) of this rank left the validity range of the device kernel's series (%s) and this assembly "
+                "has no exact-path kernel; they stopped advancing" % (stuck, engine.replay_reasons()))
         if check_nan:
-            stuck = engine.unresolved_count()
-            if stuck:
-                raise _native.Br2Error(
-                    "%d instance(s) left the validity range of the device kernel's series (%s) and this assembly is too "
-                    "large for the exact-path kernel; they stopped advancing" % (stuck, engine.replay_reasons()))
             flags = {}
             for label, short in (("position", "x"), ("velocity", "v"), ("director", "Q"), ("omega", "w")):
                 per_instance = torch.isnan(self._state_stack(short)).flatten(1).any(dim=1)
@@ -248,18 +246,18 @@ class Environment:
 
     # ------------------------------------------------------------------ export (reference :394-464)
     def render_video(self, visualize_twist_angle: bool = False, **kwargs) -> None:
-        save_folder = self.paths.renderings
-        if os.path.exists(save_folder):
-            logging.warning("The folder already exists. The data will be overwritten.")
-        os.makedirs(save_folder, exist_ok=True)
+        """The reference renders with matplotlib / ffmpeg and then exports the positions (:394-429).  Rendering is host
+        post-processing outside the path this package replaces: the export the call ends with is done FIRST (so the data
+        the reference's own ``br2.visualize`` functions need is on disk), then ``br2.visualize`` says what to feed them."""
+        self.save_data("position")
         from .visualize import plot_video_with_surface, visual_twist_with_surface
 
+        save_folder = self.paths.renderings
         plot_video_with_surface(self.data_rods, video_name="br2_simulation", fps=self.rendering_fps, step=1,
                                 save_folder=save_folder, **kwargs)
         if visualize_twist_angle:
             visual_twist_with_surface(self.data_rods, video_name="br2_simulation", fps=self.rendering_fps, step=1,
                                       save_folder=save_folder, **kwargs)
-        self.save_data("position")
 
     def save_data(self, tag: Optional[str] = None) -> None:
         """``time``, element-centre ``positions [rod, T, (batch,) 3, n]`` and ``directors
@@ -276,10 +274,14 @@ class Environment:
 
     def gather_data(self, dst=0):
         """Callback histories of ALL instances on rank ``dst`` (same layout as ``data_rods``, batch axis =
-        global batch); other ranks get ``None``.  One gather per recorded field, over NCCL / gloo."""
+        global batch); other ranks get ``None``.  Device-side captures are gathered device to device, ONE transfer per
+        capture for all rods and fields (the payload of /root/reference/br2/free_simulator.py:56-72), and stay lazy on
+        ``dst``; histories recorded on the host protocol are gathered per field."""
         if self.world_size == 1:
             return self.data_rods
-        gathered = [_dist.gather_history(sink, self.global_batch, dst=dst) for sink in self.data_rods]
+        captures = _dist.gather_captures(self.data_rods, self.engine, self.global_batch, dst=dst)
+        gathered = [_dist.gather_history(sink, self.global_batch, dst=dst, local_batch=self.batch, gathered_captures=captures)
+                    for sink in self.data_rods]
         return gathered if self.rank == dst else None
 
     def gather_field(self, rod_index, attribute, dst=None):

@@ -104,14 +104,9 @@ class FreeCallback(CallBackBaseClass):
         n = rod.n_elems
         for key, attribute in _CALLBACK_ARRAYS:
             short, shape = DYNAMIC_FIELDS[attribute]
-            sink[key].append(_Lazy(lambda short=short, shape=shape(n): capture.field(rod_index, short, shape)))
+            sink[key].append(_Lazy(capture, rod_index, short, shape(n)))
         mass = np.asarray(rod.mass)
-
-        def com():
-            x = capture.field(rod_index, "x", (3, n + 1))
-            return (x * mass).sum(axis=-1) / mass.sum()
-
-        sink["com"].append(_Lazy(com))
+        sink["com"].append(_Lazy(capture, rod_index, "x", (3, n + 1), post=lambda x: (x * mass).sum(axis=-1) / mass.sum()))
 
 
 def _load_rod_library(path):

@@ -710,6 +710,31 @@ int br2_count_steps(double t0, double duration, double dt, int64_t *n_steps, dou
     return BR2_OK;
 }
 
+int br2_capture_plan(double t0, int64_t n_steps, double dt, const int64_t *every, int32_t n_every, int64_t *ordinals,
+                     double *times, int64_t capacity, int64_t *count) {
+    if (!(dt > 0.0) || n_steps < 0 || !count || (n_every > 0 && !every))
+        return fail(BR2_EINVAL, "br2_capture_plan: bad argument");
+    volatile double time = t0;
+    const double half = 0.5 * dt;
+    int64_t found = 0;
+    for (int64_t ordinal = 1; ordinal <= n_steps; ++ordinal) {
+        time += half;
+        time += half;
+        const double q = time / dt;
+        const long long step = llrint(q);  // python's round(): to nearest, ties to even (default rounding mode)
+        bool due = false;
+        for (int32_t i = 0; i < n_every && !due; ++i) due = every[i] <= 1 || step % every[i] == 0;
+        if (!due) continue;
+        if (found < capacity) {
+            if (ordinals) ordinals[found] = ordinal;
+            if (times) times[found] = time;
+        }
+        ++found;
+    }
+    *count = found;
+    return BR2_OK;
+}
+
 int br2_step(br2_handle h, int64_t n_steps, double t0, double dt, void *stream, double *t_end) {
     if (!h) return fail(BR2_EINVAL, "br2_step: NULL handle");
     if (!h->state) return fail(BR2_ESTATE, "br2_step: no state bound (call br2_bind_state)");

@@ -221,6 +221,13 @@ int br2_step_host(br2_handle h, double *host_state, const double *host_pressures
  * (environment.py:278: the count comes from fp64 accumulation, two +dt/2 per step). */
 int br2_count_steps(double t0, double duration, double dt, int64_t *n_steps, double *t_end);
 
+/* Where a run of n_steps steps from t0 must stop for diagnostics callbacks: the steps (1-based ordinals within the run)
+ * after which `round(time / dt) % every[i] == 0` holds for some collector i, on the fp64-accumulated time -- the test
+ * FreeCallback.make_callback performs every step (free_simulator.py:49-51; every[i] <= 1 = every step).  Writes up to
+ * `capacity` ordinals / times, and the total number of stops to *count (call again with more room if count > capacity). */
+int br2_capture_plan(double t0, int64_t n_steps, double dt, const int64_t *every, int32_t n_every, int64_t *ordinals,
+                     double *times, int64_t capacity, int64_t *count);
+
 /* Which kernel br2_create would pick for this program and how it would lay the assembly out ("tile: 3 CTA(s) per instance
  * of 303, 303, 303 threads ..."), or why the faster kernels refuse it.  Host only: needs no GPU.  BR2_ELIMIT if the
  * assembly fits no kernel. */

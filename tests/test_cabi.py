@@ -55,3 +55,20 @@ def test_engine_refuses_to_run_without_cuda():
     env = Environment("nocuda", create_dirs=False)
     with pytest.raises(_native.Br2Error, match="no CPU fallback"):
         env.reset(os.path.join(DATA, "rod_library.json"), os.path.join(DATA, "assembly_single.json"))
+
+
+def test_capture_plan_matches_the_reference_step_test():
+    """br2_capture_plan == the reference's per-step test `round(time / dt) % step_skip == 0` on the fp64-accumulated time
+    (/root/reference/br2/free_simulator.py:49-51), for one and for two collectors, from a non-zero start time."""
+    from br2 import _native
+
+    for t0, n_steps, dt, every in ((0.0, 50001, 2.0e-5, [2000]), (0.04, 4100, 2.0e-5, [2000, 300]), (0.0, 7, 1.0e-3, [None])):
+        want, time = [], t0
+        for ordinal in range(1, n_steps + 1):
+            time += 0.5 * dt
+            time += 0.5 * dt
+            step = round(time / dt)
+            if any(e is None or step % e == 0 for e in every):
+                want.append((ordinal, time))
+        assert _native.capture_plan(t0, n_steps, dt, every) == want
+    assert len(_native.capture_plan(0.0, 50001, 2.0e-5, [2000])) == 25

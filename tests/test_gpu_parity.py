@@ -93,7 +93,7 @@ BATCH_CASES = [
     # BASELINE.json configs 2 / 3 (and the sample triple assembly at n=41), sampled: 64 random instances
     ("single", {"gravity": True}, 0, 10000),
     ("double", {}, 1, 10000),
-    ("triple", {"gravity": True}, 2, 4000),
+    ("triple", {"gravity": True}, 2, 10000),
 ]
 
 
@@ -239,9 +239,10 @@ def test_cluster_path_replays_out_of_range_instances_exactly(monkeypatch):
 
 
 def test_high_resolution_triple_baseline_config_4():
-    """BASELINE config 4: triple assembly with 200 elements per rod (1809 node slots) at dt = 5e-6 (SURVEY.md section 0.6:
-    dt = 2e-5 diverges at this resolution) -- a cluster of three 320-thread CTAs per instance."""
-    worst, info = _cluster_case("triple", os.path.join(DATA, "rod_library_n200.json"), {"gravity": True}, 2, 2000, 5.0e-6, 8)
+    """BASELINE config 4 at the parity sample SURVEY.md section 8(d) asks for: triple assembly with 200 elements per rod
+    (1809 node slots) at dt = 5e-6 (dt = 2e-5 diverges at this resolution), instance 0 plus 64
+    random instances, 10^4 steps -- a cluster of three 320-thread CTAs per instance."""
+    worst, info = _cluster_case("triple", os.path.join(DATA, "rod_library_n200.json"), {"gravity": True}, 2, 10000, 5.0e-6, 65)
     print("cluster triple n=200", info, worst)
     assert info["threads"] == 320
     assert worst["x"] <= POS_TOL and worst["Q"] <= DIR_TOL and worst["v"] <= VEL_TOL and worst["w"] <= OMEGA_TOL
