@@ -145,14 +145,18 @@ def lower_collection(collection):
             "assembly has %d node slots; one thread-block cluster integrates one assembly and holds at most %d"
             % (ctx.n_slots, MAX_SLOTS))
 
+    # this package's descriptors lower themselves; instances of the reference's own classes (no ``lower_*`` method) are
+    # recognised by class name and read through their public attributes (br2/_adapter.py); anything else is refused
+    from . import _adapter
+
     for rod_index, op in collection._forcing:
-        op.lower_forcing(ctx, rod_index)
+        _adapter.adapt(op, _adapter._FORCING, "forcing").lower_forcing(ctx, rod_index)
     for rod_index, op in collection._constraint_ops:
-        op.lower_constraint(ctx, rod_index)
+        _adapter.adapt(op, _adapter._CONSTRAINTS, "constraint").lower_constraint(ctx, rod_index)
     for rod_index, op in collection._damper_ops:
-        op.lower_damper(ctx, rod_index)
+        _adapter.adapt(op, _adapter._DAMPERS, "damper").lower_damper(ctx, rod_index)
     for rod_one, rod_two, idx_one, idx_two, op in collection._joints:
-        op.lower_joint(ctx, rod_one, idx_one, rod_two, idx_two)
+        _adapter.adapt(op, _adapter._JOINTS, "joint").lower_joint(ctx, rod_one, idx_one, rod_two, idx_two)
 
     prog = Program()
     S = ctx.n_slots

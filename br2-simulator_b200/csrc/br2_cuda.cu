@@ -85,38 +85,32 @@ struct KernelChoice {
 #ifndef BR2_TILE_MB64
 #define BR2_TILE_MB64 6
 #endif
-#ifndef BR2_TILE_PARK
-#define BR2_TILE_PARK 0  // 1: the 64-thread tile kernel parks x and omega in tensor memory across P3 (measured: no gain)
-#endif
 #ifndef BR2_TILE_MIN_CHUNK_STEPS
 #define BR2_TILE_MIN_CHUNK_STEPS 125  // a launch is cut into at most BR2_MAX_CHUNKS chunks of at least this many steps
 #endif
-// variant 3: tile kernel (BR2_TILE_C slots per thread, uniform constants); `threads` = CTA size
-// template flags: <slots per thread, CTA threads, min CTAs per SM, extra joints, cluster>
-// the 128-register kernel: eight 64-thread CTAs per SM, state parked in tensor memory between phases, lean shared-memory
-// layout (needs an idle thread in the CTA)
-#ifndef BR2_TILE_LEAN_MB
-#define BR2_TILE_LEAN_MB 8
+#ifndef BR2_TILE_SPLIT_SINGLE
+#define BR2_TILE_SPLIT_SINGLE false  // split-phase mbarriers in the single-segment kernels too (measured: see DESIGN.md)
 #endif
-const KernelChoice kTileLeanKernel = {64, br2::br2_step_tile_kernel<BR2_TILE_C, 64, BR2_TILE_LEAN_MB, false, false, false, 2>};
+// variant 3: tile kernel (BR2_TILE_C slots per thread, uniform constants); `threads` = CTA size
+// template flags: <slots per thread, CTA threads, min CTAs per SM, extra joints, cluster, exact arithmetic, split-phase barriers>
 const KernelChoice kTileKernels[] = {  // single-segment assemblies (ring joints only)
-    {64, br2::br2_step_tile_kernel<BR2_TILE_C, 64, BR2_TILE_MB64, false, false, false, BR2_TILE_PARK == 2 ? 0 : BR2_TILE_PARK>},
-    {128, br2::br2_step_tile_kernel<BR2_TILE_C, 128, 3, false, false, false>},
-    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, false, false, false>},
+    {64, br2::br2_step_tile_kernel<BR2_TILE_C, 64, BR2_TILE_MB64, false, false, false, BR2_TILE_SPLIT_SINGLE>},
+    {128, br2::br2_step_tile_kernel<BR2_TILE_C, 128, 3, false, false, false, true>},
+    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, false, false, false, true>},
 };
 const KernelChoice kTileExtraKernels[] = {  // several segments joined tip to base, one CTA
-    {128, br2::br2_step_tile_kernel<BR2_TILE_C, 128, 3, true, false, false>},
-    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true, false, false>},
-    {256, br2::br2_step_tile_kernel<BR2_TILE_C, 256, 1, true, false, false>},
+    {128, br2::br2_step_tile_kernel<BR2_TILE_C, 128, 3, true, false, false, true>},
+    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true, false, false, true>},
+    {256, br2::br2_step_tile_kernel<BR2_TILE_C, 256, 1, true, false, false, true>},
 };
 // one CTA per group of ring-connected rods, launched as a thread-block cluster per instance
 const KernelChoice kTileClusterKernels[] = {
-    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true, true, false>},
-    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, true, true, false>},
+    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true, true, false, true>},
+    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, true, true, false, true>},
 };
 const KernelChoice kTileClusterExactKernels[] = {  // same, exact arithmetic: the replay path of cluster-sized assemblies
-    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true, true, true>},
-    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, true, true, true>},
+    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true, true, true, true>},
+    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, true, true, true, true>},
 };
 const int kTileMaxCtaThreads = 320, kTileOneCtaThreads = 256;
 
@@ -217,7 +211,7 @@ int validate(const br2_program *p) {
 // Plan of the thread-coarsened kernel (br2_tile.cuh), or the reason the assembly does not qualify.
 struct TileExtraTables {
     std::vector<int32_t> xi, xj_i;   // xi: staging rows (BR2_TILE_XI_*), packed into xpack / xitems at the end
-    std::vector<int32_t> xpack, xitems;
+    std::vector<int32_t> xpack, xitems, xe_mask;
     std::vector<double> xj_d;
 };
 
@@ -341,6 +335,15 @@ bool make_tile_plan(const br2_program *p, int C, br2::TilePlan *plan, TileExtraT
         const int j = p->fast_i[sl * BR2_FAST_NI + BR2_FAST_OWN_JOINT];
         if (j >= 0) owned_joint[j] = 1;
     }
+    // Every CTA evaluates the extra joints that act on its own nodes -- a joint between two CTAs of a cluster is evaluated
+    // by both, with bit-identical arithmetic on the same pushed data, so no force ever travels between CTAs -- and an
+    // element's data is pushed to exactly the CTAs that read it (joint evaluation, director / omega overwrite).
+    std::vector<int32_t> xe_mask;      // per published element: consumer ranks
+    std::vector<int> xj_ranks;         // per extra joint: bit mask of the evaluating ranks
+    auto consume = [&](int xe, int rank) {
+        if ((int)xe_mask.size() <= xe) xe_mask.resize(xe + 1, 0);
+        xe_mask[xe] |= 1 << rank;
+    };
     for (int j = 0; j < p->n_joints; ++j) {
         if (owned_joint[j]) continue;
         const int32_t *ji = p->joint_i + (size_t)j * BR2_J_NI;
@@ -359,14 +362,20 @@ bool make_tile_plan(const br2_program *p, int C, br2::TilePlan *plan, TileExtraT
         xt->xj_d.insert(xt->xj_d.end(), drow, drow + 8);
         // the four nodes of the two elements: rod one +F/2, rod two -F/2
         const int node_slot[4] = {ji[BR2_J_S1], ji[BR2_J_S1] + 1, ji[BR2_J_S2], ji[BR2_J_S2] + 1};
+        int ranks = 0;
         for (int q = 0; q < 4; ++q) {
             int jn;
             const int tn = thread_of(node_slot[q], &jn);
+            ranks |= 1 << slot_rank;
             int32_t &cnt = xt->xi[(size_t)tn * XN + BR2_TILE_XI_NCNT(C, jn)];
             if (cnt >= BR2_FAST_NODE_ITEMS) return *why = "a node receives too many extra joint forces", false;
             xt->xi[(size_t)tn * XN + BR2_TILE_XI_NITEM(C, jn, cnt)] = (xj << 1) | (q >= 2 ? 1 : 0);
             ++cnt;
         }
+        xj_ranks.push_back(ranks);
+        for (int r = 0; r < plan->n_ctas; ++r)
+            if (ranks & (1 << r))
+                for (int q = 6; q < 10; ++q) consume(row[q], r);
     }
     // point forces (PointForces, /root/reference/br2/custom_activation.py:46-81): an "extra joint" of type 1 that puts
     // F min(1, t / ramp_up_time) on one node
@@ -384,6 +393,7 @@ bool make_tile_plan(const br2_program *p, int C, br2::TilePlan *plan, TileExtraT
             xt->xj_i.insert(xt->xj_i.end(), row, row + 12);
             const double drow[8] = {fd[0], fd[1], fd[2], fd[3], 0, 0, 0, 0};
             xt->xj_d.insert(xt->xj_d.end(), drow, drow + 8);
+            xj_ranks.push_back(1 << slot_rank);
             int32_t &cnt = xt->xi[(size_t)tn * XN + BR2_TILE_XI_NCNT(C, jn)];
             if (cnt >= BR2_FAST_NODE_ITEMS) return *why = "a node receives too many extra forces", false;
             xt->xi[(size_t)tn * XN + BR2_TILE_XI_NITEM(C, jn, cnt)] = (xj << 1) | 0;
@@ -394,22 +404,32 @@ bool make_tile_plan(const br2_program *p, int C, br2::TilePlan *plan, TileExtraT
         if (p->overwrite_src[sl] < 0) continue;
         int j;
         const int t = thread_of((int)sl, &j);
-        xt->xi[(size_t)t * XN + BR2_TILE_XI_OW(C, j)] = xe_id(p->overwrite_src[sl]);
+        const int reader_rank = slot_rank;  // (xe_id may move slot_rank)
+        const int xe = xe_id(p->overwrite_src[sl]);
+        xt->xi[(size_t)t * XN + BR2_TILE_XI_OW(C, j)] = xe;
+        consume(xe, reader_rank);
     }
-    // the extra joints are evaluated by the CTA of their rod-two element, one COMPONENT per thread, by consecutive threads
-    // of its LAST warps: a warp executes the joint code once whichever of its lanes take part, so packing them keeps the
-    // other warps' issue slots free, and the CTA waits at the next barrier for one component's chain of loads only
+    xe_mask.resize(plan->n_xe, 0);
+    xt->xe_mask = xe_mask;
+    for (int r = 0; r < 8; ++r) plan->xb_count[r] = 0;
+    for (int xe = 0; xe < plan->n_xe; ++xe)
+        for (int r = 0; r < plan->n_ctas; ++r)
+            if (xe_mask[xe] & (1 << r)) ++plan->xb_count[r];
+    // the extra joints are evaluated one COMPONENT per thread, by consecutive threads of the CTA's LAST warps: a warp executes
+    // the joint code once whichever of its lanes take part, so packing them keeps the other warps' issue slots free
     {
         int used[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int xj = 0; xj < plan->n_xj; ++xj) {
-            const int rank = xt->xj_i[(size_t)xj * 12 + 3];
-            const int ct = plan->cta_threads[rank], warps = (ct + 31) / 32;
-            const int last = ct - (warps - 1) * 32;  // threads in use in the last warp
-            for (int comp = 0; comp < 3; ++comp) {
-                const int k = used[rank]++;  // k-th (joint, component) of this CTA: lanes 0.. of the last warp, then the one before, ...
-                const int t = (k < last) ? (warps - 1) * 32 + k : (warps - 2 - (k - last) / 32) * 32 + (k - last) % 32;
-                if (t < 0) return *why = "more extra joint components than threads", false;
-                xt->xi[(size_t)(rank * plan->xi_stride + t) * XN + BR2_TILE_XI_JOINT] = (xj << 2) | comp;
+            for (int rank = 0; rank < plan->n_ctas; ++rank) {
+                if (!(xj_ranks[xj] & (1 << rank))) continue;
+                const int ct = plan->cta_threads[rank], warps = (ct + 31) / 32;
+                const int last = ct - (warps - 1) * 32;  // threads in use in the last warp
+                for (int comp = 0; comp < 3; ++comp) {
+                    const int k = used[rank]++;  // k-th (joint, component) of this CTA: lanes 0.. of the last warp, then the one before, ...
+                    const int t = (k < last) ? (warps - 1) * 32 + k : (warps - 2 - (k - last) / 32) * 32 + (k - last) % 32;
+                    if (t < 0) return *why = "more extra joint components than threads", false;
+                    xt->xi[(size_t)(rank * plan->xi_stride + t) * XN + BR2_TILE_XI_JOINT] = (xj << 2) | comp;
+                }
             }
         }
     }
@@ -512,6 +532,7 @@ int br2_create(const br2_program *p, int device, br2_handle *out) {
             if (rc == BR2_OK) rc = upload(h, xt.xitems.data(), xt.xitems.size(), &h->tile.xitems);
             if (rc == BR2_OK) rc = upload(h, xt.xj_i.data(), xt.xj_i.size(), &h->tile.xj_i);
             if (rc == BR2_OK) rc = upload(h, xt.xj_d.data(), xt.xj_d.size(), &h->tile.xj_d);
+            if (rc == BR2_OK) rc = upload(h, xt.xe_mask.data(), xt.xe_mask.size(), &h->tile.xe_mask);
             if (rc != BR2_OK) {
                 br2_destroy(h);
                 return rc;
@@ -563,7 +584,6 @@ int br2_select_kernel(br2_handle h, int32_t variant) {
                     pick = kc;
                     break;
                 }
-            if (BR2_TILE_PARK == 2 && need < kTileLeanKernel.threads && !getenv("BR2_TILE_NO_LEAN")) pick = kTileLeanKernel;
         }
     } else {
         for (const KernelChoice &kc : kKernels[variant])
@@ -576,12 +596,10 @@ int br2_select_kernel(br2_handle h, int32_t variant) {
     size_t smem;
     if (variant == 0)
         smem = sizeof(double) * (30 * S + 9 * (size_t)h->t.n_joints + 32);
-    else if (variant == 3 && pick.fn == kTileLeanKernel.fn)
-        smem = sizeof(double) * (size_t)br2::TileSmem<BR2_TILE_C, 1, true>::ROWS_END * (size_t)pick.threads;  // (NT = 1: rows per thread)
-    else if (variant == 3)
+    else if (variant == 3)  // rows, then the extra-joint area (layout: TileSmem)
         smem = sizeof(double) * ((size_t)br2::TileSmem<BR2_TILE_C, 0>::ROWS_END * (size_t)(pick.threads + 1) +
-                                 25 * (size_t)h->tile.n_xe + (3 + 8 + 6) * (size_t)h->tile.n_xj +
-                                 ((size_t)h->tile.n_xitems + 1) / 2);
+                                 2 * br2::TileSmem<BR2_TILE_C, 0>::EXW * (size_t)h->tile.n_xe + (4 + 8 + 4) * (size_t)h->tile.n_xj +
+                                 ((size_t)h->tile.n_xe + 1) / 2 + ((size_t)h->tile.n_xitems + 1) / 2);
     else
     {
         // fixed part: 45 T doubles + two [3][T+8] accumulators + O1 (T ints); tail (omega, extra-joint rows,
@@ -618,21 +636,6 @@ int br2_select_kernel(br2_handle h, int32_t variant) {
         int blocks = 0, sms = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, (const void *)pick.fn, pick.threads, smem));
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
-        if ((BR2_TILE_PARK && pick.threads == 64) || pick.fn == kTileLeanKernel.fn) {
-            // the occupancy calculator answers 1 for a kernel that allocates tensor memory; the hardware co-schedules as
-            // many CTAs as registers, shared memory and the 512 tensor-memory columns allow (profiles/probes/tmem_scratch_probe.cu)
-            cudaFuncAttributes fa;
-            CUDA_TRY(cudaFuncGetAttributes(&fa, (const void *)pick.fn));
-            int regs_sm = 0, smem_sm = 0;
-            CUDA_TRY(cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, h->device));
-            CUDA_TRY(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device));
-            const int warp_regs = ((fa.numRegs + 7) / 8) * 8 * 32, warps_cta = pick.threads / 32;
-            const int by_regs = 4 * ((regs_sm / 4) / warp_regs) / warps_cta;  // the register file is split over four sub-partitions
-            const int by_smem = (int)((size_t)smem_sm / (smem + fa.sharedSizeBytes + 1024));
-            const int by_tmem = 512 / br2::kTileParkCols;
-            blocks = by_regs < by_smem ? by_regs : by_smem;
-            if (by_tmem < blocks) blocks = by_tmem;
-        }
         if (blocks < 1) return fail(BR2_ELIMIT, "the tile kernel does not fit on an SM");
         h->tile_capacity = blocks * sms;
     }

@@ -45,11 +45,14 @@ struct TilePlan {
     double jd[BR2_TILE_MAX_RODS][8];        // {dv2[3], offset/2} of the joints the rod owns, {dv1[3], offset/2} as rod one
     // "extra" joints: tip-to-base joints between segments (TipToTipStraightJoint).  Few per
     // assembly; evaluated by designated threads from data their elements publish; none for single-segment assemblies.
-    int n_xe, n_xj;                         // elements that publish director / omega / radius; extra joints
+    int n_xe, n_xj;                         // elements that publish director / omega / radius / node sums; extra joints
     int n_xitems;                           // entries of `xitems`
+    int xb_count[8];                        // per rank: published elements whose data the CTA consumes (arrivals per step on its XB barrier)
+    const int *xe_mask;                     // [n_xe] bit r: the CTA of rank r consumes the element's data (device)
     const int *xi;                          // [n_ctas][xi_stride][C + 1] per thread: packed info of each slot (published xe + 1
                                             // | overwrite source xe + 1 << 8 | node items << 16 | first item << 20), then the
-                                            // extra joint the thread evaluates or -1 (device)
+                                            // extra joint component the thread evaluates (joint << 2 | component) or -1 (device).
+                                            // A joint between two CTAs of a cluster is evaluated by BOTH (each for its own nodes)
     const int *xitems;                      // node items (joint << 1 | sign), grouped per slot (device; copied to shared memory)
     const int *xj_i;                        // [n_xj][12] rank1, row1, j1, rank2, row2, j2 of the joined elements; xe of Q1, Q2, radius one, radius two
     const double *xj_d;                     // [n_xj][8] k, nu, l1[3], l2[3]
@@ -74,7 +77,7 @@ struct StepParams {
     int only_flagged;   // generic kernel: integrate only instances whose status is set, then clear it
     unsigned long long *replays;  // counts instance-launches redone by the exact path
     double uni[BR2_FC_COUNT];  // uniform copy of fast_c (all element slots identical), constant bank
-    double kd[12];             // loop-invariant products of uni and dt for the 128-register tile kernel (br2_step fills them)
+    double kd[12];             // loop-invariant products of uni and dt for the tile kernel (br2_step fills them)
     TilePlan tile;
     // launch chunking (tile kernel's work queue; the exact-path replay resumes at the chunk that failed:
     // status = 1 + chunk).  One chunk = the whole launch for the other kernels.

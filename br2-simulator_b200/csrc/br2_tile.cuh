@@ -16,6 +16,18 @@
 // instruction streams for the fp64 pipe (8-cycle dependent-issue latency, 2 cycles per warp instruction:
 // profiles/probes/dfma_latency_probe.cu).
 //
+// Synchronisation (round 2).  A step has three exchange points (first node / element -> element quantities -> joint
+// forces and couples -> dynamic step).  With one large CTA per SM -- the multi-segment and the cluster kernels -- a
+// CTA-wide barrier at each of them left the SM idle while the last warp arrived (ncu, cluster kernel: 1.38 barrier +
+// 0.40 membar stall cycles per issued instruction).  The barriers are now SPLIT-PHASE mbarriers (kSplit): a warp
+// arrives as soon as it has published, goes on with work that needs nobody else's data (slot 0's element quantities
+// after the first, all Voronoi couples after the second, the tip-to-base joints and the damper exponentials after the
+// third) and waits only where it reads a neighbour's rows.  Tip-to-base joints between segments no longer use the
+// hardware cluster barrier at all: the few elements involved PUSH director, omega, radius and node sums into the
+// consuming CTAs' shared memory (distributed shared memory stores) and arrive on the consumer's mbarrier with
+// release.cluster; both CTAs of an interface evaluate its joints themselves (bit-identical arithmetic), so the forces
+// never travel back.  The small single-segment kernel (two warps per CTA, six CTAs per SM) keeps __syncthreads.
+//
 // Semantics are those of br2_fast.cuh / br2_generic.cuh; the optimistic-series
 // protocol is the same: a CTA that leaves a series' validity range flags its instance and does not write back;
 // the exact-path pass launched right behind on the stream redoes the instance from the chunk that failed (the generic
@@ -24,7 +36,7 @@
 // Work distribution: persistent CTAs (or clusters) pull (chunk, instance) items off one queue -- see the kernel.
 // Template flags: kExtras = tip-to-base joints between segments (director overwrites included); kCluster = one CTA per
 // group of ring-connected rods, a thread-block cluster per instance (assemblies beyond one SM's registers);
-// kExact = IEEE / libm arithmetic without validity ranges.
+// kExact = IEEE / libm arithmetic without validity ranges; kSplit = split-phase mbarriers instead of __syncthreads.
 //
 // Applicability (decided on the host, br2_cuda.cu: make_tile_plan): fast-path assembly with uniform element
 // constants, every surface joint connects equal element indices of two rods, all joints of a rod pair share one
@@ -47,42 +59,67 @@ __device__ __forceinline__ void tile_sync() {
     else
         __syncthreads();
 }
-// split-phase cluster barrier: arrive (release) ... independent work ... wait (acquire)
-template <bool kCluster>
-__device__ __forceinline__ void tile_cluster_arrive() {
-    if (kCluster) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-}
-template <bool kCluster>
-__device__ __forceinline__ void tile_cluster_wait() {
-    if (kCluster) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 template <bool kCluster, typename T>
 __device__ __forceinline__ T *tile_peer(T *local, int rank) {
     if (kCluster) return cooperative_groups::this_cluster().map_shared_rank(local, rank);
     return local;
 }
 
-
-// Tensor memory as per-thread scratch (kPark kernels).  This kernel has no use for the tensor cores, so the SM's 256 KB of
-// tensor memory is idle; tcgen05.st / tcgen05.ld (32x32b shape: thread i of a warp <-> lane 32 * (warp % 4) + i, one
-// 32-bit column per register) move registers there and back without touching the shared-memory crossbar or the L1
-// (profiles/probes/tmem_scratch_probe.cu: 39-47 cycle round trip).  Values that only cross a phase are parked there so
-// that the phase in between has their registers for instruction-level parallelism.
-__device__ __forceinline__ void tmem_park(uint32_t addr, double v) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(__double2loint(v)), "r"(__double2hiint(v)) : "memory");
+// ---- split-phase barriers (mbarrier objects in shared memory) ------------------------------------------------------
+// One elected lane per warp arrives (release at CTA scope; __syncwarp orders the other lanes' stores before it), every
+// lane waits on the phase parity (of the step counter: every barrier completes once per step).  TRYWAIT suspends the warp in hardware instead of spinning.
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ double tmem_fetch(uint32_t addr) {
-    int lo, hi;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(addr) : "memory");
-    return __hiloint2double(hi, lo);
+__device__ __forceinline__ void mbar_arrive_warp(uint32_t bar) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-constexpr int kTileParkCols = 64;  // 32-bit columns per CTA (power of two >= 32): 32 doubles per thread
-// kPark == 2 (C = 2): which double lives where.  x[0] and Q[0] are not parked: their published rows (XF, QF) are the copy.
-constexpr int kPkX1 = 0, kPkV = 3, kPkW = 9, kPkQ1 = 15, kPkTA = 24;  // x[1] 3 | v 6 | w 6 | Q[1] 9 | actuation torque 6 = 30
-#define TM_AT(idx) (tm + 2 * (idx))
-
+__device__ __forceinline__ void mbar_arrive_thread(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive on the same barrier of CTA `rank` of the cluster, after this thread's (remote) stores: release at cluster scope
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, int rank) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+        "}" ::"r"(bar), "r"(rank) : "memory");
+}
+template <bool kClusterScope>
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (kClusterScope)
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "WAIT_LOOP:\n"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra WAIT_DONE;\n"
+            "bra WAIT_LOOP;\n"
+            "WAIT_DONE:\n"
+            "}" ::"r"(bar), "r"(parity) : "memory");
+    else
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "WAIT_LOOP:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra WAIT_DONE;\n"
+            "bra WAIT_LOOP;\n"
+            "WAIT_DONE:\n"
+            "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// the step's exchange points: arrive after publishing, wait before reading; kSplit = false degenerates to one
+// __syncthreads at the wait
+struct TileBars {
+    uint32_t b1, b2, b3, b4, xb;  // shared-memory addresses: three phase barriers, joint forces ready, pushed data (xb, xb + 8 by step parity)
+};
+template <bool kSplit>
+__device__ __forceinline__ void tile_arrive(uint32_t bar) {
+    if (kSplit) mbar_arrive_warp(bar);
+}
 // Where the per-thread constants live was measured (single_br2 x 4096, el-steps/s): joint direction vectors from the
 // constant bank indexed by rod 3.05e10, from a per-rod shared-memory table 2.96e10; actuation torques in shared-memory
 // rows 3.05e10, in registers 2.92e10 (every register kept across the step costs instruction-level parallelism).
@@ -129,16 +166,13 @@ struct TileMath {
     }
 };
 
-template <int C, int NT, bool kLean = false>
+template <int C, int NT>
 struct TileSmem {
     // rows of every exchange array: thread t owns row t + 1; row 0 is all zeros and never written.  A run without a
     // predecessor reads row (own - 1): row 0, or the previous rod's last run, whose "last element" entries are zero because
     // its last slot is the node-only slot.  A run without a successor reads its own row (the result is masked).  Both
     // keep a half-warp's addresses contiguous, i.e. free of bank conflicts.
-    // kLean (the 128-register kernel, eight CTAs per SM): NT rows -- the CTA's idle threads (at least one: plan requirement)
-    // take row 0 as their own, where their all-zero state publishes zeros in every array whose row 0 is read as "nothing
-    // there" -- and no actuation rows (tensor memory holds them).
-    static constexpr int R = kLean ? NT : NT + 1;
+    static constexpr int R = NT + 1;
     static constexpr int XF = 0;                  // [3][R]    position of the run's first node
     static constexpr int VF = XF + 3 * R;         // [3][R]    velocity of the run's first node
     static constexpr int QF = VF + 3 * R;         // [9][R]    director of the run's first element
@@ -153,10 +187,17 @@ struct TileSmem {
     static constexpr int FS = HF + 3 * C * R;     // [C][3][R] spring part k d of that joint (the torques use only this)
     static constexpr int ZERO_END = FS + 3 * C * R;  // everything above is zeroed at launch
     static constexpr int TA = ZERO_END;           // [C][3][R] actuation torque at full ramp (material frame)
-    static constexpr int ROWS_END = kLean ? TA : TA + 3 * C * R;
-    // after the rows (host: TileSmem<C, 0>::ROWS_END * (threads + 1) words), the extra-joint area
-    static constexpr int EX = ROWS_END;           // extra joints (rank 0's copy is the live one in a cluster):
-                                                  // EXQ [2][9][n_xe], EXW [2][3][n_xe] (by step parity), EXR [n_xe], JF [3][n_xj]
+    static constexpr int ROWS_END = TA + 3 * C * R;
+    // after the rows (host: TileSmem<C, 0>::ROWS_END * (threads + 1) words), the extra-joint area of a kExtras kernel;
+    // every CTA has its own complete copy, filled by the elements' owners (pushes through distributed shared memory):
+    //   EXD [2][n_xe][20]  by step parity, per published element: director 9 | omega 3 | radius | x_k + x_{k+1} 3 | v_k + v_{k+1} 3
+    //   JF  [n_xj][4]      half force of each extra joint this CTA evaluates
+    //   XJD [n_xj][8]      k, nu, l1[3], l2[3]   (point force: F[3], ramp_up_time)
+    //   XJI [n_xj][8] int  published element of: rod one's element, rod two's element, director one, director two; type
+    //   XPM [n_xe]    int  bit r set: the CTA of cluster rank r consumes the element's data
+    //   XIT [n_xitems] int node items (joint << 1 | sign)
+    static constexpr int EX = ROWS_END;
+    static constexpr int EXW = 20;                // doubles per published element
 };
 
 constexpr int TILE_F_VALID = 1, TILE_F_ELEM = 2, TILE_F_VOR = 4, TILE_F_ZERO_V = 8, TILE_F_ZERO_W = 16, TILE_F_OWN = 32,
@@ -205,22 +246,44 @@ __device__ __forceinline__ TileWhere tile_where(const StepParams &p, int t, long
     return wh;
 }
 
+// exp(strain ln c_r) of the rotational damper (Appendix A.5): one exponential per element for a round section
+template <bool kExact>
+__device__ __forceinline__ void tile_damper_exponentials(const StepParams &p, double len, int flags, double (&out)[3], int &bad) {
+    using M = TileMath<kExact>;
+    const double dil = len * p.uni[BR2_FC_INV_REST_LEN];
+    const double strain = (flags & TILE_F_ELEM) ? dil - 1.0 : 0.0;
+    if (p.tile.round_section) {
+        const double e2 = strain * p.uni[BR2_FC_LN_CR + 2];
+        if (!kExact) bad |= (e2 * e2 <= BR2_E2_MAX) ? 0 : 4;
+        out[0] = M::exp(e2);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double e = strain * p.uni[BR2_FC_LN_CR + i];
+            if (!kExact) bad |= (e * e <= BR2_E2_MAX) ? 0 : 4;
+            out[i] = M::exp(e);
+        }
+    }
+}
+
 // One PositionVerlet step of a thread's run.  kEnd: last step of a chunk (ends with a single kinematic half step
 // instead of the fused pair, so the state is a whole-step state); kLast: last step of the launch (also reports
-// the callback quantities).
-template <int C, int NT, bool kEnd, bool kLast, bool kExtras, bool kCluster, bool kExact, int kPark>
+// the callback quantities).  gstep: steps this CTA has executed since the kernel started (phase parity of the
+// barriers; its low bit selects the buffer of the pushed tip-to-base data).
+template <int C, int NT, bool kEnd, bool kLast, bool kExtras, bool kCluster, bool kExact, bool kSplit>
 __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileThread<C> &th, double time_mid, long long b,
-                                          int rank, int parity, uint32_t tm) {
-    using L = TileSmem<C, NT, kPark == 2>;
+                                          int rank, int gstep, const TileBars &bars) {
+    using L = TileSmem<C, NT>;
     constexpr int R = L::R;
-    static_assert(kExtras || !kCluster, "the cluster kernels carry the extra-joint code (their barrier phases live in it)");
+    static_assert(C >= 2, "slot 0's element must lie inside the thread's run");
+    static_assert(kExtras || !kCluster, "the cluster kernels carry the extra-joint code");
+    static_assert(kSplit || !kExtras, "the extra-joint code needs the split-phase barriers (a fourth exchange point)");
     using M = TileMath<kExact>;
     const DevTables &tb = p.t;
     const int t = th.t;
     const double dt = p.dt, hdt = p.kd[11];
     // loop-invariant products of the uniform constants and dt come from the constant bank (StepParams::kd, filled by br2_step
-    // with the very expressions quoted here) instead of being hoisted into registers that then spill: +2-3 % on the
-    // multi-segment kernels, neutral on the single-segment one, and what lets the 128-register build run without spills
+    // with the very expressions quoted here) instead of being hoisted into registers that then spill
 #define KD(idx, expr) p.kd[(idx)]
     TileWhere wh{};
     if (kLast) wh = tile_where<C>(p, (int)threadIdx.x, b, rank);
@@ -228,7 +291,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
     double *const inst = wh.inst;
 #define UNI(idx) p.uni[(idx)]
 #define JDV(i) p.tile.jd[th.rod][(i)]
-#define TAV(j, i) sm[L::TA + (3 * (j) + (i)) * (kPark == 2 ? 0 : R) + t]  // (kPark == 2: unused, tensor memory holds it)
+#define TAV(j, i) sm[L::TA + (3 * (j) + (i)) * R + t]
     double (&x)[C][3] = th.x;
     double (&v)[C][3] = th.v;
     double (&Q)[C][9] = th.Q;
@@ -237,7 +300,28 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
     // reported quantities (kLast only)
     double r_fint[C][3], r_fext[C][3];
 
+    // extra joints (tip-to-base joints between segments; kExtras kernels only): a handful of threads involved
+    const int n_xe = kExtras ? p.tile.n_xe : 0, n_xj = kExtras ? p.tile.n_xj : 0;
+    const int buf = gstep & 1;
+    double *const EXD = sm + L::EX + buf * (L::EXW * n_xe);           // this step's buffer of pushed element data
+    double *const JF = sm + L::EX + 2 * L::EXW * n_xe;
+    const double *const XJD = JF + 4 * n_xj;
+    const int *const XJI = (const int *)(XJD + 8 * n_xj), *const XPM = XJI + 8 * n_xj, *const XIT = XPM + ((n_xe + 1) & ~1);
+    const uint32_t xbar = bars.xb + 8u * (uint32_t)buf, xparity = ((uint32_t)gstep >> 1) & 1u;
+
     // =============================== P1: publish the run's first node / element ==============
+    // (split-phase kernels: the first element's length with them -- the previous run's last Voronoi cell needs it, and this
+    // way every Voronoi cell is computable before the second exchange point is waited for)
+    double d0[3], len0, rs0;
+    if (kSplit) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) d0[i] = x[1][i] - x[0][i];
+        double d2 = fma(d0[0], d0[0], fma(d0[1], d0[1], d0[2] * d0[2]));
+        d2 = (th.fl[0] & TILE_F_ELEM) ? d2 : 1.0;  // keeps the node-only slot finite
+        rs0 = M::rsqrt(d2);
+        len0 = fma(d2, rs0, BR2_EPS14);
+        sm[L::LF + t] = len0;
+    }
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         sm[L::XF + i * R + t] = x[0][i];
@@ -245,54 +329,42 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
     }
 #pragma unroll
     for (int i = 0; i < 9; ++i) sm[L::QF + i * R + t] = Q[0][i];
-    // extra joints (tip-to-base joints between segments; kExtras kernels only): a handful of threads involved
-    const int n_xe = kExtras ? p.tile.n_xe : 0, n_xj = kExtras ? p.tile.n_xj : 0;
-    // director / omega rows are double-buffered by step parity: the overwrite in P4 reads them while a faster
-    // thread may already be publishing the next step's values
-    double *const EX0 = tile_peer<kCluster>(sm + L::EX, 0);
-    double *const EXQ = EX0 + parity * 9 * n_xe, *const EXW = EX0 + 18 * n_xe + parity * 3 * n_xe;
-    double *const EXR = EX0 + 24 * n_xe, *const JF = EXR + n_xe;
-    // read-only copies of the joint tables (every CTA has its own): xj_d [n_xj][8], xj_i [n_xj][12], node items
-    const double *const XJD = sm + L::EX + 25 * n_xe + 3 * n_xj;
-    const int *const XJI = (const int *)(XJD + 8 * n_xj), *const XIT = XJI + 12 * n_xj;
-    if (kExtras) {
-#pragma unroll
-        for (int j = 0; j < C; ++j) {
-            const int pub = (th.xinfo[j] & 0xFF) - 1;
-            if (pub >= 0) {
-#pragma unroll
-                for (int i = 0; i < 9; ++i) EXQ[i * n_xe + pub] = Q[j][i];
-#pragma unroll
-                for (int i = 0; i < 3; ++i) EXW[i * n_xe + pub] = w[j][i];
-            }
-        }
-    }
-    __syncthreads();  // B1 (the remote director rows become visible with the cluster barrier after P2)
+    tile_arrive<kSplit>(bars.b1);
+    if (!kSplit) __syncthreads();  // B1
 
     // =============================== P2: element quantities ==================================
+    // slot 0 .. C-2 need nobody else's data; the run's last slot reads the next run's first node
     double len[C], ra2[C];
     double tint[C][3];   // internal couple on element k (complete except for the previous run's last cell)
     {
         const double dtg[3] = {KD(0, dt * UNI(BR2_FC_CT) * UNI(BR2_FC_GRAVITY)), KD(1, dt * UNI(BR2_FC_CT) * UNI(BR2_FC_GRAVITY + 1)),
                                KD(2, dt * UNI(BR2_FC_CT) * UNI(BR2_FC_GRAVITY + 2))};
         double skp[3];  // the previous element's Q^T n_L / e
+        double radx[C];
 #pragma unroll
         for (int j = 0; j < C; ++j) {
+            if (kSplit && j == C - 1) mbar_wait<false>(bars.b1, (uint32_t)gstep & 1u);  // B1
             const bool elem = th.fl[j] & TILE_F_ELEM;
             double d[3], dv[3];
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 const double xn = (j + 1 < C) ? x[(j + 1) % C][i] : sm[L::XF + i * R + th.tn];
                 const double vn = (j + 1 < C) ? v[(j + 1) % C][i] : sm[L::VF + i * R + th.tn];
-                d[i] = xn - x[j][i];
+                d[i] = (kSplit && j == 0) ? d0[i] : xn - x[j][i];
                 dv[i] = vn - v[j][i];
                 sm[L::PC + (3 * j + i) * R + t] = xn + x[j][i];
                 sm[L::PV + (3 * j + i) * R + t] = vn + v[j][i];
             }
-            double d2 = fma(d[0], d[0], fma(d[1], d[1], d[2] * d[2]));
-            d2 = elem ? d2 : 1.0;  // keeps the node-only slot finite
-            const double rs = M::rsqrt(d2);
-            len[j] = fma(d2, rs, BR2_EPS14);
+            double rs;
+            if (kSplit && j == 0) {
+                rs = rs0;
+                len[j] = len0;
+            } else {
+                double d2 = fma(d[0], d[0], fma(d[1], d[1], d[2] * d[2]));
+                d2 = elem ? d2 : 1.0;  // keeps the node-only slot finite
+                rs = M::rsqrt(d2);
+                len[j] = fma(d2, rs, BR2_EPS14);
+            }
             const double inv_len = rs * fma(-BR2_EPS14, rs, 1.0);  // 1/(|d| + 1e-14), second order 1e-23
             const double rest_len = UNI(BR2_FC_REST_LEN), inv_rest_len = UNI(BR2_FC_INV_REST_LEN);
             const double r2 = UNI(BR2_FC_VOL_OVER_PI) * inv_len;
@@ -304,10 +376,6 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
             // 3.12e10 against 3.17e10 el-steps/s: ptxas' schedule, not the instruction count, sets this kernel's pace.)
             const double rse = M::rsqrt_lo(dil);
             ra2[j] = fma(JDV(3), rse, rad);
-            if (kExtras) {
-                const int pub = (th.xinfo[j] & 0xFF) - 1;
-                if (pub >= 0) EXR[pub] = rad;
-            }
             if (kLast && elem) {
                 inst[15 * np1 + 21 * n + wh.k0 + j] = len[j];
                 inst[15 * np1 + 22 * n + wh.k0 + j] = dil;
@@ -350,48 +418,46 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 #pragma unroll
             for (int i = 0; i < 3; ++i)
                 sm[L::PR + (3 * j + i) * R + t] = fma(Q[j][i], a0, Q[j][3 + i] * a1);  // Q^T dv1 (r + o)
-            if (kPark == 2) {
-                // done with this slot until P4: its velocity and angular velocity go to tensor memory; slot 0 makes room for
-                // slot 1's director (parked since the end of the previous step) -- Q[0] comes back from its published row in P3
+            if (kExtras) radx[j] = rad;  // (an element of a tip-to-base joint pushes it below)
+        }
+        if (!kSplit) sm[L::LF + t] = len[0];
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    tmem_park(TM_AT(kPkV + 3 * j + i), v[j][i]);
-                    tmem_park(TM_AT(kPkW + 3 * j + i), w[j][i]);
-                }
-                if (j == 0) {
-                    tmem_wait_st();
+        for (int i = 0; i < 3; ++i) sm[L::SKL + i * R + t] = skp[i];
+        if (kExtras) {
+            // push what the tip-to-base joints need from my elements into every consuming CTA's buffer of this step's parity
+            // (start-of-step director and omega: the overwrite in P4 comes later).  After B1 on purpose: every warp of this CTA
+            // has then finished the previous step, so a peer that races ahead on my data cannot overwrite a buffer still read.
 #pragma unroll
-                    for (int i = 0; i < 9; ++i) Q[1][i] = tmem_fetch(TM_AT(kPkQ1 + i));
-                    tmem_wait_ld();
-                } else {
+            for (int j = 0; j < C; ++j) {
+                const int pub = (th.xinfo[j] & 0xFF) - 1;
+                if (pub >= 0) {
+                    const int mask = XPM[pub];
+                    for (int r = 0; r < (kCluster ? p.tile.n_ctas : 1); ++r) {
+                        if (!((mask >> r) & 1)) continue;
+                        double *dst = tile_peer<kCluster>(EXD, r) + pub * L::EXW;
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) tmem_park(TM_AT(kPkX1 + i), x[1][i]);
+                        for (int i = 0; i < 9; ++i) dst[i] = Q[j][i];
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            dst[9 + i] = w[j][i];
+                            dst[13 + i] = sm[L::PC + (3 * j + i) * R + t];
+                            dst[16 + i] = sm[L::PV + (3 * j + i) * R + t];
+                        }
+                        dst[12] = radx[j];
+                        if (kCluster)
+                            mbar_arrive_remote(xbar, r);
+                        else
+                            mbar_arrive_thread(xbar);
+                    }
                 }
             }
         }
-        sm[L::LF + t] = len[0];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) sm[L::SKL + i * R + t] = skp[i];
     }
-    if (kPark == 1) {  // positions and angular velocities are not needed before P4: their registers serve P3
-#pragma unroll
-        for (int j = 0; j < C; ++j)
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                tmem_park(tm + 2 * (3 * j + i), x[j][i]);
-                tmem_park(tm + 2 * (3 * C + 3 * j + i), w[j][i]);
-            }
-    }
-    __syncthreads();  // B2
-    // cluster: the other CTAs' rows are needed only by the tip-to-base joints at the end of P3 -- arrive now, wait there
-    tile_cluster_arrive<kCluster>();
+    tile_arrive<kSplit>(bars.b2);
+    if (!kSplit) __syncthreads();  // B2
 
-    // =============================== P3: Voronoi couples and own joints ======================
+    // =============================== P3a: Voronoi couples (own registers + rows published before B1) ==========
     double tw[C][3];  // world-frame joint torque on my element (own joint now, rod-one joint in P4)
-    if (kPark == 2) {
-#pragma unroll
-        for (int i = 0; i < 9; ++i) Q[0][i] = sm[L::QF + i * R + t];  // my own published row
-    }
     {
         double ap[3], cp[3];  // previous cell's A and C
 #pragma unroll
@@ -437,7 +503,10 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 #pragma unroll
         for (int i = 0; i < 3; ++i) sm[L::ML + i * R + t] = fma(0.5, cp[i], -ap[i]);
     }
-    // own joints (Appendix A.7): my element is rod two; rod one's contribution comes from its published rows
+    if (kSplit) mbar_wait<false>(bars.b2, (uint32_t)gstep & 1u);  // B2
+
+    // =============================== P3b: own joints (Appendix A.7) ==========================
+    // my element is rod two; rod one's contribution comes from its published rows
 #pragma unroll
     for (int j = 0; j < C; ++j) {
         const bool own = th.fl[j] & TILE_F_OWN;
@@ -448,13 +517,8 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             rd2[i] = fma(Q[j][i], b0, Q[j][3 + i] * b1);  // Q^T dv2 (r + o)
-            double xs;  // x_k + x_{k+1} of my element
-            if (kPark) {
-                xs = sm[L::PC + (3 * j + i) * R + t];
-            } else {
-                const double xn = (j + 1 < C) ? x[(j + 1) % C][i] : sm[L::XF + i * R + th.tn];
-                xs = xn + x[j][i];
-            }
+            const double xn = (j + 1 < C) ? x[(j + 1) % C][i] : sm[L::XF + i * R + th.tn];
+            const double xs = xn + x[j][i];  // x_k + x_{k+1} of my element
             cd2[i] = xs - sm[L::PC + (3 * j + i) * R + th.t1];       // 2 (c2 - c1)
             const double g = rd2[i] - sm[L::PR + (3 * j + i) * R + th.t1];
             // (c2 + rd2) - (c1 + rd1), rounded to 12 decimals like np.round_(x, 12)
@@ -482,10 +546,8 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
             sm[L::FS + (3 * j + i) * R + t] = fs[i];
             // rod two takes -F: half on each node of the element (node k+1 of the run's last element belongs
             // to the next thread, which reads HF)
-            if (kPark != 2) {  // (kPark == 2: the velocities are parked; P4 applies this force from the HF row)
-                v[j][i] = fma(-th.dtmc[j], hf, v[j][i]);
-                if (j + 1 < C) v[(j + 1) % C][i] = fma(-th.dtmc[(j + 1) % C], hf, v[(j + 1) % C][i]);
-            }
+            v[j][i] = fma(-th.dtmc[j], hf, v[j][i]);
+            if (j + 1 < C) v[(j + 1) % C][i] = fma(-th.dtmc[(j + 1) % C], hf, v[(j + 1) % C][i]);
             if (kLast) {
                 r_fext[j][i] = (j == 0) ? -hf : r_fext[j][i] - hf;
                 if (j + 1 < C) r_fext[(j + 1) % C][i] = -hf;
@@ -496,80 +558,51 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
         tw[j][1] = fma(rd2[0], fs[2], -rd2[2] * fs[0]);
         tw[j][2] = fma(rd2[1], fs[0], -rd2[0] * fs[1]);
     }
-    // one tip-to-base joint per designated thread (Appendix A.8): un-rounded spring between the two element
-    // surfaces along fixed material directions, un-projected damping, no torque
-    tile_cluster_wait<kCluster>();
-    if (kExtras && th.xjoint >= 0) {
-        // one COMPONENT of one joint per thread (three consecutive lanes per joint): the warp that holds them is late at
-        // the next barrier by one component's chain of loads, not three
-        const int xj = th.xjoint >> 2, i = th.xjoint & 3;
-        {
-            const int *ji = XJI + xj * 12;
+    tile_arrive<kSplit>(bars.b3);
+
+    // ---- work that needs nobody's rows, while the others finish their joints -----------------------------------
+    // one tip-to-base joint COMPONENT per designated thread (Appendix A.8: un-rounded spring between the two element
+    // surfaces along fixed material directions, un-projected damping, no torque), from the pushed data of this step
+    if (kExtras) {
+        if (th.xjoint >= 0) {
+            const int xj = th.xjoint >> 2, i = th.xjoint & 3;
+            const int2 ja = *(const int2 *)(XJI + xj * 8), jb = *(const int2 *)(XJI + xj * 8 + 2);
             const double *jd = XJD + xj * 8;
-            if (ji[10] == 1) {
+            if (XJI[xj * 8 + 4] == 1) {
                 // point force (custom_activation.PointForces): F min(1, t / ramp_up_time) on one node
                 const double fac = fmin(1.0, time_mid / jd[3]);
-                JF[i * n_xj + xj] = jd[i] * fac;
+                JF[xj * 4 + i] = jd[i] * fac;
             } else {
-                const double *const sm1 = tile_peer<kCluster>(sm, ji[0]), *const sm2 = tile_peer<kCluster>(sm, ji[3]);
-                const int row1 = ji[1] + 1, j1 = ji[2], row2 = ji[4] + 1, j2 = ji[5], q1 = ji[6], q2 = ji[7];
+                mbar_wait<kCluster>(xbar, xparity);  // everything pushed for this step has landed
+                const double *e1 = EXD + ja.x * L::EXW, *e2 = EXD + ja.y * L::EXW;
+                const double *q1 = EXD + jb.x * L::EXW, *q2 = EXD + jb.y * L::EXW;
                 const double kj = jd[0], nuj = jd[1];
-                const double r1 = EXR[ji[8]], r2 = EXR[ji[9]];
-                const double c1 = 0.5 * sm1[L::PC + (3 * j1 + i) * R + row1], c2 = 0.5 * sm2[L::PC + (3 * j2 + i) * R + row2];
-                const double vrel = 0.5 * sm2[L::PV + (3 * j2 + i) * R + row2] - 0.5 * sm1[L::PV + (3 * j1 + i) * R + row1];
-                const double a1 = fma(EXQ[i * n_xe + q1], jd[2], fma(EXQ[(3 + i) * n_xe + q1], jd[3], EXQ[(6 + i) * n_xe + q1] * jd[4])) * r1;
-                const double a2 = fma(EXQ[i * n_xe + q2], jd[5], fma(EXQ[(3 + i) * n_xe + q2], jd[6], EXQ[(6 + i) * n_xe + q2] * jd[7])) * r2;
+                const double c1 = 0.5 * e1[13 + i], c2 = 0.5 * e2[13 + i];
+                const double vrel = 0.5 * e2[16 + i] - 0.5 * e1[16 + i];
+                const double a1 = fma(q1[i], jd[2], fma(q1[3 + i], jd[3], q1[6 + i] * jd[4])) * e1[12];
+                const double a2 = fma(q2[i], jd[5], fma(q2[3 + i], jd[6], q2[6 + i] * jd[7])) * e2[12];
                 const double gap = (c2 + a2) - (c1 + a1);
-                JF[i * n_xj + xj] = 0.5 * fma(kj, gap, -nuj * vrel);
+                JF[xj * 4 + i] = 0.5 * fma(kj, gap, -nuj * vrel);
             }
         }
+        mbar_arrive_warp(bars.b4);
     }
-    // cluster: the joint forces are gathered at the very end of P4 -- arrive now, wait there
-    tile_cluster_arrive<kCluster>();
-    __syncthreads();  // B3
+    // damper exponentials (element lengths are mine): before the wait when the barrier is split-phase
+    double dexp[C][3];
+    if (kSplit) {
+#pragma unroll
+        for (int j = 0; j < C; ++j) tile_damper_exponentials<kExact>(p, len[j], th.fl[j], dexp[j], th.bad);
+        mbar_wait<false>(bars.b3, (uint32_t)gstep & 1u);  // B3
+    } else {
+        __syncthreads();  // B3
+    }
 
     // =============================== P4: assemble, dynamic step ==============================
     {
-        if (kPark == 1) {
-            tmem_wait_st();
-#pragma unroll
-            for (int j = 0; j < C; ++j)
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    x[j][i] = tmem_fetch(tm + 2 * (3 * j + i));
-                    w[j][i] = tmem_fetch(tm + 2 * (3 * C + 3 * j + i));
-                }
-            tmem_wait_ld();
-        }
-        if (kPark == 2) {
-            tmem_wait_st();
-#pragma unroll
-            for (int j = 0; j < C; ++j)
-#pragma unroll
-                for (int i = 0; i < 3; ++i) v[j][i] = tmem_fetch(TM_AT(kPkV + 3 * j + i));
-            if (kLast) {  // the reporting step reads positions (soft-fix spring)
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    x[1][i] = tmem_fetch(TM_AT(kPkX1 + i));
-                    x[0][i] = sm[L::XF + i * R + t];
-                }
-            }
-            tmem_wait_ld();
-            // the force of the joints I own (rod two takes -F, half on each node of the element), deferred from P3
-#pragma unroll
-            for (int j = 0; j < C; ++j)
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const double hf = sm[L::HF + (3 * j + i) * R + t];
-                    v[j][i] = fma(-th.dtmc[j], hf, v[j][i]);
-                    if (j + 1 < C) v[(j + 1) % C][i] = fma(-th.dtmc[(j + 1) % C], hf, v[(j + 1) % C][i]);
-                }
-        }
-        if (kLast) tile_cluster_wait<kCluster>();  // the reporting step gathers them early (external forces are reported)
         const double ramp_raw = time_mid * tb.act_inv_ramp;
         const double ramp = (ramp_raw < 1.0) ? ramp_raw : 1.0;
         // what the previous run's last element contributes to my first node / element (rows: see TileSmem)
-        const int tprev = (kPark == 2) ? max(t - 1, 0) : t - 1, top = (th.to > 0) ? th.to - 1 : 0;  // (an idle thread of the lean layout sits in row 0)
+        const int tprev = t - 1, top = (th.to > 0) ? th.to - 1 : 0;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const double fp = sm[L::HF + (3 * (C - 1) + i) * R + top] - sm[L::HF + (3 * (C - 1) + i) * R + tprev];
@@ -585,15 +618,6 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
         for (int j = 0; j < C; ++j) {
             const int k = wh.k0 + j;
             double text[3];
-            double ta[3];
-            if (kPark == 2) {  // (fetching everything at the start of P4, or earlier than needed anywhere, was measured: the longer
-                               // live ranges spill, 2.94e10 against 3.00e10 el-steps/s)
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    w[j][i] = tmem_fetch(TM_AT(kPkW + 3 * j + i));
-                    ta[i] = tmem_fetch(TM_AT(kPkTA + 3 * j + i));
-                }
-            }
             {
                 double fso[3], rd1[3];
 #pragma unroll
@@ -617,18 +641,18 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 #pragma unroll
             for (int i = 0; i < 3; ++i)
                 text[i] = fma(Q[j][3 * i], tw[j][0], fma(Q[j][3 * i + 1], tw[j][1], Q[j][3 * i + 2] * tw[j][2]));
-            if (kPark == 2) tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 3; ++i) text[i] = fma((kPark == 2) ? ta[i] : TAV(j, i), ramp, text[i]);
+            for (int i = 0; i < 3; ++i) text[i] = fma(TAV(j, i), ramp, text[i]);
             if (kExtras && (th.xinfo[j] >> 8) != 0) {
                 if (kLast) {  // half forces of the extra joints on this node (every other step: after the rotation below)
                     const int cnt = (th.xinfo[j] >> 16) & 0xF, first = th.xinfo[j] >> 20;
+                    if (cnt) mbar_wait<false>(bars.b4, (uint32_t)gstep & 1u);
                     for (int q = 0; q < cnt; ++q) {
                         const int item = XIT[first + q];
                         const double sgn = (item & 1) ? -1.0 : 1.0;
 #pragma unroll
                         for (int i = 0; i < 3; ++i) {
-                            const double f = sgn * JF[i * n_xj + (item >> 1)];
+                            const double f = sgn * JF[(item >> 1) * 4 + i];
                             v[j][i] = fma(th.dtmc[j], f, v[j][i]);
                             r_fext[j][i] += f;
                         }
@@ -638,28 +662,24 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
                 // (after the surface joints above have used the old director); sources are start-of-step values
                 const int ow = ((th.xinfo[j] >> 8) & 0xFF) - 1;
                 if (ow >= 0) {
+                    mbar_wait<kCluster>(xbar, xparity);
+                    const double *src = EXD + ow * L::EXW;
 #pragma unroll
-                    for (int i = 0; i < 9; ++i) Q[j][i] = EXQ[i * n_xe + ow];
+                    for (int i = 0; i < 9; ++i) Q[j][i] = src[i];
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) w[j][i] = EXW[i * n_xe + ow];
+                    for (int i = 0; i < 3; ++i) w[j][i] = src[9 + i];
                 }
             }
             const double dil = len[j] * UNI(BR2_FC_INV_REST_LEN);
-            const double strain = (th.fl[j] & TILE_F_ELEM) ? dil - 1.0 : 0.0;
+            if (!kSplit) tile_damper_exponentials<kExact>(p, len[j], th.fl[j], dexp[j], th.bad);
             double damp[3];
             if (p.tile.round_section) {
-                const double e2 = strain * UNI(BR2_FC_LN_CR + 2);
-                if (!kExact) th.bad |= (e2 * e2 <= BR2_E2_MAX) ? 0 : 4;
-                const double ex = M::exp(e2);
+                const double ex = dexp[j][0];
                 damp[2] = UNI(BR2_FC_CR + 2) * ex;
                 damp[0] = damp[1] = UNI(BR2_FC_CR) * (ex * ex);
             } else {
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const double e = strain * UNI(BR2_FC_LN_CR + i);
-                    if (!kExact) th.bad |= (e * e <= BR2_E2_MAX) ? 0 : 4;
-                    damp[i] = UNI(BR2_FC_CR + i) * M::exp(e);
-                }
+                for (int i = 0; i < 3; ++i) damp[i] = UNI(BR2_FC_CR + i) * dexp[j][i];
             }
             double wnew[3];
 #pragma unroll
@@ -715,13 +735,13 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 #pragma unroll
         for (int j = 0; j < C; ++j) th.bad |= M::rotate(Q[j], w[j], hdt, hmult) ? 1 : 0;
         if (kExtras && !kLast) {
-            // half forces of the tip-to-base joints on my nodes -- last, so that a cluster's other CTAs had the whole of
-            // P4 to deliver them
-            tile_cluster_wait<kCluster>();
+            // half forces of the tip-to-base joints on my nodes -- last, so that their evaluation (by other warps, between
+            // B3's arrive and wait) has long finished
 #pragma unroll
             for (int j = 0; j < C; ++j) {
                 const int cnt = (th.xinfo[j] >> 16) & 0xF, first = th.xinfo[j] >> 20;
                 if (cnt) {
+                    mbar_wait<false>(bars.b4, (uint32_t)gstep & 1u);
                     // the first three items (a joined element's node has three: one per rod of the other segment) without a
                     // branch between them, so that their loads are in flight together; same order of summation as the loop
                     int item[3];
@@ -731,7 +751,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 #pragma unroll
                     for (int q = 0; q < 3; ++q)
 #pragma unroll
-                        for (int i = 0; i < 3; ++i) f[q][i] = JF[i * n_xj + (item[q] >> 1)];
+                        for (int i = 0; i < 3; ++i) f[q][i] = JF[(item[q] >> 1) * 4 + i];
 #pragma unroll
                     for (int q = 0; q < 3; ++q) {
                         const double sd = (item[q] & 1) ? -th.dtmc[j] : th.dtmc[j];
@@ -743,23 +763,9 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
                         const int it = XIT[first + q];
                         const double sgn = (it & 1) ? -1.0 : 1.0;
 #pragma unroll
-                        for (int i = 0; i < 3; ++i) v[j][i] = fma(th.dtmc[j] * sgn, JF[i * n_xj + (it >> 1)], v[j][i]);
+                        for (int i = 0; i < 3; ++i) v[j][i] = fma(th.dtmc[j] * sgn, JF[(it >> 1) * 4 + i], v[j][i]);
                     }
                 }
-            }
-        }
-        if (kPark == 2) {
-            // the rotated director of slot 1 waits in tensor memory until P2 has finished with slot 0; the positions come
-            // back: x[1] from tensor memory, x[0] from its published row (nobody has overwritten it: P1 of the next step is mine)
-#pragma unroll
-            for (int i = 0; i < 9; ++i) tmem_park(TM_AT(kPkQ1 + i), Q[1][i]);
-            if (!kLast) {
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    x[1][i] = tmem_fetch(TM_AT(kPkX1 + i));
-                    x[0][i] = sm[L::XF + i * R + t];
-                }
-                tmem_wait_ld();
             }
         }
 #pragma unroll
@@ -777,38 +783,45 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 #undef TAV
 }
 
-template <int C, int NT, int kMinBlocks, bool kExtras, bool kCluster, bool kExact, int kPark = 0>
+template <int C, int NT, int kMinBlocks, bool kExtras, bool kCluster, bool kExact, bool kSplit>
 __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __grid_constant__ StepParams p) {
-    static_assert(!kPark || (NT <= 128 && !kExtras), "register parking: one lane per thread, no divergent joint code");
-    using L = TileSmem<C, NT, kPark == 2>;
+    using L = TileSmem<C, NT>;
     constexpr int R = L::R;
     extern __shared__ double sm[];
     __shared__ long long s_item;
     __shared__ int s_chunk;
     __shared__ int s_why;
+    __shared__ unsigned long long s_bar[6];  // B1, B2, B3, B4 (joint forces ready), XB[2] (pushed element data, by step parity)
 
     const DevTables &tb = p.t;
     const TilePlan &tp = p.tile;
     const int t = threadIdx.x;
     // kCluster: the CTAs of a thread-block cluster integrate one instance together, one group of ring-connected
-    // rods (a segment) each; they meet at the step's barriers and exchange the tip-to-base joints' data through
-    // distributed shared memory.  The cluster, not the CTA, pulls work items.
+    // rods (a segment) each; they exchange the tip-to-base joints' data through distributed shared memory (pushes + remote
+    // mbarrier arrives, see tile_step) and meet at a cluster barrier only between work items.  The cluster, not the CTA,
+    // pulls work items.
     const int rank = kCluster ? (int)cooperative_groups::this_cluster().block_rank() : 0;
     const long long total_items = p.batch * (long long)p.n_chunks;
     // exact-path pass: nothing to do unless the optimistic pass just before it flagged an instance
     if (kExact && *(volatile unsigned long long *)p.fail_counter == 0ULL) return;
-    __shared__ uint32_t s_tmem;
-    uint32_t tm = 0;
-    if (kPark) {  // this CTA's columns of tensor memory; my warp's lane quadrant
-        if (t < 32) {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"l"((uint64_t)__cvta_generic_to_shared(&s_tmem)), "n"(kTileParkCols));
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    TileBars bars;
+    bars.b1 = smem_addr(&s_bar[0]);
+    bars.b2 = bars.b1 + 8;
+    bars.b3 = bars.b1 + 16;
+    bars.b4 = bars.b1 + 24;
+    bars.xb = bars.b1 + 32;
+    if (kSplit) {
+        if (t == 0) {
+            for (int i = 0; i < 4; ++i) mbar_init(bars.b1 + 8 * i, NT / 32);
+            // one arrival per published element this CTA consumes, per step
+            const int pushes = kExtras ? max(tp.xb_count[rank], 1) : 1;
+            mbar_init(bars.xb, pushes);
+            mbar_init(bars.xb + 8, pushes);
+            if (kCluster) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        asm volatile("tcgen05.fence::before_thread_sync;");
-        __syncthreads();
-        asm volatile("tcgen05.fence::after_thread_sync;");
-        tm = s_tmem + ((uint32_t)(32 * ((t >> 5) & 3)) << 16);
+        // (visible to the CTA, and to the cluster, at the first tile_sync of the item loop)
     }
+    int gstep = 0;  // steps executed so far: the barriers' phase parity
 
     // Persistent CTAs pull (chunk, instance) items off one queue: the launch is cut into n_chunks runs of chunk_steps
     // steps so that the last wave of instances does not leave most SMs idle (4096 instances on 888 resident CTAs would
@@ -862,7 +875,7 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
         const bool final_chunk = (chunk == p.n_chunks - 1);
 
         TileThread<C> th;
-        th.t = t + 1;  // (kPark == 2: an idle thread's own row is row 0, set below)
+        th.t = t + 1;
         th.bad = 0;
         // ---- which run is mine -------------------------------------------------------------------
         const bool active = t < tp.cta_threads[rank];
@@ -874,7 +887,6 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
             // rows I read from: next / previous run of my rod, my partner as rod one of the joints I own, the owner
             // of the joints in which I am rod one (and the owner of my predecessor's); the zero row when there is none
             th.tn = (active && k0 + C <= n) ? t + 2 : t + 1;
-            if (kPark == 2 && !active) th.t = th.tn = 0;
             const int r1 = tp.partner[rod], ro = tp.owner[rod];
             th.t1 = (active && r1 >= 0) ? 1 + tp.rod_t0[r1] + (t - tp.rod_t0[rod]) : 0;
             th.to = (active && ro >= 0) ? 1 + tp.rod_t0[ro] + (t - tp.rod_t0[rod]) : 0;
@@ -908,10 +920,7 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
                 }
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
-                    if (kPark == 2)
-                        tmem_park(TM_AT(kPkTA + 3 * j + i), ta[i]);
-                    else
-                        sm[L::TA + (3 * j + i) * R + t + 1] = ta[i];
+                    sm[L::TA + (3 * j + i) * R + t + 1] = ta[i];
                     th.x[j][i] = valid ? __ldcg(inst + i * np1 + k) : 0.0;
                     th.v[j][i] = valid ? __ldcg(inst + 3 * np1 + i * np1 + k) : 0.0;
                     th.w[j][i] = elem ? __ldcg(inst + 6 * np1 + 9 * n + i * n + k) : 0.0;
@@ -935,11 +944,19 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
                 }
             }
             th.xjoint = (kExtras && tp.n_xj > 0 && active) ? tp.xi[(rank * tp.xi_stride + t) * (C + 1) + C] : -1;
-            if (kExtras) {  // this CTA's copy of the extra joints' tables
-                double *const XJD = sm + L::EX + 25 * tp.n_xe + 3 * tp.n_xj;
-                int *const XJI = (int *)(XJD + 8 * tp.n_xj), *const XIT = XJI + 12 * tp.n_xj;
+            if (kExtras) {  // this CTA's copy of the extra joints' tables (layout: TileSmem)
+                double *const XJD = sm + L::EX + 2 * L::EXW * tp.n_xe + 4 * tp.n_xj;
+                int *const XJI = (int *)(XJD + 8 * tp.n_xj), *const XPM = XJI + 8 * tp.n_xj, *const XIT = XPM + ((tp.n_xe + 1) & ~1);
                 for (int i = t; i < 8 * tp.n_xj; i += NT) XJD[i] = tp.xj_d[i];
-                for (int i = t; i < 12 * tp.n_xj; i += NT) XJI[i] = tp.xj_i[i];
+                for (int i = t; i < tp.n_xj; i += NT) {
+                    const int *row = tp.xj_i + 12 * i;
+                    XJI[8 * i + 0] = row[8];   // published element of rod one's element (node sums, radius)
+                    XJI[8 * i + 1] = row[9];   // ... of rod two's element
+                    XJI[8 * i + 2] = row[6];   // ... of director one
+                    XJI[8 * i + 3] = row[7];   // ... of director two
+                    XJI[8 * i + 4] = row[10];  // type: 0 tip-to-base joint, 1 point force
+                }
+                for (int i = t; i < tp.n_xe; i += NT) XPM[i] = tp.xe_mask[i];
                 for (int i = t; i < tp.n_xitems; i += NT) XIT[i] = tp.xitems[i];
             }
             th.rod = rod;  // indexes the per-rod joint descriptors in the constant bank (TilePlan::jd)
@@ -959,18 +976,16 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
             for (int i = 0; i < 3; ++i) th.x[j][i] = fma(hdt, th.v[j][i], th.x[j][i]);
             th.bad |= TileMath<kExact>::rotate(th.Q[j], th.w[j], hdt, hdt) ? 1 : 0;
         }
-        if (kPark == 2) {
-#pragma unroll
-            for (int i = 0; i < 9; ++i) tmem_park(TM_AT(kPkQ1 + i), th.Q[1][i]);
-        }
         for (int step = 0; step < n_steps - 1; ++step) {
-            tile_step<C, NT, false, false, kExtras, kCluster, kExact, kPark>(p, sm, th, time + hdt, b, rank, step & 1, tm);
+            tile_step<C, NT, false, false, kExtras, kCluster, kExact, kSplit>(p, sm, th, time + hdt, b, rank, gstep, bars);
             time = (time + hdt) + hdt;
+            ++gstep;
         }
         if (final_chunk)
-            tile_step<C, NT, true, true, kExtras, kCluster, kExact, kPark>(p, sm, th, time + hdt, b, rank, (n_steps - 1) & 1, tm);
+            tile_step<C, NT, true, true, kExtras, kCluster, kExact, kSplit>(p, sm, th, time + hdt, b, rank, gstep, bars);
         else
-            tile_step<C, NT, true, false, kExtras, kCluster, kExact, kPark>(p, sm, th, time + hdt, b, rank, (n_steps - 1) & 1, tm);
+            tile_step<C, NT, true, false, kExtras, kCluster, kExact, kSplit>(p, sm, th, time + hdt, b, rank, gstep, bars);
+        ++gstep;
 
         // a CTA that left the series' validity range keeps the chunk-start state and asks for the exact path, which
         // resumes this instance from the start of this chunk (status = 1 + chunk, reason bits from bit 8 up)
@@ -1024,10 +1039,6 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
             }
             *(volatile int *)(p.progress + b) = chunk + 1;
         }
-    }
-    if (kPark) {
-        __syncthreads();
-        if (t < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "n"(kTileParkCols));
     }
 }
 
