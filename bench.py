@@ -84,6 +84,8 @@ def parse_args():
     ap.add_argument("--substeps", type=int, default=2000, help="integration steps per launch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra_workloads (configs[2], [3], [4]) lines")
+    ap.add_argument("--n-elements", type=int, default=None, help="experiment: override the rod library's elements per rod")
+    ap.add_argument("--dt", type=float, default=None, help="experiment: override the time step")
     ap.add_argument("--variant", type=int, default=-1, help="force a kernel variant (0 generic, 1/2 fast, 3 tile); -1 = automatic")
     return ap.parse_args()
 
@@ -91,7 +93,18 @@ def parse_args():
 def resolve_workload(args, world):
     """(name, spec, instances on each GPU, instances in total): what both arms run and describe."""
     name = args.workload or ("single" if world == 1 else "sweep")
-    w = WORKLOADS[name]
+    w = dict(WORKLOADS[name])
+    if args.n_elements:  # experiments only (kernel studies): a rod library with another resolution
+        import tempfile as _tmp
+
+        library = json.load(open(os.path.join(DATA, w.get("rod_db", "rod_library.json"))))
+        library["DefaultParams"]["n_elements"] = args.n_elements
+        path = os.path.join(_tmp.mkdtemp(prefix="br2_bench_"), "rod_library.json")
+        json.dump(library, open(path, "w"))
+        rods = len(json.load(open(os.path.join(DATA, w["assembly"])))["Segments"]) * 3
+        w.update(rod_db=path, elements=rods * args.n_elements, config="experiment: %d elements per rod" % args.n_elements)
+    if args.dt:
+        w["dt"] = args.dt
     batch = args.batch or w["batch"]
     if w.get("total"):
         total = batch

@@ -88,29 +88,37 @@ struct KernelChoice {
 #ifndef BR2_TILE_MIN_CHUNK_STEPS
 #define BR2_TILE_MIN_CHUNK_STEPS 125  // a launch is cut into at most BR2_MAX_CHUNKS chunks of at least this many steps
 #endif
+// split-phase mbarriers (true) or CTA barriers (false) at the step's three exchange points, per kernel family
+// (measured: see DESIGN.md); the tip-to-base joint data is pushed through (distributed) shared memory either way
 #ifndef BR2_TILE_SPLIT_SINGLE
-#define BR2_TILE_SPLIT_SINGLE false  // split-phase mbarriers in the single-segment kernels too (measured: see DESIGN.md)
+#define BR2_TILE_SPLIT_SINGLE false
+#endif
+#ifndef BR2_TILE_SPLIT_EXTRA
+#define BR2_TILE_SPLIT_EXTRA true
+#endif
+#ifndef BR2_TILE_SPLIT_CLUSTER
+#define BR2_TILE_SPLIT_CLUSTER true
 #endif
 // variant 3: tile kernel (BR2_TILE_C slots per thread, uniform constants); `threads` = CTA size
 // template flags: <slots per thread, CTA threads, min CTAs per SM, extra joints, cluster, exact arithmetic, split-phase barriers>
 const KernelChoice kTileKernels[] = {  // single-segment assemblies (ring joints only)
     {64, br2::br2_step_tile_kernel<BR2_TILE_C, 64, BR2_TILE_MB64, false, false, false, BR2_TILE_SPLIT_SINGLE>},
-    {128, br2::br2_step_tile_kernel<BR2_TILE_C, 128, 3, false, false, false, true>},
-    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, false, false, false, true>},
+    {128, br2::br2_step_tile_kernel<BR2_TILE_C, 128, 3, false, false, false, BR2_TILE_SPLIT_EXTRA>},
+    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, false, false, false, BR2_TILE_SPLIT_CLUSTER>},
 };
 const KernelChoice kTileExtraKernels[] = {  // several segments joined tip to base, one CTA
-    {128, br2::br2_step_tile_kernel<BR2_TILE_C, 128, 3, true, false, false, true>},
-    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true, false, false, true>},
-    {256, br2::br2_step_tile_kernel<BR2_TILE_C, 256, 1, true, false, false, true>},
+    {128, br2::br2_step_tile_kernel<BR2_TILE_C, 128, 3, true, false, false, BR2_TILE_SPLIT_EXTRA>},
+    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true, false, false, BR2_TILE_SPLIT_EXTRA>},
+    {256, br2::br2_step_tile_kernel<BR2_TILE_C, 256, 1, true, false, false, BR2_TILE_SPLIT_EXTRA>},
 };
 // one CTA per group of ring-connected rods, launched as a thread-block cluster per instance
 const KernelChoice kTileClusterKernels[] = {
-    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true, true, false, true>},
-    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, true, true, false, true>},
+    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true, true, false, BR2_TILE_SPLIT_CLUSTER>},
+    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, true, true, false, BR2_TILE_SPLIT_CLUSTER>},
 };
 const KernelChoice kTileClusterExactKernels[] = {  // same, exact arithmetic: the replay path of cluster-sized assemblies
-    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true, true, true, true>},
-    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, true, true, true, true>},
+    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true, true, true, BR2_TILE_SPLIT_CLUSTER>},
+    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, true, true, true, BR2_TILE_SPLIT_CLUSTER>},
 };
 const int kTileMaxCtaThreads = 320, kTileOneCtaThreads = 256;
 

@@ -212,8 +212,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
         }
         const double d2 = fma(d[0], d[0], fma(d[1], d[1], d[2] * d[2])) + (1.0 - elem_mask);  // keeps non-elements finite
         const double rs = fast_rsqrt(d2);
-        const double len = fma(d2, rs, BR2_EPS14);
-        const double inv_len = rs * fma(-BR2_EPS14, rs, 1.0);  // 1/(|d| + 1e-14), second order 1e-23
+        const double len = fma(d2, rs, BR2_EPS_LEN);
+        const double inv_len = rs * fma(-BR2_EPS_LEN, rs, 1.0);  // 1/(|d| + 1e-14), second order 1e-23
         const double rest_len = FC(BR2_FC_REST_LEN), inv_rest_len = FC(BR2_FC_INV_REST_LEN);
         const double r2 = FC(BR2_FC_VOL_OVER_PI) * inv_len;
         const double rad = r2 * fast_rsqrt(r2);
@@ -323,7 +323,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
             // Hertz-like repulsion when the surfaces interpenetrate: -k_rep |pen|^1.5 along the centre line
             const double cn2 = fma(cd[0], cd[0], fma(cd[1], cd[1], cd[2] * cd[2])) + (has_joint ? 0.0 : 1.0);
             const double rcn = fast_rsqrt(cn2);
-            const double ap = fmax(fma(-cn2, rcn, ra1 + ra2), 0.0);   // max(-pen, 0)
+            const double ap_raw = fmax(fma(-cn2, rcn, ra1 + ra2), 0.0);   // max(-pen, 0)
+            const double ap = rint(ap_raw * BR2_PEN_SCALE) * BR2_PEN_INV_SCALE;  // np.round_(penetration_strain, 12)
             const double ap3 = ap * ap * ap;
             const double mag = -FC(BR2_FC_JKREP) * (ap3 * fast_rsqrt(ap3 + BR2_TINY)) * rcn;  // ap^1.5 = ap^3 / sqrt(ap^3)
             // torques use the spring part only: t = rd x (k d); rotate into each material frame
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
                 }
                 const double cn2 = fma(cd[0], cd[0], fma(cd[1], cd[1], cd[2] * cd[2]));
                 const double rcn = fast_rsqrt(cn2);
-                const double pen = fma(cn2, rcn, -(ra1 + ra2));
+                const double pen = rint(fma(cn2, rcn, -(ra1 + ra2)) * BR2_PEN_SCALE) * BR2_PEN_INV_SCALE;  // np.round_(penetration_strain, 12)
                 if (pen < 0.0) {
                     const double ap = -pen;
                     const double mag = -jd[2] * ap * (ap * fast_rsqrt(ap)) * rcn;

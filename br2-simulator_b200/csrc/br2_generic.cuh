@@ -15,7 +15,7 @@ __device__ __forceinline__ void mat_rotate(double (&Q)[9], const double (&w)[3],
     // Q <- R(prefac * w) Q with the row-director Rodrigues matrix (Appendix A.4)
     double v0 = prefac * w[0], v1 = prefac * w[1], v2 = prefac * w[2];
     double theta = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
-    double inv = 1.0 / (theta + 1e-14);
+    double inv = 1.0 / (theta + BR2_ROTATION_NORM_GUARD);
     v0 *= inv;
     v1 *= inv;
     v2 *= inv;
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_generic_kernel(
                 vn[i] = Vs[i * S + s + 1];
                 d[i] = xn[i] - x[i];
             }
-            len = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) + 1e-14;
+            len = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) + BR2_LENGTH_GUARD;
             const double tg[3] = {d[0] / len, d[1] / len, d[2] / len};
             rad = sqrt(volume / len / BR2_PI);
             dil = len / rest_len;
@@ -218,8 +218,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_generic_kernel(
             double w2 = ROWDOT(1, 0) - ROWDOT(0, 1);
             const double tr = ROWDOT(0, 0) + ROWDOT(1, 1) + ROWDOT(2, 2);
 #undef ROWDOT
-            const double theta = acos(0.5 * tr - 0.5 - 1e-10);
-            const double scale = -0.5 * theta / sin(theta + 1e-14);
+            const double theta = acos(0.5 * tr - 0.5 - BR2_ARCCOS_GUARD);
+            const double scale = -0.5 * theta / sin(theta + BR2_SIN_GUARD);
             const double kap[3] = {w0 * scale / rest_vlen, w1 * scale / rest_vlen, w2 * scale / rest_vlen};
             double tau[3];
 #pragma unroll
@@ -272,12 +272,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_generic_kernel(
                     rd1[i] = g1 * (r1 + o1);
                     rd2[i] = g2 * (r2 + o2);
                     const double di = (c2[i] + rd2[i]) - (c1[i] + rd1[i]);
-                    dvec[i] = rint(di * 1e12) / 1e12;
+                    dvec[i] = rint(di * BR2_DISTANCE_ROUND_SCALE) / BR2_DISTANCE_ROUND_SCALE;
                     Fs[i] = kj * dvec[i];
                 }
                 const double dist = sqrt(dvec[0] * dvec[0] + dvec[1] * dvec[1] + dvec[2] * dvec[2]);
                 double nd[3] = {0, 0, 0};
-                if (dist >= 1e-12) {
+                if (dist >= BR2_ZERO_DISTANCE_GUARD) {
 #pragma unroll
                     for (int i = 0; i < 3; ++i) nd[i] = dvec[i] / dist;
                 }
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_generic_kernel(
                 for (int i = 0; i < 3; ++i) F[i] = Fs[i] + (-nuj * (proj * nd[i]));
                 const double cd[3] = {c2[0] - c1[0], c2[1] - c1[1], c2[2] - c1[2]};
                 const double cn = sqrt(cd[0] * cd[0] + cd[1] * cd[1] + cd[2] * cd[2]);
-                const double pen = cn - (r1 + o1 + r2 + o2);
+                const double pen = rint((cn - (r1 + o1 + r2 + o2)) * BR2_PENETRATION_ROUND_SCALE) / BR2_PENETRATION_ROUND_SCALE;
                 if (pen < 0) {
                     const double ap = fabs(pen);
                     const double mag = -krep * (ap * sqrt(ap));
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_generic_kernel(
                     const double e0 = cd[0] - x[0], e1 = cd[1] - x[1], e2 = cd[2] - x[2];
                     const double dist = sqrt(e0 * e0 + e1 * e1 + e2 * e2);
                     double u0 = 0.0, u1 = 0.0, u2 = 0.0;
-                    if (!(dist <= 1e-8)) {
+                    if (!(dist <= BR2_SOFTFIX_ZERO_DISTANCE)) {
                         u0 = e0 / dist;
                         u1 = e1 / dist;
                         u2 = e2 / dist;
@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_generic_kernel(
                         const double e0 = cd[0] - x[0], e1 = cd[1] - x[1], e2 = cd[2] - x[2];
                         const double dist = sqrt(e0 * e0 + e1 * e1 + e2 * e2);
                         double u0 = 0.0, u1 = 0.0, u2 = 0.0;
-                        if (!(dist <= 1e-8)) {
+                        if (!(dist <= BR2_SOFTFIX_ZERO_DISTANCE)) {
                             u0 = e0 / dist;
                             u1 = e1 / dist;
                             u2 = e2 / dist;

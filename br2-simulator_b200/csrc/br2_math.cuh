@@ -23,12 +23,29 @@ __constant__ double kLogC[16] = {
     32768.0 / 109395.0, 65536.0 / 230945.0, 262144.0 / 969969.0, 524288.0 / 2028117.0, 4194304.0 / 16900975.0,
     8388608.0 / 35102025.0, 33554432.0 / 145422675.0, 67108864.0 / 300540195.0};
 __constant__ double kExpC[7] = {1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0};
-__constant__ double kMisc[8] = {1e-14, 1e-300, 1e12, 1e-12, 1e-24, 0.375, -0.5 - 1e-10, 1.5 + 1e-10};
-#define BR2_EPS14 kMisc[0]
+// Named guards of the restated upstream (PyElastica 0.3.1) arithmetic -- SURVEY.md Appendix E's confidence ledger: if a
+// check against the real package disagrees with one of them, THIS is the place to flip it (oracle/mini_elastica and
+// oracle/fused/br2_oracle.c carry the same names).
+#define BR2_LENGTH_GUARD 1e-14             // lengths = |dx| + guard                        (rod geometry)
+#define BR2_ROTATION_NORM_GUARD 1e-14      // axis = u / (|u| + guard)                       (Rodrigues update)
+#define BR2_ARCCOS_GUARD 1e-10             // theta = arccos(0.5 tr - 0.5 - guard)           (curvature log map)
+#define BR2_SIN_GUARD 1e-14                // scale = -0.5 theta / sin(theta + guard)
+#define BR2_DISTANCE_ROUND_SCALE 1e12      // np.round_(distance_vector, 12)                 (surface joint)
+#define BR2_ZERO_DISTANCE_GUARD 1e-12      // no damping direction below this |distance|
+#define BR2_PENETRATION_ROUND_SCALE 1e12   // np.round_(penetration_strain, 12) before the `< 0` test
+#define BR2_SOFTFIX_ZERO_DISTANCE 1e-8     // FreeBaseEndSoftFixed: unit vector 0 below (free_custom_systems.py:170-173)
+__constant__ double kMisc[8] = {BR2_LENGTH_GUARD, 1e-300, BR2_DISTANCE_ROUND_SCALE, 1.0 / BR2_DISTANCE_ROUND_SCALE,
+                                BR2_ZERO_DISTANCE_GUARD * BR2_ZERO_DISTANCE_GUARD, 0.375, -0.5 - BR2_ARCCOS_GUARD, 1.5 + BR2_ARCCOS_GUARD};
+__constant__ double kGuard[4] = {BR2_ROTATION_NORM_GUARD, BR2_SIN_GUARD, BR2_PENETRATION_ROUND_SCALE, 1.0 / BR2_PENETRATION_ROUND_SCALE};
+#define BR2_EPS_LEN kMisc[0]
 #define BR2_TINY kMisc[1]
 #define BR2_1E12 kMisc[2]
 #define BR2_1EM12 kMisc[3]
 #define BR2_1EM24 kMisc[4]
+#define BR2_EPS_ROT kGuard[0]
+#define BR2_EPS_SIN kGuard[1]
+#define BR2_PEN_SCALE kGuard[2]
+#define BR2_PEN_INV_SCALE kGuard[3]
 
 // Raw hardware seeds (MUFU.RCP64H / MUFU.RSQ64H): ~2^-20 relative accuracy, for quantities that
 // multiply something tiny (damping of a joint, thinning of a 1e-8 m gap).
@@ -85,7 +102,7 @@ __device__ __forceinline__ bool rotate_directors(double (&Q)[9], double u0, doub
     const double tt = t + BR2_TINY;                 // keeps rsqrt finite for a resting element
     const double rs = fast_rsqrt(tt);
     const double theta = tt * rs;
-    const double m = mult * theta * fast_rcp(theta + BR2_EPS14);
+    const double m = mult * theta * fast_rcp(theta + BR2_EPS_ROT);
     const double m2 = m * m;
     const double tphi = m2 * t;                   // phi^2
     double sinc, cosc;
@@ -127,7 +144,7 @@ __device__ __forceinline__ double logmap_scale_small(double y) {
     const double r0 = fma(q1, z4, q0), r1 = fma(q3, z4, q2);
     const double f = fma(r1, z8, r0);                          // theta / sin(theta)
     const double inv_sin = 0.5 * seed_rsqrt(z * (1.0 - z));    // 1 / sin(theta), ~2^-20 relative
-    const double guard = fma(-BR2_EPS14 * (1.0 - y), inv_sin, 1.0);
+    const double guard = fma(-BR2_EPS_SIN * (1.0 - y), inv_sin, 1.0);
     return -0.5 * f * guard;
 }
 
@@ -174,7 +191,7 @@ __device__ __forceinline__ bool rotate_directors_tiny(double (&Q)[9], const doub
     // (the guard from ONE seed, 1 - (1e-14 / hdt) / |w| clamped to [0, 1], is one MUFU and one dependent step shorter and
     // was measured 3.5 % SLOWER on the tile kernel -- ptxas' schedule decides, not the instruction count)
     const double absu = hdt * (tt * seed_rsqrt(tt));
-    const double g = fma(-BR2_EPS14, seed_rcp(absu + BR2_EPS14), 1.0);
+    const double g = fma(-BR2_EPS_ROT, seed_rcp(absu + BR2_EPS_ROT), 1.0);
     const double hm = hmult * g;
     const double u0 = hm * w[0], u1 = hm * w[1], u2 = hm * w[2];
     const double tphi = (hm * hm) * tw;  // phi^2
@@ -214,7 +231,7 @@ __device__ __forceinline__ double logmap_ratio_tiny(double y) {
     po = fma(po, z2, kLogC[1]);
     const double f = fma(po, z, pe);
     const double inv_sin = seed_rsqrt(fma(-y, y, y + y));
-    const double guard = fma(fma(BR2_EPS14, y, -BR2_EPS14), inv_sin, 1.0);
+    const double guard = fma(fma(BR2_EPS_SIN, y, -BR2_EPS_SIN), inv_sin, 1.0);
     return f * guard;
 }
 

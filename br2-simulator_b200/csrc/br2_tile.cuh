@@ -113,6 +113,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 // the step's exchange points: arrive after publishing, wait before reading; kSplit = false degenerates to one
 // __syncthreads at the wait
+#ifndef BR2_TILE_HOIST_DAMPER
+#define BR2_TILE_HOIST_DAMPER 0  // damper exponentials before the third wait (costs registers: measured)
+#endif
 struct TileBars {
     uint32_t b1, b2, b3, b4, xb;  // shared-memory addresses: three phase barriers, joint forces ready, pushed data (xb, xb + 8 by step parity)
 };
@@ -139,14 +142,14 @@ struct TileMath {
     static __device__ __forceinline__ double logmap_ratio(double y) {
         if (!kExact) return logmap_ratio_tiny(y);
         const double theta = acos(1.0 - y);
-        return theta / sin(theta + 1e-14);
+        return theta / sin(theta + BR2_SIN_GUARD);
     }
     // Q <- R Q for one (hmult == hdt) or two fused (hmult == 2 hdt) kinematic half steps; true = left the series' range
     static __device__ __forceinline__ bool rotate(double (&Q)[9], const double (&w)[3], double hdt, double hmult) {
         if (!kExact) return rotate_directors_tiny(Q, w, hdt, hmult);
         const double u0 = hdt * w[0], u1 = hdt * w[1], u2 = hdt * w[2];
         const double theta = sqrt(u0 * u0 + u1 * u1 + u2 * u2);
-        const double inv = 1.0 / (theta + 1e-14);
+        const double inv = 1.0 / (theta + BR2_ROTATION_NORM_GUARD);
         const double a0 = u0 * inv, a1 = u1 * inv, a2 = u2 * inv;   // the reference's guarded axis (Appendix A.4)
         double sn, cs;
         sincos((hmult > 1.5 * hdt) ? 2.0 * theta : theta, &sn, &cs);  // same axis both half steps: the angles add
@@ -277,7 +280,6 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
     constexpr int R = L::R;
     static_assert(C >= 2, "slot 0's element must lie inside the thread's run");
     static_assert(kExtras || !kCluster, "the cluster kernels carry the extra-joint code");
-    static_assert(kSplit || !kExtras, "the extra-joint code needs the split-phase barriers (a fourth exchange point)");
     using M = TileMath<kExact>;
     const DevTables &tb = p.t;
     const int t = th.t;
@@ -319,7 +321,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
         double d2 = fma(d0[0], d0[0], fma(d0[1], d0[1], d0[2] * d0[2]));
         d2 = (th.fl[0] & TILE_F_ELEM) ? d2 : 1.0;  // keeps the node-only slot finite
         rs0 = M::rsqrt(d2);
-        len0 = fma(d2, rs0, BR2_EPS14);
+        len0 = fma(d2, rs0, BR2_EPS_LEN);
         sm[L::LF + t] = len0;
     }
 #pragma unroll
@@ -363,9 +365,9 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
                 double d2 = fma(d[0], d[0], fma(d[1], d[1], d[2] * d[2]));
                 d2 = elem ? d2 : 1.0;  // keeps the node-only slot finite
                 rs = M::rsqrt(d2);
-                len[j] = fma(d2, rs, BR2_EPS14);
+                len[j] = fma(d2, rs, BR2_EPS_LEN);
             }
-            const double inv_len = rs * fma(-BR2_EPS14, rs, 1.0);  // 1/(|d| + 1e-14), second order 1e-23
+            const double inv_len = rs * fma(-BR2_EPS_LEN, rs, 1.0);  // 1/(|d| + 1e-14), second order 1e-23
             const double rest_len = UNI(BR2_FC_REST_LEN), inv_rest_len = UNI(BR2_FC_INV_REST_LEN);
             const double r2 = UNI(BR2_FC_VOL_OVER_PI) * inv_len;
             const double rad = r2 * M::rsqrt(r2);
@@ -534,7 +536,8 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
         // Hertz-like repulsion when the surfaces interpenetrate: -k_rep pen^1.5 along the centre line
         const double cn2 = fma(cd2[0], cd2[0], fma(cd2[1], cd2[1], cd2[2] * cd2[2])) + BR2_TINY;  // 4 |cd|^2
         const double rcn = M::rsqrt(cn2);                                 // 1 / (2 |cd|)
-        const double pen = fmax(fma(-0.5 * cn2, rcn, ra1 + ra2[j]), 0.0);     // max(r1 + r2 - |cd|, 0)
+        const double pen_raw = fmax(fma(-0.5 * cn2, rcn, ra1 + ra2[j]), 0.0);  // max(r1 + r2 - |cd|, 0)
+        const double pen = rint(pen_raw * BR2_PEN_SCALE) * BR2_PEN_INV_SCALE;  // np.round_(penetration_strain, 12)
         const double hmag = KD(7, -0.5 * UNI(BR2_FC_JKREP)) * (pen * M::sqrt_lo(pen)) * rcn;  // times cd2 = half the repulsion
         double fs[3];
 #pragma unroll
@@ -585,17 +588,19 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
                 JF[xj * 4 + i] = 0.5 * fma(kj, gap, -nuj * vrel);
             }
         }
-        mbar_arrive_warp(bars.b4);
+        if (kSplit) mbar_arrive_warp(bars.b4);  // (CTA barriers: B3 below orders the joint forces before their readers)
     }
     // damper exponentials (element lengths are mine): before the wait when the barrier is split-phase
+    constexpr bool kHoistDamper = kSplit && BR2_TILE_HOIST_DAMPER;
     double dexp[C][3];
-    if (kSplit) {
+    if (kHoistDamper) {
 #pragma unroll
         for (int j = 0; j < C; ++j) tile_damper_exponentials<kExact>(p, len[j], th.fl[j], dexp[j], th.bad);
-        mbar_wait<false>(bars.b3, (uint32_t)gstep & 1u);  // B3
-    } else {
-        __syncthreads();  // B3
     }
+    if (kSplit)
+        mbar_wait<false>(bars.b3, (uint32_t)gstep & 1u);  // B3
+    else
+        __syncthreads();  // B3
 
     // =============================== P4: assemble, dynamic step ==============================
     {
@@ -646,7 +651,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
             if (kExtras && (th.xinfo[j] >> 8) != 0) {
                 if (kLast) {  // half forces of the extra joints on this node (every other step: after the rotation below)
                     const int cnt = (th.xinfo[j] >> 16) & 0xF, first = th.xinfo[j] >> 20;
-                    if (cnt) mbar_wait<false>(bars.b4, (uint32_t)gstep & 1u);
+                    if (kSplit && cnt) mbar_wait<false>(bars.b4, (uint32_t)gstep & 1u);
                     for (int q = 0; q < cnt; ++q) {
                         const int item = XIT[first + q];
                         const double sgn = (item & 1) ? -1.0 : 1.0;
@@ -671,15 +676,32 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
                 }
             }
             const double dil = len[j] * UNI(BR2_FC_INV_REST_LEN);
-            if (!kSplit) tile_damper_exponentials<kExact>(p, len[j], th.fl[j], dexp[j], th.bad);
             double damp[3];
-            if (p.tile.round_section) {
-                const double ex = dexp[j][0];
-                damp[2] = UNI(BR2_FC_CR + 2) * ex;
-                damp[0] = damp[1] = UNI(BR2_FC_CR) * (ex * ex);
-            } else {
+            if (kHoistDamper) {
+                if (p.tile.round_section) {
+                    const double ex = dexp[j][0];
+                    damp[2] = UNI(BR2_FC_CR + 2) * ex;
+                    damp[0] = damp[1] = UNI(BR2_FC_CR) * (ex * ex);
+                } else {
 #pragma unroll
-                for (int i = 0; i < 3; ++i) damp[i] = UNI(BR2_FC_CR + i) * dexp[j][i];
+                    for (int i = 0; i < 3; ++i) damp[i] = UNI(BR2_FC_CR + i) * dexp[j][i];
+                }
+            } else {
+                const double strain = (th.fl[j] & TILE_F_ELEM) ? dil - 1.0 : 0.0;
+                if (p.tile.round_section) {
+                    const double e2 = strain * UNI(BR2_FC_LN_CR + 2);
+                    if (!kExact) th.bad |= (e2 * e2 <= BR2_E2_MAX) ? 0 : 4;
+                    const double ex = M::exp(e2);
+                    damp[2] = UNI(BR2_FC_CR + 2) * ex;
+                    damp[0] = damp[1] = UNI(BR2_FC_CR) * (ex * ex);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const double e = strain * UNI(BR2_FC_LN_CR + i);
+                        if (!kExact) th.bad |= (e * e <= BR2_E2_MAX) ? 0 : 4;
+                        damp[i] = UNI(BR2_FC_CR + i) * M::exp(e);
+                    }
+                }
             }
             double wnew[3];
 #pragma unroll
@@ -741,7 +763,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
             for (int j = 0; j < C; ++j) {
                 const int cnt = (th.xinfo[j] >> 16) & 0xF, first = th.xinfo[j] >> 20;
                 if (cnt) {
-                    mbar_wait<false>(bars.b4, (uint32_t)gstep & 1u);
+                    if (kSplit) mbar_wait<false>(bars.b4, (uint32_t)gstep & 1u);
                     // the first three items (a joined element's node has three: one per rod of the other segment) without a
                     // branch between them, so that their loads are in flight together; same order of summation as the loop
                     int item[3];
@@ -810,7 +832,7 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
     bars.b3 = bars.b1 + 16;
     bars.b4 = bars.b1 + 24;
     bars.xb = bars.b1 + 32;
-    if (kSplit) {
+    if (kSplit || kExtras) {
         if (t == 0) {
             for (int i = 0; i < 4; ++i) mbar_init(bars.b1 + 8 * i, NT / 32);
             // one arrival per published element this CTA consumes, per step

@@ -25,6 +25,17 @@
 #include <string.h>
 #ifdef _OPENMP
 #include <omp.h>
+
+/* Named guards of the restated upstream arithmetic (same names in oracle/mini_elastica and in
+ * br2-simulator_b200/csrc/br2_math.cuh): flip here if a check against real PyElastica 0.3.1 disagrees. */
+#define LENGTH_GUARD 1e-14
+#define ROTATION_NORM_GUARD 1e-14
+#define ARCCOS_GUARD 1e-10
+#define SIN_GUARD 1e-14
+#define DISTANCE_ROUND_SCALE 1e12          /* np.round_(distance_vector, 12) */
+#define ZERO_DISTANCE_GUARD 1e-12
+#define PENETRATION_ROUND_SCALE 1e12       /* np.round_(penetration_strain, 12) */
+#define SOFTFIX_ZERO_DISTANCE 1e-8         /* free_custom_systems.py:170-173 */
 #endif
 
 #define PI 3.141592653589793
@@ -116,9 +127,9 @@ static void kinematic_half_step(rodv *r, double prefac) {
     for (int k = 0; k < n; ++k) {
         double v0 = prefac * WW(0, k), v1 = prefac * WW(1, k), v2 = prefac * WW(2, k);
         double theta = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
-        v0 /= theta + 1e-14;
-        v1 /= theta + 1e-14;
-        v2 /= theta + 1e-14;
+        v0 /= theta + ROTATION_NORM_GUARD;
+        v1 /= theta + ROTATION_NORM_GUARD;
+        v2 /= theta + ROTATION_NORM_GUARD;
         theta *= 1.0;
         double s = sin(theta), q = 1.0 - cos(theta);
         double R[3][3];
@@ -161,7 +172,7 @@ static void internal_forces_and_torques(rodv *r, double *scratch) {
     /* geometry, dilatations */
     for (int k = 0; k < n; ++k) {
         double d0 = X(0, k + 1) - X(0, k), d1 = X(1, k + 1) - X(1, k), d2 = X(2, k + 1) - X(2, k);
-        double l = sqrt(d0 * d0 + d1 * d1 + d2 * d2) + 1e-14;
+        double l = sqrt(d0 * d0 + d1 * d1 + d2 * d2) + LENGTH_GUARD;
         r->len[k] = l;
         tan_[0 * n + k] = d0 / l;
         tan_[1 * n + k] = d1 / l;
@@ -208,8 +219,8 @@ static void internal_forces_and_torques(rodv *r, double *scratch) {
                     (A(2, 0) * Bq(2, 0) + A(2, 1) * Bq(2, 1) + A(2, 2) * Bq(2, 2));
 #undef A
 #undef Bq
-        double theta = acos(0.5 * tr - 0.5 - 1e-10);
-        double scale = -0.5 * theta / sin(theta + 1e-14);
+        double theta = acos(0.5 * tr - 0.5 - ARCCOS_GUARD);
+        double scale = -0.5 * theta / sin(theta + SIN_GUARD);
         w0 *= scale;
         w1 *= scale;
         w2 *= scale;
@@ -275,7 +286,7 @@ static void soft_fixed_base_values(rodv *r, const double *d) {
     double e0 = d[0] - X(0, 0), e1 = d[1] - X(1, 0), e2 = d[2] - X(2, 0);
     double dist = sqrt(e0 * e0 + e1 * e1 + e2 * e2);
     double u0 = 0.0, u1 = 0.0, u2 = 0.0;
-    if (!(dist <= 1e-8)) {
+    if (!(dist <= SOFTFIX_ZERO_DISTANCE)) {
         u0 = e0 / dist;
         u1 = e1 / dist;
         u2 = e2 / dist;
@@ -399,7 +410,7 @@ static void surface_joint(rodv *r1, int i1, rodv *r2, int i2, const double *jd) 
     }
     for (int i = 0; i < 3; ++i) {
         d[i] = (c2[i] + rd2[i]) - (c1[i] + rd1[i]);
-        d[i] = rint(d[i] * 1e12) / 1e12;
+        d[i] = rint(d[i] * DISTANCE_ROUND_SCALE) / DISTANCE_ROUND_SCALE;
         Fs[i] = k * d[i];
     }
     double vrel[3];
@@ -410,13 +421,14 @@ static void surface_joint(rodv *r1, int i1, rodv *r2, int i2, const double *jd) 
     }
     double dist = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
     double nd[3] = {0, 0, 0};
-    if (dist >= 1e-12)
+    if (dist >= ZERO_DISTANCE_GUARD)
         for (int i = 0; i < 3; ++i) nd[i] = d[i] / dist;
     double proj = vrel[0] * nd[0] + vrel[1] * nd[1] + vrel[2] * nd[2];
     for (int i = 0; i < 3; ++i) F[i] = Fs[i] + (-nu * (proj * nd[i]));
     double cd[3] = {c2[0] - c1[0], c2[1] - c1[1], c2[2] - c1[2]};
     double cn = sqrt(cd[0] * cd[0] + cd[1] * cd[1] + cd[2] * cd[2]);
     double pen = cn - (r1->rad[i1] + o1 + r2->rad[i2] + o2);
+    pen = rint(pen * PENETRATION_ROUND_SCALE) / PENETRATION_ROUND_SCALE; /* np.round_(penetration_strain, 12) */
     if (pen < 0) {
         double mag = -krep * pow(fabs(pen), 1.5);
         for (int i = 0; i < 3; ++i) F[i] += mag * (cd[i] / cn);

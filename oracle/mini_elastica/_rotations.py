@@ -24,9 +24,9 @@ def _get_rotation_matrix(scale, axis_collection):
         v1 = axis_collection[1, k]
         v2 = axis_collection[2, k]
         theta = np.sqrt(v0 * v0 + v1 * v1 + v2 * v2)
-        v0 /= theta + 1e-14
-        v1 /= theta + 1e-14
-        v2 /= theta + 1e-14
+        v0 /= theta + ROTATION_NORM_GUARD
+        v1 /= theta + ROTATION_NORM_GUARD
+        v2 /= theta + ROTATION_NORM_GUARD
         theta *= scale
         u_prefix = np.sin(theta)
         u_sq_prefix = 1.0 - np.cos(theta)
@@ -95,8 +95,8 @@ def _inv_rotate(director_collection):
                 + director_collection[2, 2, k + 1] * director_collection[2, 2, k]
             )
         )
-        theta = np.arccos(0.5 * trace - 0.5 - 1e-10)
-        scale = -0.5 * theta / np.sin(theta + 1e-14)
+        theta = np.arccos(0.5 * trace - 0.5 - ARCCOS_GUARD)
+        scale = -0.5 * theta / np.sin(theta + SIN_GUARD)
         vector_collection[0, k] *= scale
         vector_collection[1, k] *= scale
         vector_collection[2, k] *= scale

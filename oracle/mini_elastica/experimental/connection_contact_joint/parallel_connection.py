@@ -17,7 +17,11 @@ from ...joint import FreeJoint
 
 # Named constants (SURVEY.md Appendix E confidence ledger).
 DISTANCE_ROUND_DECIMALS = 12
+DISTANCE_ROUND_SCALE = 10.0 ** DISTANCE_ROUND_DECIMALS
 ZERO_DISTANCE_GUARD = 1e-12
+# upstream also rounds the penetration strain to 12 decimals (np.round_(penetration_strain, 12)) before the `< 0` test
+PENETRATION_ROUND_DECIMALS = 12
+PENETRATION_ROUND_SCALE = 10.0 ** PENETRATION_ROUND_DECIMALS
 
 
 def get_connection_vector_straight_straight_rod(rod_one, rod_two, rod_one_idx, rod_two_idx):
@@ -164,7 +168,7 @@ class SurfaceJointSideBySide(FreeJoint):
         )
         # np.round_(x, 12) == rint(x * 1e12) / 1e12
         for i in range(3):
-            distance_vector[i] = np.rint(distance_vector[i] * 1e12) / 1e12
+            distance_vector[i] = np.rint(distance_vector[i] * DISTANCE_ROUND_SCALE) / DISTANCE_ROUND_SCALE
         spring_force = k * distance_vector
 
         rod_one_element_velocity = 0.5 * (
@@ -183,7 +187,7 @@ class SurfaceJointSideBySide(FreeJoint):
             + distance_vector[2] * distance_vector[2]
         )
         normalized_distance_vector = np.zeros(3)
-        if distance >= 1e-12:
+        if distance >= ZERO_DISTANCE_GUARD:
             normalized_distance_vector[:] = distance_vector / distance
         normal_relative_velocity = (
             relative_velocity[0] * normalized_distance_vector[0]
@@ -208,6 +212,7 @@ class SurfaceJointSideBySide(FreeJoint):
             + rod_two_radius[index_two]
             + offset_rod_two
         )
+        penetration_strain = np.rint(penetration_strain * PENETRATION_ROUND_SCALE) / PENETRATION_ROUND_SCALE
         if penetration_strain < 0:
             total_force += (
                 -k_repulsive * np.abs(penetration_strain) ** 1.5 * center_distance_unit_vec

@@ -39,7 +39,7 @@ class RodBase:
 @njit(cache=True)
 def _compute_geometry_from_state(position_collection, volume, lengths, tangents, radius):
     position_diff = position_difference_kernel(position_collection)
-    lengths[:] = _batch_norm(position_diff) + 1e-14
+    lengths[:] = _batch_norm(position_diff) + LENGTH_GUARD
     for k in range(lengths.shape[0]):
         tangents[0, k] = position_diff[0, k] / lengths[k]
         tangents[1, k] = position_diff[1, k] / lengths[k]
