@@ -106,6 +106,17 @@ class Engine:
             self.launches += 2 if self._variant else 1
         return t_end.value
 
+    def metrics(self, previous=None):
+        """``[batch, 12]`` device tensor of per-instance terminal metrics (br2_metrics, include/br2cuda.h): NaN mask,
+        max |x|, max |v| and -- with ``previous``, a clone of the state block taken before the run -- the six steady-state
+        deltas.  One kernel, one pass over the state; asynchronous on the current stream."""
+        out = self.torch.empty((self.batch, _native.METRICS_N), dtype=self.torch.float64, device=self.device)
+        stream = self.torch.cuda.current_stream(self.device).cuda_stream
+        with self.torch.cuda.device(self.device):
+            _native.check(self.lib.br2_metrics(self.handle, previous.data_ptr() if previous is not None else None,
+                                               out.data_ptr(), ctypes.c_void_p(stream)))
+        return out
+
     def kernel_info(self):
         vals = [ctypes.c_int32(0) for _ in range(6)]
         _native.check(self.lib.br2_kernel_info(self.handle, *[ctypes.byref(v) for v in vals]))

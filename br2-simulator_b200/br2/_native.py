@@ -12,6 +12,7 @@ import numpy as np
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.environ.get("BR2_CUDA_LIB") or os.path.join(PKG_DIR, "lib", "libbr2cuda.so")
 ABI_VERSION = 2
+METRICS_N = 12  # BR2_METRICS_N
 
 _i32p = ctypes.POINTER(ctypes.c_int32)
 _f64p = ctypes.POINTER(ctypes.c_double)
@@ -46,7 +47,7 @@ EXPORTS = (
     "br2_last_error", "br2_abi_version", "br2_create", "br2_destroy", "br2_words_per_instance",
     "br2_bind_state", "br2_set_actuation", "br2_step", "br2_step_host", "br2_count_steps",
     "br2_kernel_info", "br2_fp64_peak_tflops", "br2_select_kernel", "br2_selftest_math", "br2_replay_count",
-    "br2_replay_reasons", "br2_unresolved_count", "br2_describe_plan", "br2_capture_plan",
+    "br2_replay_reasons", "br2_unresolved_count", "br2_describe_plan", "br2_capture_plan", "br2_metrics",
 )
 
 
@@ -75,6 +76,7 @@ def load():
                                     ctypes.POINTER(ctypes.c_int64), _f64p]
     lib.br2_capture_plan.argtypes = [ctypes.c_double, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p, ctypes.c_int32,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]
+    lib.br2_metrics.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     lib.br2_kernel_info.argtypes = [ctypes.c_void_p] + [_i32p] * 6
     lib.br2_select_kernel.argtypes = [ctypes.c_void_p, ctypes.c_int32]
     lib.br2_replay_count.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]

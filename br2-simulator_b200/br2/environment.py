@@ -160,7 +160,7 @@ class Environment:
 
         previous = None
         if check_steady_state == 2:
-            previous = {short: self._state_stack(short).clone() for short in ("x", "v", "a", "Q", "w", "alpha")}
+            previous = engine.state.clone()  # the reference concatenates copies of six arrays per rod (:255-266)
 
         if not duration:
             duration = dt
@@ -189,45 +189,28 @@ class Environment:
             progress.close()
         self.time = time
 
-        torch = engine.torch
+        # ---- terminal checks (reference :289-349): one device kernel reduces the batch state to a few numbers per
+        # instance (br2_metrics); one gather brings the ranks' rows together
+        if check_steady_state in (1, 2) or check_nan:
+            metrics = engine.metrics(previous)
+            metrics = _dist.gather_batch(metrics, self.global_batch, device=engine.device).cpu().numpy()
         if check_steady_state == 1:
             # the reference measures node POSITIONS here although it calls them velocities (:292-298)
-            per_instance = torch.linalg.vector_norm(self._state_stack("x"), dim=1).amax(dim=-1)
-            per_instance = _dist.gather_batch(per_instance, self.global_batch, device=self.engine.device)
-            max_velocity = float(per_instance.max())
+            per_instance = metrics[:, 1]
+            max_velocity = float(per_instance.max()) if not np.isnan(per_instance).any() else float("nan")
             status.velocity_steady_state_status = max_velocity < self.velocity_threshold
             status.max_velocity = max_velocity
-            status.max_velocity_per_instance = per_instance.cpu().numpy()
+            status.max_velocity_per_instance = per_instance
         elif check_steady_state == 2:
             # the reference computes these six deltas and discards them (:300-338); they are exposed
             # under a name its combined_* properties do not pick up.
-            deltas = {}
-            for short in previous:
-                diff = previous[short] - self._state_stack(short)
-                dims = (1, 2) if short == "Q" else (1,)
-                norms = torch.linalg.vector_norm(diff, dim=dims)
-                deltas[short] = torch.nan_to_num(norms, nan=-np.inf).amax(dim=-1).cpu().numpy()
-            status.steady_state_deltas = deltas
-        # instances that left the optimistic kernel's range with no exact-path kernel to redo them stop advancing
-        # (br2_cuda.cu: br2_select_kernel): never silently -- checked after every run (one small device-to-host copy).
-        # With a collective check requested below every rank must fail together, so the flag is reduced first.
-        stuck = engine.unresolved_count()
-        if self.world_size > 1 and (check_nan or check_steady_state == 1):
-            stuck_anywhere = _dist.reduce_flags(stuck > 0)
-        else:
-            stuck_anywhere = stuck > 0
-        if stuck_anywhere:
-            raise _native.Br2Error(
-                "%d instance(s) of this rank left the validity range of the device kernel's series (%s) and this assembly "
-                "has no exact-path kernel; they stopped advancing" % (stuck, engine.replay_reasons()))
+            status.steady_state_deltas = {short: metrics[:, 3 + i] for i, short in enumerate(("x", "v", "a", "Q", "w", "alpha"))}
         if check_nan:
+            mask = metrics[:, 0].astype(np.int64)
             flags = {}
-            for label, short in (("position", "x"), ("velocity", "v"), ("director", "Q"), ("omega", "w")):
-                per_instance = torch.isnan(self._state_stack(short)).flatten(1).any(dim=1)
-                per_instance = _dist.gather_batch(per_instance.to(torch.int32), self.global_batch,
-                                                  device=self.engine.device).bool()
-                flags[label] = per_instance.cpu().numpy()
-                setattr(status, "%s_nan_status" % label, bool(per_instance.any()))
+            for bit, label in enumerate(("position", "velocity", "director", "omega")):
+                flags[label] = (mask >> bit & 1).astype(bool)
+                setattr(status, "%s_nan_status" % label, bool(flags[label].any()))
             status.nan_per_instance = flags
         status.end_status = True
         return status

@@ -26,6 +26,7 @@
 #endif
 #include "br2_fast.cuh"
 #include "br2_generic.cuh"
+#include "br2_metrics.cuh"
 #include "br2_tables.cuh"
 #include "br2_tile.cuh"
 
@@ -94,7 +95,7 @@ struct KernelChoice {
 #define BR2_TILE_SPLIT_SINGLE false
 #endif
 #ifndef BR2_TILE_SPLIT_EXTRA
-#define BR2_TILE_SPLIT_EXTRA true
+#define BR2_TILE_SPLIT_EXTRA false
 #endif
 #ifndef BR2_TILE_SPLIT_CLUSTER
 #define BR2_TILE_SPLIT_CLUSTER true
@@ -985,6 +986,24 @@ int br2_replay_reasons(br2_handle h, int64_t *rotation, int64_t *curvature, int6
     if (rotation) *rotation = (int64_t)v[1];
     if (curvature) *curvature = (int64_t)v[2];
     if (strain) *strain = (int64_t)v[3];
+    return BR2_OK;
+}
+
+int br2_metrics(br2_handle h, const double *dev_previous, double *dev_out, void *stream) {
+    if (!h || !dev_out) return fail(BR2_EINVAL, "br2_metrics: bad argument");
+    if (!h->state) return fail(BR2_ESTATE, "br2_metrics: no state bound (call br2_bind_state)");
+    CUDA_TRY(cudaSetDevice(h->device));
+    br2::MetricsParams mp;
+    mp.t = h->t;
+    mp.state = h->state;
+    mp.previous = dev_previous;
+    mp.out = dev_out;
+    mp.batch = h->batch;
+    int sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    const long long want = h->batch < 16LL * sms ? h->batch : 16LL * sms;  // grid-stride over the instances
+    br2::br2_metrics_kernel<<<(unsigned)want, br2::kMetricsThreads, 0, (cudaStream_t)stream>>>(mp);
+    CUDA_TRY(cudaGetLastError());
     return BR2_OK;
 }
 

@@ -76,40 +76,34 @@ __device__ __forceinline__ void mbar_arrive_warp(uint32_t bar) {
     __syncwarp();
     if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_thread(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// arrive on the same barrier of CTA `rank` of the cluster, after this thread's (remote) stores: release at cluster scope
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, int rank) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n"
-        ".reg .b32 ra;\n"
-        "mapa.shared::cluster.u32 ra, %0, %1;\n"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
-        "}" ::"r"(bar), "r"(rank) : "memory");
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
 }
-template <bool kClusterScope>
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (kClusterScope)
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "WAIT_LOOP:\n"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
-            "@p bra WAIT_DONE;\n"
-            "bra WAIT_LOOP;\n"
-            "WAIT_DONE:\n"
-            "}" ::"r"(bar), "r"(parity) : "memory");
-    else
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "WAIT_LOOP:\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-            "@p bra WAIT_DONE;\n"
-            "bra WAIT_LOOP;\n"
-            "WAIT_DONE:\n"
-            "}" ::"r"(bar), "r"(parity) : "memory");
+// ---- pushes into a peer CTA's shared memory (cluster kernels) -------------------------------------------------------
+// st.async writes 8 bytes into the peer's shared memory and, when the write has landed, counts them off the peer's
+// mbarrier (complete_tx).  The consumer arms the barrier with the byte count it expects (one arrive.expect_tx per step)
+// and waits on it at CTA scope: no release / acquire fence at cluster scope anywhere -- those compile to MEMBAR.ALL.GPU
+// on the producer and CCTL.IVALL (an L1 invalidation) on the consumer, which the first version of this path paid per step.
+__device__ __forceinline__ uint32_t cluster_addr(uint32_t local, int rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
+    return remote;
+}
+__device__ __forceinline__ void st_async_f64(uint32_t remote, double v, uint32_t remote_bar) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote),
+                 "l"(__double_as_longlong(v)), "r"(remote_bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // the step's exchange points: arrive after publishing, wait before reading; kSplit = false degenerates to one
 // __syncthreads at the wait
@@ -200,7 +194,8 @@ struct TileSmem {
     //   XPM [n_xe]    int  bit r set: the CTA of cluster rank r consumes the element's data
     //   XIT [n_xitems] int node items (joint << 1 | sign)
     static constexpr int EX = ROWS_END;
-    static constexpr int EXW = 20;                // doubles per published element
+    static constexpr int EXW = 20;                // doubles per published element (row stride)
+    static constexpr int EXN = 19;                // ... of which in use
 };
 
 constexpr int TILE_F_VALID = 1, TILE_F_ELEM = 2, TILE_F_VOR = 4, TILE_F_ZERO_V = 8, TILE_F_ZERO_W = 16, TILE_F_OWN = 32,
@@ -331,6 +326,8 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
     }
 #pragma unroll
     for (int i = 0; i < 9; ++i) sm[L::QF + i * R + t] = Q[0][i];
+    if (kCluster && threadIdx.x == 0 && p.tile.xb_count[rank] > 0)  // arm this step's buffer: bytes my peers (and I) will push into it
+        mbar_expect_tx(xbar, (uint32_t)(L::EXN * 8 * p.tile.xb_count[rank]));
     tile_arrive<kSplit>(bars.b1);
     if (!kSplit) __syncthreads();  // B1
 
@@ -345,7 +342,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
         double radx[C];
 #pragma unroll
         for (int j = 0; j < C; ++j) {
-            if (kSplit && j == C - 1) mbar_wait<false>(bars.b1, (uint32_t)gstep & 1u);  // B1
+            if (kSplit && j == C - 1) mbar_wait(bars.b1, (uint32_t)gstep & 1u);  // B1
             const bool elem = th.fl[j] & TILE_F_ELEM;
             double d[3], dv[3];
 #pragma unroll
@@ -426,30 +423,37 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 #pragma unroll
         for (int i = 0; i < 3; ++i) sm[L::SKL + i * R + t] = skp[i];
         if (kExtras) {
-            // push what the tip-to-base joints need from my elements into every consuming CTA's buffer of this step's parity
-            // (start-of-step director and omega: the overwrite in P4 comes later).  After B1 on purpose: every warp of this CTA
-            // has then finished the previous step, so a peer that races ahead on my data cannot overwrite a buffer still read.
+            // What the tip-to-base joints need from my elements goes into every consuming CTA's buffer of this step's parity
+            // (start-of-step director and omega: the overwrite in P4 comes later).  One CTA: plain stores, ordered before
+            // their readers by B2.  Cluster: asynchronous stores that count themselves off the consumer's barrier -- after B1
+            // on purpose: every warp of this CTA has then finished the previous step, so a peer that races ahead on my data
+            // cannot overwrite a buffer still being read.
 #pragma unroll
             for (int j = 0; j < C; ++j) {
                 const int pub = (th.xinfo[j] & 0xFF) - 1;
                 if (pub >= 0) {
-                    const int mask = XPM[pub];
-                    for (int r = 0; r < (kCluster ? p.tile.n_ctas : 1); ++r) {
-                        if (!((mask >> r) & 1)) continue;
-                        double *dst = tile_peer<kCluster>(EXD, r) + pub * L::EXW;
+                    double val[L::EXN];
 #pragma unroll
-                        for (int i = 0; i < 9; ++i) dst[i] = Q[j][i];
+                    for (int i = 0; i < 9; ++i) val[i] = Q[j][i];
 #pragma unroll
-                        for (int i = 0; i < 3; ++i) {
-                            dst[9 + i] = w[j][i];
-                            dst[13 + i] = sm[L::PC + (3 * j + i) * R + t];
-                            dst[16 + i] = sm[L::PV + (3 * j + i) * R + t];
+                    for (int i = 0; i < 3; ++i) {
+                        val[9 + i] = w[j][i];
+                        val[13 + i] = sm[L::PC + (3 * j + i) * R + t];
+                        val[16 + i] = sm[L::PV + (3 * j + i) * R + t];
+                    }
+                    val[12] = radx[j];
+                    if (kCluster) {
+                        const int mask = XPM[pub];
+                        const uint32_t local = smem_addr(EXD + pub * L::EXW);
+                        for (int r = 0; r < p.tile.n_ctas; ++r) {
+                            if (!((mask >> r) & 1)) continue;
+                            const uint32_t dst = cluster_addr(local, r), bar = cluster_addr(xbar, r);
+#pragma unroll
+                            for (int i = 0; i < L::EXN; ++i) st_async_f64(dst + 8 * i, val[i], bar);
                         }
-                        dst[12] = radx[j];
-                        if (kCluster)
-                            mbar_arrive_remote(xbar, r);
-                        else
-                            mbar_arrive_thread(xbar);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < L::EXN; ++i) EXD[pub * L::EXW + i] = val[i];
                     }
                 }
             }
@@ -505,7 +509,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 #pragma unroll
         for (int i = 0; i < 3; ++i) sm[L::ML + i * R + t] = fma(0.5, cp[i], -ap[i]);
     }
-    if (kSplit) mbar_wait<false>(bars.b2, (uint32_t)gstep & 1u);  // B2
+    if (kSplit) mbar_wait(bars.b2, (uint32_t)gstep & 1u);  // B2
 
     // =============================== P3b: own joints (Appendix A.7) ==========================
     // my element is rod two; rod one's contribution comes from its published rows
@@ -576,7 +580,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
                 const double fac = fmin(1.0, time_mid / jd[3]);
                 JF[xj * 4 + i] = jd[i] * fac;
             } else {
-                mbar_wait<kCluster>(xbar, xparity);  // everything pushed for this step has landed
+                if (kCluster) mbar_wait(xbar, xparity);  // everything pushed for this step has landed (one CTA: B2 did that)
                 const double *e1 = EXD + ja.x * L::EXW, *e2 = EXD + ja.y * L::EXW;
                 const double *q1 = EXD + jb.x * L::EXW, *q2 = EXD + jb.y * L::EXW;
                 const double kj = jd[0], nuj = jd[1];
@@ -598,7 +602,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
         for (int j = 0; j < C; ++j) tile_damper_exponentials<kExact>(p, len[j], th.fl[j], dexp[j], th.bad);
     }
     if (kSplit)
-        mbar_wait<false>(bars.b3, (uint32_t)gstep & 1u);  // B3
+        mbar_wait(bars.b3, (uint32_t)gstep & 1u);  // B3
     else
         __syncthreads();  // B3
 
@@ -651,7 +655,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
             if (kExtras && (th.xinfo[j] >> 8) != 0) {
                 if (kLast) {  // half forces of the extra joints on this node (every other step: after the rotation below)
                     const int cnt = (th.xinfo[j] >> 16) & 0xF, first = th.xinfo[j] >> 20;
-                    if (kSplit && cnt) mbar_wait<false>(bars.b4, (uint32_t)gstep & 1u);
+                    if (kSplit && cnt) mbar_wait(bars.b4, (uint32_t)gstep & 1u);
                     for (int q = 0; q < cnt; ++q) {
                         const int item = XIT[first + q];
                         const double sgn = (item & 1) ? -1.0 : 1.0;
@@ -667,7 +671,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
                 // (after the surface joints above have used the old director); sources are start-of-step values
                 const int ow = ((th.xinfo[j] >> 8) & 0xFF) - 1;
                 if (ow >= 0) {
-                    mbar_wait<kCluster>(xbar, xparity);
+                    if (kCluster) mbar_wait(xbar, xparity);
                     const double *src = EXD + ow * L::EXW;
 #pragma unroll
                     for (int i = 0; i < 9; ++i) Q[j][i] = src[i];
@@ -763,7 +767,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
             for (int j = 0; j < C; ++j) {
                 const int cnt = (th.xinfo[j] >> 16) & 0xF, first = th.xinfo[j] >> 20;
                 if (cnt) {
-                    if (kSplit) mbar_wait<false>(bars.b4, (uint32_t)gstep & 1u);
+                    if (kSplit) mbar_wait(bars.b4, (uint32_t)gstep & 1u);
                     // the first three items (a joined element's node has three: one per rod of the other segment) without a
                     // branch between them, so that their loads are in flight together; same order of summation as the loop
                     int item[3];
@@ -835,10 +839,8 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
     if (kSplit || kExtras) {
         if (t == 0) {
             for (int i = 0; i < 4; ++i) mbar_init(bars.b1 + 8 * i, NT / 32);
-            // one arrival per published element this CTA consumes, per step
-            const int pushes = kExtras ? max(tp.xb_count[rank], 1) : 1;
-            mbar_init(bars.xb, pushes);
-            mbar_init(bars.xb + 8, pushes);
+            mbar_init(bars.xb, 1);  // one arming arrive per step (expect_tx); the pushes count bytes, not arrivals
+            mbar_init(bars.xb + 8, 1);
             if (kCluster) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         // (visible to the CTA, and to the cluster, at the first tile_sync of the item loop)

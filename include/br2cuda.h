@@ -252,6 +252,16 @@ int br2_unresolved_count(br2_handle h, int64_t *count);
  * (neighbouring elements rotated too far apart) and the damper's exponential (axial strain too large); only
  * the tile kernel records reasons.  Synchronises the device. */
 int br2_replay_reasons(br2_handle h, int64_t *rotation, int64_t *curvature, int64_t *strain);
+/* Terminal metrics of a run, per instance, in ONE pass over the batch state on `stream` (replaces the host-side checks of
+ * environment.py:289-349): dev_out [batch][BR2_METRICS_N] doubles =
+ *   [0] NaN mask (bit 0 position, 1 velocity, 2 director, 3 omega; :343-348)   [1] max_nodes |x| (the reference's "velocity"
+ *   steady-state test measures positions, :292-298; NaN if any is)             [2] max_nodes |v|
+ *   [3..8] nanmax |previous - current| of position, velocity, acceleration, director (Frobenius norm per element), omega,
+ *   alpha (:300-338) when dev_previous -- a copy of the state block taken before the run -- is given, else -inf.
+ * Asynchronous; read dev_out after synchronising the stream. */
+#define BR2_METRICS_N 12
+int br2_metrics(br2_handle h, const double *dev_previous, double *dev_out, void *stream);
+
 /* Evaluate the fast kernel's fp64 helpers on device arrays of n doubles (tests only):
  * which = 0 rcp, 1 rsqrt, 2 sinc(theta) [in: theta^2 <= 0.01], 3 cosc(theta) [in: theta^2 <= 0.01],
  *         4 log-map scale [in: cos theta >= 0.875], 5 exp(d) [in: |d| <= 0.02];

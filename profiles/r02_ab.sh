@@ -3,7 +3,7 @@
 tag=$1; lib=$2
 [ -n "$lib" ] && export BR2_CUDA_LIB=$PWD/$lib
 B="timeout -s KILL 300 python bench.py --no-extras --no-cpu-baseline"
-$B --steps 5 --warmup 3 > gpurun_out/${tag}_single.json 2> gpurun_out/${tag}_single.err
+$B --steps 3 --warmup 3 > gpurun_out/${tag}_single.json 2> gpurun_out/${tag}_single.err
 $B --workload double --steps 3 --warmup 2 > gpurun_out/${tag}_double.json 2> gpurun_out/${tag}_double.err
 $B --workload triple --steps 3 --warmup 2 > gpurun_out/${tag}_triple.json 2> gpurun_out/${tag}_triple.err
 $B --workload triple200 --batch 1024 --steps 3 --warmup 2 > gpurun_out/${tag}_t200x1024.json 2> gpurun_out/${tag}_t200x1024.err

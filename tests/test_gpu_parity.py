@@ -695,3 +695,39 @@ def test_work_queue_grouping_does_not_change_a_bit(assembly, monkeypatch):
     assert np.isfinite(states[0]).all()
     np.testing.assert_array_equal(states[0], states[1])
     np.testing.assert_array_equal(states[0], states[2])
+
+
+def test_terminal_metrics_kernel_matches_the_reference_formulas():
+    """br2_metrics (one device pass over the batch state) against the reference's own numpy expressions
+    (/root/reference/br2/environment.py:289-349) evaluated on host copies: steady-state mode 1 and mode 2, NaN flags,
+    per instance; one instance is poisoned with a NaN to exercise numpy's max / nanmax semantics."""
+    batch, dt = 5, 2.0e-5
+    pressures = np.random.default_rng(5).uniform(0.0, 40.0, size=(3, batch)) * PSI
+    action = {name: pressures[i] for i, name in enumerate(NAMES)}
+    env = make_env("double", batch)
+    env.simulator._callback_ops = []
+    env.run(action, duration=200 * dt - 0.5 * dt, disable_progress_bar=True)
+    fields = ("position_collection", "velocity_collection", "acceleration_collection", "director_collection",
+              "omega_collection", "alpha_collection")
+    before = {f: np.concatenate([getattr(rod, f) for rod in env.simulator], axis=-1) for f in fields}
+    status = env.run(action, duration=150 * dt - 0.5 * dt, disable_progress_bar=True, check_nan=True, check_steady_state=2)
+    after = {f: np.concatenate([getattr(rod, f) for rod in env.simulator], axis=-1) for f in fields}
+    for short, f in zip(("x", "v", "a", "Q", "w", "alpha"), fields):
+        axis = (1, 2) if short == "Q" else 1
+        want = np.nanmax(np.linalg.norm(before[f] - after[f], axis=axis), axis=-1)  # per instance
+        got = status.steady_state_deltas[short]
+        assert got.shape == (batch,) and np.abs(got - want).max() <= 1e-13 * max(want.max(), 1e-300), short
+    assert not any(status.nan_per_instance[k].any() for k in status.nan_per_instance)
+    # mode 1 + NaN semantics: poison one node of instance 2
+    x = env.simulator[3].position_collection
+    x[2, 1, 7] = np.nan
+    env.simulator[3].position_collection = x
+    status = env.run(action, duration=None, disable_progress_bar=True, check_nan=True, check_steady_state=1)
+    after_x = np.concatenate([rod.position_collection for rod in env.simulator], axis=-1)
+    want = np.linalg.norm(after_x, axis=1).max(axis=-1)
+    clean = [0, 1, 3, 4]
+    assert np.isnan(status.max_velocity_per_instance[2]) and np.isnan(want[2]) and np.isnan(status.max_velocity)
+    assert np.abs(status.max_velocity_per_instance[clean] - want[clean]).max() <= 1e-14
+    assert list(status.nan_per_instance["position"]) == [False, False, True, False, False]
+    assert status.position_nan_status
+    env.close()
