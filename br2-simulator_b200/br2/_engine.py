@@ -93,6 +93,22 @@ class Engine:
             host[a, :] = np.asarray(value, dtype=np.float64)
         self.pressures[: self.n_actions].copy_(self.torch.from_numpy(host), non_blocking=False)
 
+    def set_instance_params(self, uni=None, act_d=None, joint_scale=None):
+        """Material constants that differ between the instances (br2_set_instance_params, include/br2cuda.h): host arrays
+        ``uni [batch, FC_COUNT]``, ``act_d [batch, n_act, 3]``, ``joint_scale [batch]``; ``None`` returns to the shared
+        constants.  The device copies are kept alive here (the library borrows them)."""
+        if uni is None:
+            _native.check(self.lib.br2_set_instance_params(self.handle, None, None, None))
+            self._instance_tables = None
+            return
+        torch = self.torch
+        tables = []
+        for array, shape in ((uni, (self.batch, -1)), (act_d, (self.batch, -1)), (joint_scale, (self.batch,))):
+            host = np.ascontiguousarray(np.asarray(array, dtype=np.float64).reshape(shape))
+            tables.append(torch.from_numpy(host).to(self.device) if host.size else torch.zeros(1, dtype=torch.float64, device=self.device))
+        _native.check(self.lib.br2_set_instance_params(self.handle, *[t.data_ptr() for t in tables]))
+        self._instance_tables = tables
+
     # ------------------------------------------------------------------ stepping
     def step(self, n_steps, t0, dt):
         """Advance all instances ``n_steps`` steps on the current stream; returns the end time."""
@@ -103,7 +119,7 @@ class Engine:
                                             ctypes.c_void_p(stream), ctypes.byref(t_end)))
         if n_steps > 0:
             # the fast kernel is followed by the exact-path replay pass (br2_step launches both)
-            self.launches += 2 if self._variant else 1
+            self.launches += 2 if self._variant and getattr(self, "_instance_tables", None) is None else 1
         return t_end.value
 
     def metrics(self, previous=None):

@@ -47,7 +47,7 @@ EXPORTS = (
     "br2_last_error", "br2_abi_version", "br2_create", "br2_destroy", "br2_words_per_instance",
     "br2_bind_state", "br2_set_actuation", "br2_step", "br2_step_host", "br2_count_steps",
     "br2_kernel_info", "br2_fp64_peak_tflops", "br2_select_kernel", "br2_selftest_math", "br2_replay_count",
-    "br2_replay_reasons", "br2_unresolved_count", "br2_describe_plan", "br2_capture_plan", "br2_metrics",
+    "br2_replay_reasons", "br2_unresolved_count", "br2_describe_plan", "br2_capture_plan", "br2_metrics", "br2_set_instance_params",
 )
 
 
@@ -76,6 +76,7 @@ def load():
                                     ctypes.POINTER(ctypes.c_int64), _f64p]
     lib.br2_capture_plan.argtypes = [ctypes.c_double, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p, ctypes.c_int32,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]
+    lib.br2_set_instance_params.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     lib.br2_metrics.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     lib.br2_kernel_info.argtypes = [ctypes.c_void_p] + [_i32p] * 6
     lib.br2_select_kernel.argtypes = [ctypes.c_void_p, ctypes.c_int32]

@@ -125,6 +125,9 @@ class Environment:
         assert os.path.exists(rod_database_path), "Rod database path does not exists."
         assert os.path.exists(assembly_config_path), "Assembly configuration does not exists."
         verbose = kwargs.pop("verbose", False)
+        # extension: material parameters that differ between the instances of the batch (br2/_sweep.py), e.g.
+        # per_instance={"youngs_modulus": np.linspace(0.8e7, 1.2e7, batch), "alpha": 60 + rng.normal(size=batch)}
+        per_instance = kwargs.pop("per_instance", None)
         self.assy = FreeAssembly(self, **kwargs)
         self.shearable_rods = self.assy.build(rod_database_path, assembly_config_path, verbose=verbose)
         self.simulator = self.assy.simulator
@@ -133,6 +136,14 @@ class Environment:
         self.simulator.device = self.device
         self.simulator.finalize()
         self.engine = self.simulator.engine
+        if per_instance:
+            from . import _sweep
+
+            start, stop = self.batch_range
+            local = {key: (value if np.ndim(value) == 0 else np.asarray(value)[start:stop] if len(value) == self.global_batch
+                           else value) for key, value in per_instance.items()}
+            self.engine.set_instance_params(*_sweep.instance_tables(self.assy, self.simulator.program, local, self.batch,
+                                                                    self.time_step))
         self.do_step, self.stages_and_updates = extend_stepper_interface(self.StatefulStepper, self.simulator)
         self.time = start_time
 

@@ -136,6 +136,7 @@ class FreeAssembly:
         self.simulator = BR2Simulator()
         self.actuation = defaultdict(list)
         self.free = {}  # "<segment>_<position>_<rod type>" -> rod
+        self.rod_specs = {}  # same keys -> the rod spec it was built from (br2/_sweep.py recomputes constants from it)
         self.toggle_gravity = gravity
         # "t_multiplier" (sic) scales the joint stiffness in the reference (:88)
         self.k_multiplier = kwargs.get("t_multiplier", 1)
@@ -182,6 +183,7 @@ class FreeAssembly:
                 spec["base_radius"] = spec["outer_radius"]
                 if "gamma" in spec:
                     spec["gamma"] = [angle + seg["y-rotation"][position] for angle in spec["gamma"]]
+                    spec["y_rotation"] = seg["y-rotation"][position]  # (kept for br2/_sweep.py)
                 name = "%s_%d_%s" % (seg_name, position, rod_type)
                 self.free[name] = self.add_free(name, _first_action_of(activations, seg_name, position), **spec)
                 members.append(name)
@@ -263,6 +265,7 @@ class FreeAssembly:
     def add_free(self, name, actuation_name, alpha=[], beta=[], gamma=[], **rod_spec):
         rod = self.create_rod(name, **rod_spec)
         shared = self.get_actuation_reference(actuation_name)
+        self.rod_specs[name] = dict(rod_spec, alpha=list(alpha), beta=list(beta), gamma=list(gamma), actuated=shared is not None)
         if shared is not None:
             self.add_angled_fibers(rod, shared, alpha)
             self.add_angled_fibers(rod, shared, beta)

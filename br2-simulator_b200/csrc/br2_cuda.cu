@@ -78,6 +78,7 @@ typedef void (*kernel_fn)(const StepParams);
 struct KernelChoice {
     int threads;
     kernel_fn fn;
+    kernel_fn fn_pi;  // tile kernels: the instantiation that reads per-instance material constants (or nullptr)
 };
 
 #ifndef BR2_TILE_C
@@ -103,37 +104,47 @@ struct KernelChoice {
 // variant 3: tile kernel (BR2_TILE_C slots per thread, uniform constants); `threads` = CTA size
 // template flags: <slots per thread, CTA threads, min CTAs per SM, extra joints, cluster, exact arithmetic, split-phase barriers>
 const KernelChoice kTileKernels[] = {  // single-segment assemblies (ring joints only)
-    {64, br2::br2_step_tile_kernel<BR2_TILE_C, 64, BR2_TILE_MB64, false, false, false, BR2_TILE_SPLIT_SINGLE>},
-    {128, br2::br2_step_tile_kernel<BR2_TILE_C, 128, 3, false, false, false, BR2_TILE_SPLIT_EXTRA>},
-    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, false, false, false, BR2_TILE_SPLIT_CLUSTER>},
+    {64, br2::br2_step_tile_kernel<BR2_TILE_C, 64, BR2_TILE_MB64, false, false, false, BR2_TILE_SPLIT_SINGLE>,
+     br2::br2_step_tile_kernel<BR2_TILE_C, 64, BR2_TILE_MB64, false, false, false, BR2_TILE_SPLIT_SINGLE, true>},
+    {128, br2::br2_step_tile_kernel<BR2_TILE_C, 128, 3, false, false, false, BR2_TILE_SPLIT_EXTRA>,
+     br2::br2_step_tile_kernel<BR2_TILE_C, 128, 3, false, false, false, BR2_TILE_SPLIT_EXTRA, true>},
+    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, false, false, false, BR2_TILE_SPLIT_CLUSTER>,
+     br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, false, false, false, BR2_TILE_SPLIT_CLUSTER, true>},
 };
 const KernelChoice kTileExtraKernels[] = {  // several segments joined tip to base, one CTA
-    {128, br2::br2_step_tile_kernel<BR2_TILE_C, 128, 3, true, false, false, BR2_TILE_SPLIT_EXTRA>},
-    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true, false, false, BR2_TILE_SPLIT_EXTRA>},
-    {256, br2::br2_step_tile_kernel<BR2_TILE_C, 256, 1, true, false, false, BR2_TILE_SPLIT_EXTRA>},
+    {128, br2::br2_step_tile_kernel<BR2_TILE_C, 128, 3, true, false, false, BR2_TILE_SPLIT_EXTRA>,
+     br2::br2_step_tile_kernel<BR2_TILE_C, 128, 3, true, false, false, BR2_TILE_SPLIT_EXTRA, true>},
+    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true, false, false, BR2_TILE_SPLIT_EXTRA>,
+     br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true, false, false, BR2_TILE_SPLIT_EXTRA, true>},
+    {256, br2::br2_step_tile_kernel<BR2_TILE_C, 256, 1, true, false, false, BR2_TILE_SPLIT_EXTRA>,
+     br2::br2_step_tile_kernel<BR2_TILE_C, 256, 1, true, false, false, BR2_TILE_SPLIT_EXTRA, true>},
 };
 // one CTA per group of ring-connected rods, launched as a thread-block cluster per instance
 const KernelChoice kTileClusterKernels[] = {
-    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true, true, false, BR2_TILE_SPLIT_CLUSTER>},
-    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, true, true, false, BR2_TILE_SPLIT_CLUSTER>},
+    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true, true, false, BR2_TILE_SPLIT_CLUSTER>,
+     br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true, true, false, BR2_TILE_SPLIT_CLUSTER, true>},
+    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, true, true, false, BR2_TILE_SPLIT_CLUSTER>,
+     br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, true, true, false, BR2_TILE_SPLIT_CLUSTER, true>},
 };
 const KernelChoice kTileClusterExactKernels[] = {  // same, exact arithmetic: the replay path of cluster-sized assemblies
-    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true, true, true, BR2_TILE_SPLIT_CLUSTER>},
-    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, true, true, true, BR2_TILE_SPLIT_CLUSTER>},
+    {192, br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true, true, true, BR2_TILE_SPLIT_CLUSTER>,
+     br2::br2_step_tile_kernel<BR2_TILE_C, 192, 2, true, true, true, BR2_TILE_SPLIT_CLUSTER, true>},
+    {320, br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, true, true, true, BR2_TILE_SPLIT_CLUSTER>,
+     br2::br2_step_tile_kernel<BR2_TILE_C, 320, 1, true, true, true, BR2_TILE_SPLIT_CLUSTER, true>},
 };
 const int kTileMaxCtaThreads = 320, kTileOneCtaThreads = 256;
 
 // variant 0: generic, 1: fast with per-slot constants, 2: fast with uniform constants
 const KernelChoice kKernels[3][6] = {
-    {{128, br2::br2_step_generic_kernel<128, 4>}, {256, br2::br2_step_generic_kernel<256, 2>},
-     {384, br2::br2_step_generic_kernel<384, 1>}, {512, br2::br2_step_generic_kernel<512, 1>},
-     {768, br2::br2_step_generic_kernel<768, 1>}, {1024, br2::br2_step_generic_kernel<1024, 1>}},
-    {{128, br2::br2_step_fast_kernel<128, BR2_MB128, false>}, {256, br2::br2_step_fast_kernel<256, 2, false>},
-     {384, br2::br2_step_fast_kernel<384, 1, false>}, {512, br2::br2_step_fast_kernel<512, 1, false>},
-     {768, br2::br2_step_fast_kernel<768, 1, false>}, {1024, br2::br2_step_fast_kernel<1024, 1, false>}},
-    {{128, br2::br2_step_fast_kernel<128, BR2_MB128, true>}, {256, br2::br2_step_fast_kernel<256, 2, true>},
-     {384, br2::br2_step_fast_kernel<384, 1, true>}, {512, br2::br2_step_fast_kernel<512, 1, true>},
-     {768, br2::br2_step_fast_kernel<768, 1, true>}, {1024, br2::br2_step_fast_kernel<1024, 1, true>}},
+    {{128, br2::br2_step_generic_kernel<128, 4>, nullptr}, {256, br2::br2_step_generic_kernel<256, 2>, nullptr},
+     {384, br2::br2_step_generic_kernel<384, 1>, nullptr}, {512, br2::br2_step_generic_kernel<512, 1>, nullptr},
+     {768, br2::br2_step_generic_kernel<768, 1>, nullptr}, {1024, br2::br2_step_generic_kernel<1024, 1>, nullptr}},
+    {{128, br2::br2_step_fast_kernel<128, BR2_MB128, false>, nullptr}, {256, br2::br2_step_fast_kernel<256, 2, false>, nullptr},
+     {384, br2::br2_step_fast_kernel<384, 1, false>, nullptr}, {512, br2::br2_step_fast_kernel<512, 1, false>, nullptr},
+     {768, br2::br2_step_fast_kernel<768, 1, false>, nullptr}, {1024, br2::br2_step_fast_kernel<1024, 1, false>, nullptr}},
+    {{128, br2::br2_step_fast_kernel<128, BR2_MB128, true>, nullptr}, {256, br2::br2_step_fast_kernel<256, 2, true>, nullptr},
+     {384, br2::br2_step_fast_kernel<384, 1, true>, nullptr}, {512, br2::br2_step_fast_kernel<512, 1, true>, nullptr},
+     {768, br2::br2_step_fast_kernel<768, 1, true>, nullptr}, {1024, br2::br2_step_fast_kernel<1024, 1, true>, nullptr}},
 };
 
 }  // namespace
@@ -161,6 +172,10 @@ struct br2_handle_s {
     unsigned long long *work = nullptr;  // tile kernel's queue: [0] item counter, then int progress[batch]
     int tile_capacity = 0;            // CTAs of the tile kernel resident on the device
     unsigned long long *replays = nullptr;  // device counter
+    const double *inst_uni = nullptr;          // per-instance material constants (borrowed device buffers), or nullptr
+    const double *inst_act_d = nullptr;
+    const double *inst_joint_scale = nullptr;
+    int n_act = 0;
     double *scratch_state = nullptr;  // br2_step_host
     double *scratch_pressures = nullptr;
     long long scratch_batch = 0;
@@ -424,21 +439,20 @@ bool make_tile_plan(const br2_program *p, int C, br2::TilePlan *plan, TileExtraT
     for (int xe = 0; xe < plan->n_xe; ++xe)
         for (int r = 0; r < plan->n_ctas; ++r)
             if (xe_mask[xe] & (1 << r)) ++plan->xb_count[r];
-    // the extra joints are evaluated one COMPONENT per thread, by consecutive threads of the CTA's LAST warps: a warp executes
-    // the joint code once whichever of its lanes take part, so packing them keeps the other warps' issue slots free
-    {
-        int used[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // The extra joints are evaluated one COMPONENT per thread, by consecutive threads of the CTA's LAST warps: a warp executes
+    // the joint code once whichever of its lanes take part, so packing them keeps the other warps' issue slots free.
+    // (Placing them on warps without any other duty in the extra-joint protocol was measured: no difference.)
+    for (int rank = 0; rank < plan->n_ctas; ++rank) {
+        const int ct = plan->cta_threads[rank], warps = (ct + 31) / 32;
+        const int last = ct - (warps - 1) * 32;  // threads in use in the last warp
+        int used = 0;
         for (int xj = 0; xj < plan->n_xj; ++xj) {
-            for (int rank = 0; rank < plan->n_ctas; ++rank) {
-                if (!(xj_ranks[xj] & (1 << rank))) continue;
-                const int ct = plan->cta_threads[rank], warps = (ct + 31) / 32;
-                const int last = ct - (warps - 1) * 32;  // threads in use in the last warp
-                for (int comp = 0; comp < 3; ++comp) {
-                    const int k = used[rank]++;  // k-th (joint, component) of this CTA: lanes 0.. of the last warp, then the one before, ...
-                    const int t = (k < last) ? (warps - 1) * 32 + k : (warps - 2 - (k - last) / 32) * 32 + (k - last) % 32;
-                    if (t < 0) return *why = "more extra joint components than threads", false;
-                    xt->xi[(size_t)(rank * plan->xi_stride + t) * XN + BR2_TILE_XI_JOINT] = (xj << 2) | comp;
-                }
+            if (!(xj_ranks[xj] & (1 << rank))) continue;
+            for (int comp = 0; comp < 3; ++comp) {
+                const int k = used++;  // k-th (joint, component) of this CTA: lanes 0.. of the last warp, then the one before, ...
+                const int t = (k < last) ? (warps - 1) * 32 + k : (warps - 2 - (k - last) / 32) * 32 + (k - last) % 32;
+                if (t < 0) return *why = "more extra joint components than threads", false;
+                xt->xi[(size_t)(rank * plan->xi_stride + t) * XN + BR2_TILE_XI_JOINT] = (xj << 2) | comp;
             }
         }
     }
@@ -516,6 +530,7 @@ int br2_create(const br2_program *p, int device, br2_handle *out) {
         UP(fast_c, S * BR2_FC_COUNT);
         UP(act_i, (size_t)p->n_act);
         UP(act_d, (size_t)p->n_act * 3);
+        h->n_act = p->n_act;
         t.act_inv_ramp = 1.0 / p->act_ramp_up_time;
         for (int i = 0; i < BR2_FC_COUNT; ++i) h->uni[i] = p->fast_c[(size_t)i * S];  // slot 0's column
         for (size_t sl = 0; sl < S; ++sl) {
@@ -570,10 +585,10 @@ int br2_select_kernel(br2_handle h, int32_t variant) {
         return fail(BR2_EINVAL, "br2_select_kernel: the one-slot-per-thread fast kernel does not serve point forces");
     CUDA_TRY(cudaSetDevice(h->device));
     const size_t S = (size_t)h->t.n_slots;
-    KernelChoice pick{0, nullptr};
+    KernelChoice pick{0, nullptr, nullptr};
     if (variant == 3) {
         const int need = h->tile.rod_t0[BR2_TILE_MAX_RODS];  // threads of the largest CTA
-        h->exact = KernelChoice{0, nullptr};
+        h->exact = KernelChoice{0, nullptr, nullptr};
         if (h->tile.n_ctas > 1) {
             for (size_t i = 0; i < sizeof(kTileClusterKernels) / sizeof(kTileClusterKernels[0]); ++i)
                 if (kTileClusterKernels[i].threads >= need) {
@@ -620,9 +635,14 @@ int br2_select_kernel(br2_handle h, int32_t variant) {
     if (smem > 227 * 1024)
         return fail(BR2_ELIMIT, "assembly needs " + std::to_string(smem) + " B of shared memory per CTA (max 232448)");
     CUDA_TRY(cudaFuncSetAttribute((const void *)pick.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (variant == 3 && h->exact.fn)
+    if (pick.fn_pi)
+        CUDA_TRY(cudaFuncSetAttribute((const void *)pick.fn_pi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (variant == 3 && h->exact.fn) {
         CUDA_TRY(cudaFuncSetAttribute((const void *)h->exact.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (variant != 3) h->exact = KernelChoice{0, nullptr};
+        if (h->exact.fn_pi)
+            CUDA_TRY(cudaFuncSetAttribute((const void *)h->exact.fn_pi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    if (variant != 3) h->exact = KernelChoice{0, nullptr, nullptr};
     h->kernel = pick;
     h->smem_bytes = smem;
     h->variant = variant;
@@ -651,14 +671,14 @@ int br2_select_kernel(br2_handle h, int32_t variant) {
     if (variant != 0) {
         // exact-path replay kernel; an assembly that only fits a cluster has none (one CTA cannot hold it): instances
         // that leave the optimistic kernel's range then stay flagged and frozen -- br2_unresolved_count reports them
-        h->replay = KernelChoice{0, nullptr};
+        h->replay = KernelChoice{0, nullptr, nullptr};
         for (const KernelChoice &kc : kKernels[0])
             if (kc.threads >= h->t.n_slots) {
                 h->replay = kc;
                 break;
             }
         h->replay_smem = sizeof(double) * (30 * S + 9 * (size_t)h->t.n_joints + 32);
-        if (h->replay_smem > 227 * 1024) h->replay = KernelChoice{0, nullptr};
+        if (h->replay_smem > 227 * 1024) h->replay = KernelChoice{0, nullptr, nullptr};
         if (!h->replay.fn && variant != 3) return fail(BR2_ELIMIT, "assembly too large for the replay kernel");
         if (h->replay.fn)
             CUDA_TRY(cudaFuncSetAttribute((const void *)h->replay.fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -704,6 +724,22 @@ int br2_set_actuation(br2_handle h, const double *dev_pressures) {
     if (!h) return fail(BR2_EINVAL, "br2_set_actuation: NULL handle");
     if (!dev_pressures && h->t.n_actions > 0) return fail(BR2_EINVAL, "br2_set_actuation: NULL pressures");
     h->pressures = dev_pressures;
+    return BR2_OK;
+}
+
+int br2_set_instance_params(br2_handle h, const double *dev_uni, const double *dev_act_d, const double *dev_joint_scale) {
+    if (!h) return fail(BR2_EINVAL, "br2_set_instance_params: NULL handle");
+    if (!dev_uni) {  // back to the constants every instance shares
+        h->inst_uni = h->inst_act_d = h->inst_joint_scale = nullptr;
+        return BR2_OK;
+    }
+    if (h->variant != 3 || !h->kernel.fn_pi)
+        return fail(BR2_ESTATE, "br2_set_instance_params: only the tile kernel reads per-instance constants (" +
+                                    (h->tile_ok ? std::string("select variant 3") : h->tile_why) + ")");
+    if ((h->n_act > 0 && !dev_act_d) || !dev_joint_scale) return fail(BR2_EINVAL, "br2_set_instance_params: NULL table");
+    h->inst_uni = dev_uni;
+    h->inst_act_d = dev_act_d;
+    h->inst_joint_scale = dev_joint_scale;
     return BR2_OK;
 }
 
@@ -785,6 +821,15 @@ int br2_step(br2_handle h, int64_t n_steps, double t0, double dt, void *stream, 
         sp.kd[11] = 0.5 * dt;
     }
     sp.tile = h->tile;
+    sp.inst_uni = h->inst_uni;
+    sp.inst_act_d = h->inst_act_d;
+    sp.inst_joint_scale = h->inst_joint_scale;
+    sp.n_act = h->n_act;
+    const bool per_instance = h->inst_uni != nullptr;
+    if (per_instance && (h->variant != 3 || !h->kernel.fn_pi))
+        return fail(BR2_ESTATE, "br2_step: per-instance material parameters need the tile kernel (br2_select_kernel 3)");
+    const void *step_fn = per_instance ? (const void *)h->kernel.fn_pi : (const void *)h->kernel.fn;
+    const void *exact_fn = per_instance ? (const void *)h->exact.fn_pi : (const void *)h->exact.fn;
     sp.status = h->status;
     sp.replays = h->replays;
     sp.only_flagged = 0;
@@ -846,19 +891,21 @@ int br2_step(br2_handle h, int64_t n_steps, double t0, double dt, void *stream, 
         attr[0].val.clusterDim.y = attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        CUDA_TRY(cudaLaunchKernelExC(&cfg, (const void *)h->kernel.fn, args));
-        if (h->exact.fn) {
+        CUDA_TRY(cudaLaunchKernelExC(&cfg, step_fn, args));
+        if (exact_fn) {
             // exact-path pass of the same kernel (IEEE division / libm, no validity ranges) for the instances the
             // optimistic pass flagged; every CTA returns at once when there are none.  The queue restarts, the count
             // of flagged instances stays.
             CUDA_TRY(cudaMemsetAsync(h->work + 1, 0, sizeof(unsigned long long) + sizeof(int) * (size_t)h->batch, (cudaStream_t)stream));
-            CUDA_TRY(cudaLaunchKernelExC(&cfg, (const void *)h->exact.fn, args));
+            CUDA_TRY(cudaLaunchKernelExC(&cfg, exact_fn, args));
         }
     } else {
-        CUDA_TRY(cudaLaunchKernel((const void *)h->kernel.fn, dim3(grid), dim3((unsigned)h->kernel.threads), args,
+        CUDA_TRY(cudaLaunchKernel(step_fn, dim3(grid), dim3((unsigned)h->kernel.threads), args,
                                   h->smem_bytes, (cudaStream_t)stream));
     }
-    if (h->variant != 0 && h->replay.fn) {
+    // (per-instance material parameters: the generic kernel reads the shared tables, so it cannot redo such an instance;
+    // one that leaves the optimistic range stays flagged and br2_unresolved_count reports it)
+    if (h->variant != 0 && h->replay.fn && !per_instance) {
         // exact-path replay, stream-ordered behind the fast kernel: CTAs of unflagged instances exit at once
         sp.only_flagged = 1;
         CUDA_TRY(cudaLaunchKernel((const void *)h->replay.fn, dim3((unsigned)h->batch), dim3((unsigned)h->replay.threads),

@@ -84,6 +84,11 @@ struct StepParams {
     int chunk_steps, n_chunks;
     long long queue_group;                // instances per group of the tile kernel's work queue (see the kernel)
     double chunk_t0[BR2_MAX_CHUNKS];      // fp64-accumulated start time of each chunk
+    // per-instance material parameters (tile kernels' kPerInst instantiations; br2_set_instance_params)
+    const double *inst_uni;               // [batch][BR2_FC_COUNT] what `uni` holds, per instance
+    const double *inst_act_d;             // [batch][n_act][3] actuation torque per unit pressure, per instance
+    const double *inst_joint_scale;       // [batch] factor on the tip-to-base joints' stiffness
+    int n_act;
     unsigned long long *fail_counter;     // instances flagged by the optimistic pass of this launch
     unsigned long long *work_counter;     // next item of the queue (zeroed before every launch)
     int *progress;                        // [batch] chunks of the instance already written back

@@ -76,16 +76,33 @@ __device__ __forceinline__ void mbar_arrive_warp(uint32_t bar) {
     __syncwarp();
     if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// (the suspend-time hint keeps a waiting warp asleep until the phase completes: without it TRYWAIT returned after a few
+// hundred cycles and the loop around it cost 120 issued instructions per warp and step on the cluster kernel)
+#ifndef BR2_MBAR_SUSPEND_HINT
+#define BR2_MBAR_SUSPEND_HINT 0x989680u
+#endif
+constexpr uint32_t kMbarSuspendHint = BR2_MBAR_SUSPEND_HINT;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}" ::"r"(bar), "r"(parity) : "memory");
+    if (kMbarSuspendHint != 0u)
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "WAIT_LOOP:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+            "@p bra WAIT_DONE;\n"
+            "bra WAIT_LOOP;\n"
+            "WAIT_DONE:\n"
+            "}" ::"r"(bar), "r"(parity), "r"(kMbarSuspendHint) : "memory");
+    else
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "WAIT_LOOP:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra WAIT_DONE;\n"
+            "bra WAIT_LOOP;\n"
+            "WAIT_DONE:\n"
+            "}" ::"r"(bar), "r"(parity) : "memory");
 }
 // ---- pushes into a peer CTA's shared memory (cluster kernels) -------------------------------------------------------
 // st.async writes 8 bytes into the peer's shared memory and, when the write has landed, counts them off the peer's
@@ -245,32 +262,35 @@ __device__ __forceinline__ TileWhere tile_where(const StepParams &p, int t, long
 }
 
 // exp(strain ln c_r) of the rotational damper (Appendix A.5): one exponential per element for a round section
-template <bool kExact>
-__device__ __forceinline__ void tile_damper_exponentials(const StepParams &p, double len, int flags, double (&out)[3], int &bad) {
+template <bool kExact, bool kPerInst>
+__device__ __forceinline__ void tile_damper_exponentials(const StepParams &p, const double *smu, double len, int flags,
+                                                         double (&out)[3], int &bad) {
     using M = TileMath<kExact>;
-    const double dil = len * p.uni[BR2_FC_INV_REST_LEN];
+#define UNI(idx) (kPerInst ? smu[(idx)] : p.uni[(idx)])
+    const double dil = len * UNI(BR2_FC_INV_REST_LEN);
     const double strain = (flags & TILE_F_ELEM) ? dil - 1.0 : 0.0;
     if (p.tile.round_section) {
-        const double e2 = strain * p.uni[BR2_FC_LN_CR + 2];
+        const double e2 = strain * UNI(BR2_FC_LN_CR + 2);
         if (!kExact) bad |= (e2 * e2 <= BR2_E2_MAX) ? 0 : 4;
         out[0] = M::exp(e2);
     } else {
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            const double e = strain * p.uni[BR2_FC_LN_CR + i];
+            const double e = strain * UNI(BR2_FC_LN_CR + i);
             if (!kExact) bad |= (e * e <= BR2_E2_MAX) ? 0 : 4;
             out[i] = M::exp(e);
         }
     }
+#undef UNI
 }
 
 // One PositionVerlet step of a thread's run.  kEnd: last step of a chunk (ends with a single kinematic half step
 // instead of the fused pair, so the state is a whole-step state); kLast: last step of the launch (also reports
 // the callback quantities).  gstep: steps this CTA has executed since the kernel started (phase parity of the
 // barriers; its low bit selects the buffer of the pushed tip-to-base data).
-template <int C, int NT, bool kEnd, bool kLast, bool kExtras, bool kCluster, bool kExact, bool kSplit>
-__device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileThread<C> &th, double time_mid, long long b,
-                                          int rank, int gstep, const TileBars &bars) {
+template <int C, int NT, bool kEnd, bool kLast, bool kExtras, bool kCluster, bool kExact, bool kSplit, bool kPerInst>
+__device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const double *smu, TileThread<C> &th, double time_mid,
+                                          long long b, int rank, int gstep, const TileBars &bars) {
     using L = TileSmem<C, NT>;
     constexpr int R = L::R;
     static_assert(C >= 2, "slot 0's element must lie inside the thread's run");
@@ -281,12 +301,14 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
     const double dt = p.dt, hdt = p.kd[11];
     // loop-invariant products of the uniform constants and dt come from the constant bank (StepParams::kd, filled by br2_step
     // with the very expressions quoted here) instead of being hoisted into registers that then spill
-#define KD(idx, expr) p.kd[(idx)]
+    // kPerInst (material parameters that differ between the instances of a batch): both tables come from this CTA's copy
+    // in shared memory (smu: uni[BR2_FC_COUNT] then kd[12]), read as broadcasts, instead of from the constant bank
+#define KD(idx, expr) (kPerInst ? smu[BR2_FC_COUNT + (idx)] : p.kd[(idx)])
     TileWhere wh{};
     if (kLast) wh = tile_where<C>(p, (int)threadIdx.x, b, rank);
     const int n = wh.n, np1 = wh.n + 1;
     double *const inst = wh.inst;
-#define UNI(idx) p.uni[(idx)]
+#define UNI(idx) (kPerInst ? smu[(idx)] : p.uni[(idx)])
 #define JDV(i) p.tile.jd[th.rod][(i)]
 #define TAV(j, i) sm[L::TA + (3 * (j) + (i)) * R + t]
     double (&x)[C][3] = th.x;
@@ -599,7 +621,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
     double dexp[C][3];
     if (kHoistDamper) {
 #pragma unroll
-        for (int j = 0; j < C; ++j) tile_damper_exponentials<kExact>(p, len[j], th.fl[j], dexp[j], th.bad);
+        for (int j = 0; j < C; ++j) tile_damper_exponentials<kExact, kPerInst>(p, smu, len[j], th.fl[j], dexp[j], th.bad);
     }
     if (kSplit)
         mbar_wait(bars.b3, (uint32_t)gstep & 1u);  // B3
@@ -809,7 +831,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, TileT
 #undef TAV
 }
 
-template <int C, int NT, int kMinBlocks, bool kExtras, bool kCluster, bool kExact, bool kSplit>
+template <int C, int NT, int kMinBlocks, bool kExtras, bool kCluster, bool kExact, bool kSplit, bool kPerInst = false>
 __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __grid_constant__ StepParams p) {
     using L = TileSmem<C, NT>;
     constexpr int R = L::R;
@@ -818,6 +840,7 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
     __shared__ int s_chunk;
     __shared__ int s_why;
     __shared__ unsigned long long s_bar[6];  // B1, B2, B3, B4 (joint forces ready), XB[2] (pushed element data, by step parity)
+    __shared__ double s_uni[kPerInst ? BR2_FC_COUNT + 12 : 1];  // kPerInst: this instance's constants (uni, then kd)
 
     const DevTables &tb = p.t;
     const TilePlan &tp = p.tile;
@@ -933,13 +956,15 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
                 if (valid && fi[BR2_FAST_SOFTFIX_ROW] >= 0) f |= TILE_F_SOFTFIX;
                 th.fl[j] = f;
                 th.xinfo[j] = (kExtras && tp.n_xj > 0 && active) ? tp.xi[(rank * tp.xi_stride + t) * (C + 1) + j] : 0;
-                th.dtmc[j] = dt * p.uni[BR2_FC_CT] / tb.slot_c[(long long)BR2_SC_MASS * S + sc];
+                const double c_t = kPerInst ? p.inst_uni[b * BR2_FC_COUNT + BR2_FC_CT] : p.uni[BR2_FC_CT];
+                th.dtmc[j] = dt * c_t / tb.slot_c[(long long)BR2_SC_MASS * S + sc];
                 double ta[3] = {0.0, 0.0, 0.0};
                 if (valid) {
                     for (int r = fi[BR2_FAST_ACT_BEGIN]; r < fi[BR2_FAST_ACT_END]; ++r) {
                         const double P = p.pressures[(long long)tb.act_i[r] * p.batch + b];
 #pragma unroll
-                        for (int i = 0; i < 3; ++i) ta[i] = fma(P, tb.act_d[r * 3 + i], ta[i]);
+                        for (int i = 0; i < 3; ++i)
+                            ta[i] = fma(P, kPerInst ? p.inst_act_d[(b * p.n_act + r) * 3 + i] : tb.act_d[r * 3 + i], ta[i]);
                     }
                 }
 #pragma unroll
@@ -971,7 +996,11 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
             if (kExtras) {  // this CTA's copy of the extra joints' tables (layout: TileSmem)
                 double *const XJD = sm + L::EX + 2 * L::EXW * tp.n_xe + 4 * tp.n_xj;
                 int *const XJI = (int *)(XJD + 8 * tp.n_xj), *const XPM = XJI + 8 * tp.n_xj, *const XIT = XPM + ((tp.n_xe + 1) & ~1);
-                for (int i = t; i < 8 * tp.n_xj; i += NT) XJD[i] = tp.xj_d[i];
+                for (int i = t; i < 8 * tp.n_xj; i += NT) {
+                    // (a tip-to-base joint's stiffness is proportional to Young's modulus: free_simulator.py:220-228)
+                    const bool stiffness = kPerInst && (i & 7) == 0 && tp.xj_i[12 * (i >> 3) + 10] == 0;
+                    XJD[i] = stiffness ? tp.xj_d[i] * p.inst_joint_scale[b] : tp.xj_d[i];
+                }
                 for (int i = t; i < tp.n_xj; i += NT) {
                     const int *row = tp.xj_i + 12 * i;
                     XJI[8 * i + 0] = row[8];   // published element of rod one's element (node sums, radius)
@@ -987,6 +1016,23 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
         }
         // zero the exchange arrays (the zero row stays zero for the whole chunk)
         for (int i = t; i < L::ZERO_END; i += NT) sm[i] = 0.0;
+        if (kPerInst) {
+            // this instance's constants, and the products br2_step forms on the host for the shared ones (same expressions)
+            for (int i = t; i < BR2_FC_COUNT; i += NT) s_uni[i] = p.inst_uni[b * BR2_FC_COUNT + i];
+            if (t < 12) {
+                const double *u = p.inst_uni + b * BR2_FC_COUNT;
+                const double dt = p.dt;
+                double kd = 0.5 * dt;                                                   // [11]
+                if (t < 3) kd = dt * u[BR2_FC_CT] * u[BR2_FC_GRAVITY + t];
+                else if (t == 3) kd = 0.5 * u[BR2_FC_INV_REST_VLEN];
+                else if (t == 4) kd = -0.5 * u[BR2_FC_INV_REST_VLEN];
+                else if (t == 5) kd = -0.25 * u[BR2_FC_JNU];
+                else if (t == 6) kd = 0.5 * u[BR2_FC_JK];
+                else if (t == 7) kd = -0.5 * u[BR2_FC_JKREP];
+                else if (t < 11) kd = dt * u[BR2_FC_JINV + (t - 8)];
+                s_uni[BR2_FC_COUNT + t] = kd;
+            }
+        }
         tile_sync<kCluster>();
 
         double time = p.chunk_t0[chunk];
@@ -1001,14 +1047,14 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
             th.bad |= TileMath<kExact>::rotate(th.Q[j], th.w[j], hdt, hdt) ? 1 : 0;
         }
         for (int step = 0; step < n_steps - 1; ++step) {
-            tile_step<C, NT, false, false, kExtras, kCluster, kExact, kSplit>(p, sm, th, time + hdt, b, rank, gstep, bars);
+            tile_step<C, NT, false, false, kExtras, kCluster, kExact, kSplit, kPerInst>(p, sm, s_uni, th, time + hdt, b, rank, gstep, bars);
             time = (time + hdt) + hdt;
             ++gstep;
         }
         if (final_chunk)
-            tile_step<C, NT, true, true, kExtras, kCluster, kExact, kSplit>(p, sm, th, time + hdt, b, rank, gstep, bars);
+            tile_step<C, NT, true, true, kExtras, kCluster, kExact, kSplit, kPerInst>(p, sm, s_uni, th, time + hdt, b, rank, gstep, bars);
         else
-            tile_step<C, NT, true, false, kExtras, kCluster, kExact, kSplit>(p, sm, th, time + hdt, b, rank, gstep, bars);
+            tile_step<C, NT, true, false, kExtras, kCluster, kExact, kSplit, kPerInst>(p, sm, s_uni, th, time + hdt, b, rank, gstep, bars);
         ++gstep;
 
         // a CTA that left the series' validity range keeps the chunk-start state and asks for the exact path, which

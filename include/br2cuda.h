@@ -208,6 +208,15 @@ int br2_bind_state(br2_handle h, double *dev_state, int64_t batch);
  * (replaces FreeAssembly.set_actuation's shared python lists, free_simulator.py:276-289). */
 int br2_set_actuation(br2_handle h, const double *dev_pressures);
 
+/* Material parameters that differ BETWEEN the instances of the batch (sweeps over Young's / shear modulus, damping constant,
+ * fibre angles: the rod-spec keys of free_simulator.py:108-120, 291-340), tile kernel only.  Borrowed device buffers:
+ * dev_uni [batch][BR2_FC_COUNT] = per instance what column 0 of fast_c holds for the shared case; dev_act_d
+ * [batch][n_act][3] = per instance act_d; dev_joint_scale [batch] = factor on the tip-to-base joints' stiffness (it is
+ * proportional to Young's modulus, :220-228).  dev_uni == NULL returns to the shared constants.  Geometry, masses and the
+ * joint direction vectors stay common to the batch.  The exact-path replay of one-CTA assemblies reads the shared tables,
+ * so a per-instance run that leaves the optimistic kernel's range is reported by br2_unresolved_count instead of redone. */
+int br2_set_instance_params(br2_handle h, const double *dev_uni, const double *dev_act_d, const double *dev_joint_scale);
+
 /* Advance every bound instance n_steps PositionVerlet steps starting at time t0 (replaces n_steps
  * calls of do_step, environment.py:279-285).  Asynchronous on `stream` (a cudaStream_t, e.g.
  * torch.cuda.current_stream().cuda_stream).  *t_end receives the fp64-accumulated end time. */
