@@ -12,6 +12,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libbr2oracle.so")
+LIB_F32 = os.path.join(HERE, "libbr2oracle_f32.so")  # same code in single precision: precision study only, never a checker
 
 ROD_NI, F_NI, F_ND, C_NI, C_ND, J_NI, J_ND = 4, 4, 6, 2, 14, 5, 10
 STATE = ("x", "v", "Q", "w", "a", "alpha", "f_int", "t_int", "f_ext", "t_ext", "len", "dil", "rad")
@@ -27,6 +28,8 @@ def build(force=False):
     src = os.path.join(HERE, "br2_oracle.c")
     if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
         subprocess.check_call(["make", "-s", "-C", HERE, "-B", "libbr2oracle.so"])
+    if force or not os.path.exists(LIB_F32) or os.path.getmtime(LIB_F32) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", HERE, "-B", "libbr2oracle_f32.so"])
     return LIB
 
 
@@ -53,15 +56,18 @@ def _diag(m):
 
 
 class FusedOracle:
-    def __init__(self):
-        self._lib = ctypes.CDLL(build())
+    def __init__(self, real=np.float64):
+        """``real=np.float32`` loads the single-precision build of the same C code (how far would an fp32 path drift?)."""
+        self.real = np.dtype(real)
+        build()
+        self._lib = ctypes.CDLL(LIB if self.real == np.float64 else LIB_F32)
         self._lib.br2o_run.restype = ctypes.c_double
         self._lib.br2o_run.argtypes = [ctypes.POINTER(_Program), ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_int64, ctypes.c_int64, ctypes.c_double, ctypes.c_double,
                                        ctypes.c_int32]
 
     @classmethod
-    def from_simulator(cls, simulator, action_names):
+    def from_simulator(cls, simulator, action_names, real=np.float64):
         """``action_names``: ordered list of action keys; pressures are passed in that order."""
         from ..br2_port import ops
         from ..mini_elastica import AnalyticalLinearDamper, GravityForces
@@ -69,7 +75,7 @@ class FusedOracle:
             SurfaceJointSideBySide,
         )
 
-        self = cls()
+        self = cls(real)
         self.action_names = list(action_names)
         rods = list(simulator._systems)
         self.rods = rods
@@ -168,10 +174,10 @@ class FusedOracle:
             return np.ascontiguousarray(np.array(rows, dtype=dtype).reshape(-1, width))
 
         self._keep = dict(
-            rod_i=np.ascontiguousarray(rod_i), consts=np.ascontiguousarray(np.concatenate(consts)),
-            forcing_i=arr(f_i, F_NI, np.int64), forcing_d=arr(f_d, F_ND, np.float64),
-            cons_i=arr(c_i, C_NI, np.int64), cons_d=arr(c_d, C_ND, np.float64),
-            joint_i=arr(j_i, J_NI, np.int64), joint_d=arr(j_d, J_ND, np.float64),
+            rod_i=np.ascontiguousarray(rod_i), consts=np.ascontiguousarray(np.concatenate(consts).astype(self.real)),
+            forcing_i=arr(f_i, F_NI, np.int64), forcing_d=arr(f_d, F_ND, self.real),
+            cons_i=arr(c_i, C_NI, np.int64), cons_d=arr(c_d, C_ND, self.real),
+            joint_i=arr(j_i, J_NI, np.int64), joint_d=arr(j_d, J_ND, self.real),
         )
         k = self._keep
         self._prog = _Program(
@@ -187,7 +193,7 @@ class FusedOracle:
         for rod, fields in zip(self.rods, self.layout):
             for name, (off, size) in fields.items():
                 one[off:off + size] = np.asarray(getattr(rod, _ATTR[name])).ravel()
-        return np.ascontiguousarray(np.tile(one, (batch, 1)))
+        return np.ascontiguousarray(np.tile(one, (batch, 1)).astype(self.real))
 
     def view(self, W, rod, name):
         """[batch, ...] view of one field of one rod inside a workspace."""
@@ -198,8 +204,8 @@ class FusedOracle:
 
     def run(self, W, pressures, n_steps, t0, dt, n_threads=0):
         """Advance every instance ``n_steps`` steps in place.  ``pressures``: [n_actions, batch]."""
-        assert W.flags.c_contiguous and W.dtype == np.float64 and W.shape[1] == self.words
-        pressures = np.ascontiguousarray(np.asarray(pressures, dtype=np.float64).reshape(len(self.action_names), -1))
+        assert W.flags.c_contiguous and W.dtype == self.real and W.shape[1] == self.words
+        pressures = np.ascontiguousarray(np.asarray(pressures, dtype=self.real).reshape(len(self.action_names), -1))
         assert pressures.shape[1] == W.shape[0]
         return self._lib.br2o_run(ctypes.byref(self._prog), W.ctypes.data, pressures.ctypes.data,
                                   W.shape[0], int(n_steps), float(t0), float(dt), int(n_threads))
