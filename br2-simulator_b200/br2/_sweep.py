@@ -104,7 +104,7 @@ def instance_tables(assy, program, per_instance, batch, dt):
                 angle = deg * np.pi / 180
                 scale = (np.pi * (this.inner_radius ** 3) * ((np.sin(angle) ** 2) + 2 * (np.cos(angle) ** 2)) / (np.sin(2 * angle)))
                 twist.append(np.stack([np.zeros(batch), np.zeros(batch), scale / n], axis=1))
-        scale = np.pi * this.radius[-1] * (this.inner_radius ** 2)
+        scale = np.pi * this._host["rad"][-1] * (this.inner_radius ** 2)  # (the rest radius the builder read: host template)
         for degrees in spec["gamma"]:
             # a swept gamma replaces the library's angle; the segment's y-rotation is added on top, as the builder does
             deg = angles["gamma"] + spec.get("y_rotation", 0.0) if angles["gamma"] is not None else np.full(batch, float(degrees))
