@@ -779,17 +779,19 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
         // node rates are complete only now (the element after a node lives in the same thread, later in the loop):
         // constraints, then the trailing kinematic half step of this step fused with the leading half step of the
         // next one (unless this is the last step of the launch)
-        const double hmult = kEnd ? hdt : dt;
-#pragma unroll
-        for (int j = 0; j < C; ++j) th.bad |= M::rotate(Q[j], w[j], hdt, hmult) ? 1 : 0;
         if (kExtras && !kLast) {
-            // half forces of the tip-to-base joints on my nodes -- last, so that their evaluation (by other warps, between
-            // B3's arrive and wait) has long finished
+            // half forces of the tip-to-base joints on my nodes: after the dynamic step, so that their evaluation (by other
+            // warps, between B3's arrive and wait) has long finished, and BEFORE the rotations, whose long dependent chains
+            // cover the latency of these few loads (at the very end of the step it was exposed: +1 ... 2 % measured; fetching
+            // them at the start of P4 in the CTA-barrier kernels is no better)
+            bool any = false;
+#pragma unroll
+            for (int j = 0; j < C; ++j) any = any || ((th.xinfo[j] >> 16) & 0xF) != 0;
+            if (kSplit && any) mbar_wait(bars.b4, (uint32_t)gstep & 1u);
 #pragma unroll
             for (int j = 0; j < C; ++j) {
                 const int cnt = (th.xinfo[j] >> 16) & 0xF, first = th.xinfo[j] >> 20;
                 if (cnt) {
-                    if (kSplit) mbar_wait(bars.b4, (uint32_t)gstep & 1u);
                     // the first three items (a joined element's node has three: one per rod of the other segment) without a
                     // branch between them, so that their loads are in flight together; same order of summation as the loop
                     int item[3];
@@ -816,6 +818,9 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
                 }
             }
         }
+        const double hmult = kEnd ? hdt : dt;
+#pragma unroll
+        for (int j = 0; j < C; ++j) th.bad |= M::rotate(Q[j], w[j], hdt, hmult) ? 1 : 0;
 #pragma unroll
         for (int j = 0; j < C; ++j) {
 #pragma unroll
