@@ -85,13 +85,23 @@ class Engine:
 
     # ------------------------------------------------------------------ actuation
     def set_pressures(self, values):
-        """``values``: per action slot a scalar or a length-batch array."""
+        """``values``: per action slot a scalar or a length-batch array.  Staged in pinned host memory and copied
+        asynchronously on the current stream (the next launch is ordered behind it); the staging buffer is reused once
+        its previous copy has completed."""
         if self.n_actions == 0:
             return
-        host = np.zeros((self.n_actions, self.batch))
+        torch = self.torch
+        if getattr(self, "_pressure_stage", None) is None:
+            self._pressure_stage = torch.empty((self.n_actions, self.batch), dtype=torch.float64).pin_memory()
+            self._pressure_done = None
+        if self._pressure_done is not None:
+            self._pressure_done.synchronize()
+        host = self._pressure_stage.numpy()
         for a, value in enumerate(values):
             host[a, :] = np.asarray(value, dtype=np.float64)
-        self.pressures[: self.n_actions].copy_(self.torch.from_numpy(host), non_blocking=False)
+        self.pressures[: self.n_actions].copy_(self._pressure_stage, non_blocking=True)
+        self._pressure_done = torch.cuda.Event()
+        self._pressure_done.record(torch.cuda.current_stream(self.device))
 
     def set_instance_params(self, uni=None, act_d=None, joint_scale=None):
         """Material constants that differ between the instances (br2_set_instance_params, include/br2cuda.h): host arrays

@@ -124,6 +124,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 // the step's exchange points: arrive after publishing, wait before reading; kSplit = false degenerates to one
 // __syncthreads at the wait
+#ifndef BR2_TILE_SHUFFLE
+#define BR2_TILE_SHUFFLE 0  // A/B: the next run's first node / element through warp shuffles where it is the next lane (measured: DESIGN.md)
+#endif
 #ifndef BR2_TILE_HOIST_DAMPER
 #define BR2_TILE_HOIST_DAMPER 0  // damper exponentials before the third wait (costs registers: measured)
 #endif
@@ -261,6 +264,14 @@ __device__ __forceinline__ TileWhere tile_where(const StepParams &p, int t, long
     return wh;
 }
 
+// A/B experiment (BR2_TILE_SHUFFLE): what the next run published, from the next lane's registers when that run lives in
+// the next lane of this warp, from its shared-memory row otherwise (last lane of a warp, last run of a rod)
+__device__ __forceinline__ double tile_next(double mine, const double *row, bool via_row) {
+    double up = __shfl_down_sync(0xffffffffu, mine, 1);
+    if (via_row) up = *row;
+    return up;
+}
+
 // exp(strain ln c_r) of the rotational damper (Appendix A.5): one exponential per element for a round section
 template <bool kExact, bool kPerInst>
 __device__ __forceinline__ void tile_damper_exponentials(const StepParams &p, const double *smu, double len, int flags,
@@ -341,10 +352,14 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
         len0 = fma(d2, rs0, BR2_EPS_LEN);
         sm[L::LF + t] = len0;
     }
+    const bool next_via_row = BR2_TILE_SHUFFLE && ((threadIdx.x & 31) == 31 || th.tn != t + 1);
+    double x0_start[3], v0_start[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         sm[L::XF + i * R + t] = x[0][i];
         sm[L::VF + i * R + t] = v[0][i];
+        x0_start[i] = x[0][i];
+        v0_start[i] = v[0][i];
     }
 #pragma unroll
     for (int i = 0; i < 9; ++i) sm[L::QF + i * R + t] = Q[0][i];
@@ -369,8 +384,10 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
             double d[3], dv[3];
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                const double xn = (j + 1 < C) ? x[(j + 1) % C][i] : sm[L::XF + i * R + th.tn];
-                const double vn = (j + 1 < C) ? v[(j + 1) % C][i] : sm[L::VF + i * R + th.tn];
+                const double xn = (j + 1 < C) ? x[(j + 1) % C][i]
+                                  : BR2_TILE_SHUFFLE ? tile_next(x0_start[i], &sm[L::XF + i * R + th.tn], next_via_row) : sm[L::XF + i * R + th.tn];
+                const double vn = (j + 1 < C) ? v[(j + 1) % C][i]
+                                  : BR2_TILE_SHUFFLE ? tile_next(v0_start[i], &sm[L::VF + i * R + th.tn], next_via_row) : sm[L::VF + i * R + th.tn];
                 d[i] = (kSplit && j == 0) ? d0[i] : xn - x[j][i];
                 dv[i] = vn - v[j][i];
                 sm[L::PC + (3 * j + i) * R + t] = xn + x[j][i];
@@ -493,8 +510,11 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
             const bool vor = th.fl[j] & TILE_F_VOR;
             double Qn[9];
 #pragma unroll
-            for (int i = 0; i < 9; ++i) Qn[i] = (j + 1 < C) ? Q[(j + 1) % C][i] : sm[L::QF + i * R + th.tn];
-            const double lenn = (j + 1 < C) ? len[(j + 1) % C] : sm[L::LF + th.tn];
+            for (int i = 0; i < 9; ++i)
+                Qn[i] = (j + 1 < C) ? Q[(j + 1) % C][i]
+                        : BR2_TILE_SHUFFLE ? tile_next(Q[0][i], &sm[L::QF + i * R + th.tn], next_via_row) : sm[L::QF + i * R + th.tn];
+            const double lenn = (j + 1 < C) ? len[(j + 1) % C]
+                                : BR2_TILE_SHUFFLE ? tile_next(len[0], &sm[L::LF + th.tn], next_via_row) : sm[L::LF + th.tn];
             const double *q = Q[j];
             // antisymmetric part and trace of Qn Q^T
             const double w0 = fma(Qn[6], q[3], fma(Qn[7], q[4], fma(Qn[8], q[5], fma(-Qn[3], q[6], fma(-Qn[4], q[7], -Qn[5] * q[8])))));
