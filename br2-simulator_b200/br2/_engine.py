@@ -114,8 +114,14 @@ class Engine:
         torch = self.torch
         tables = []
         for array, shape in ((uni, (self.batch, -1)), (act_d, (self.batch, -1)), (joint_scale, (self.batch,))):
-            host = np.ascontiguousarray(np.asarray(array, dtype=np.float64).reshape(shape))
-            tables.append(torch.from_numpy(host).to(self.device) if host.size else torch.zeros(1, dtype=torch.float64, device=self.device))
+            host = np.asarray(array, dtype=np.float64)
+            if host.size == 0:  # (an assembly without actuation rows)
+                tables.append(torch.zeros(1, dtype=torch.float64, device=self.device))
+                continue
+            host = np.ascontiguousarray(host.reshape(shape))
+            if host.shape[0] != self.batch:
+                raise ValueError("per-instance table has %d rows, the batch %d" % (host.shape[0], self.batch))
+            tables.append(torch.from_numpy(host).to(self.device))
         _native.check(self.lib.br2_set_instance_params(self.handle, *[t.data_ptr() for t in tables]))
         self._instance_tables = tables
 
