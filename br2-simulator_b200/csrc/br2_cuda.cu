@@ -345,12 +345,14 @@ bool make_tile_plan(const br2_program *p, int C, br2::TilePlan *plan, TileExtraT
         return slot_rank * plan->xi_stride + slot_row;
     };
     std::vector<int> xe_of_slot(S, -1);
+    std::vector<int> xe_rank;  // the CTA that holds (and publishes) the element
     auto xe_id = [&](int slot) {
         if (xe_of_slot[slot] < 0) {
             xe_of_slot[slot] = plan->n_xe++;
             int j;
             const int t = thread_of(slot, &j);
             xt->xi[(size_t)t * XN + BR2_TILE_XI_PUB(C, j)] = xe_of_slot[slot];
+            xe_rank.push_back(slot_rank);
         }
         return xe_of_slot[slot];
     };
@@ -438,7 +440,7 @@ bool make_tile_plan(const br2_program *p, int C, br2::TilePlan *plan, TileExtraT
     for (int r = 0; r < 8; ++r) plan->xb_count[r] = 0;
     for (int xe = 0; xe < plan->n_xe; ++xe)
         for (int r = 0; r < plan->n_ctas; ++r)
-            if (xe_mask[xe] & (1 << r)) ++plan->xb_count[r];
+            if ((xe_mask[xe] & (1 << r)) && xe_rank[xe] != r) ++plan->xb_count[r];  // (a CTA's own elements reach it by plain stores)
     // The extra joints are evaluated one COMPONENT per thread, by consecutive threads of the CTA's LAST warps: a warp executes
     // the joint code once whichever of its lanes take part, so packing them keeps the other warps' issue slots free.
     // (Placing them on warps without any other duty in the extra-joint protocol was measured: no difference.)

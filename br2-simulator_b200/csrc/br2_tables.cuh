@@ -47,7 +47,7 @@ struct TilePlan {
     // assembly; evaluated by designated threads from data their elements publish; none for single-segment assemblies.
     int n_xe, n_xj;                         // elements that publish director / omega / radius / node sums; extra joints
     int n_xitems;                           // entries of `xitems`
-    int xb_count[8];                        // per rank: published elements whose data the CTA consumes (arrivals per step on its XB barrier)
+    int xb_count[8];                        // per rank: published elements of OTHER CTAs whose data the CTA consumes (x 152 bytes per step on its XB barrier)
     const int *xe_mask;                     // [n_xe] bit r: the CTA of rank r consumes the element's data (device)
     const int *xi;                          // [n_ctas][xi_stride][C + 1] per thread: packed info of each slot (published xe + 1
                                             // | overwrite source xe + 1 << 8 | node items << 16 | first item << 20), then the

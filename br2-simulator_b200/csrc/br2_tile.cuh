@@ -363,7 +363,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
     }
 #pragma unroll
     for (int i = 0; i < 9; ++i) sm[L::QF + i * R + t] = Q[0][i];
-    if (kCluster && threadIdx.x == 0 && p.tile.xb_count[rank] > 0)  // arm this step's buffer: bytes my peers (and I) will push into it
+    if (kCluster && threadIdx.x == 0 && p.tile.xb_count[rank] > 0)  // arm this step's buffer: bytes my peers will push into it
         mbar_expect_tx(xbar, (uint32_t)(L::EXN * 8 * p.tile.xb_count[rank]));
     tile_arrive<kSplit>(bars.b1);
     if (!kSplit) __syncthreads();  // B1
@@ -462,15 +462,19 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
 #pragma unroll
         for (int i = 0; i < 3; ++i) sm[L::SKL + i * R + t] = skp[i];
         if (kExtras) {
-            // What the tip-to-base joints need from my elements goes into every consuming CTA's buffer of this step's parity
-            // (start-of-step director and omega: the overwrite in P4 comes later).  One CTA: plain stores, ordered before
-            // their readers by B2.  Cluster: asynchronous stores that count themselves off the consumer's barrier -- after B1
-            // on purpose: every warp of this CTA has then finished the previous step, so a peer that races ahead on my data
-            // cannot overwrite a buffer still being read.
+            // What the tip-to-base joints need from my elements (start-of-step director and omega: the overwrite in P4 comes
+            // later) goes into this CTA's buffer of this step's parity with plain stores -- ordered before their readers by
+            // B2 -- and, in a cluster, from there into every OTHER consuming CTA's buffer, one asynchronous store per double
+            // that counts itself off the consumer's barrier.  The remote stores are issued by the WARP, lane i moving double
+            // i: one thread issuing its 19 (or 38) `st.async` in a row took 1400 (2500) cycles per step -- ~70 cycles each,
+            // measured with clock64 -- and the whole cluster ran at that thread's pace.  After B1 on purpose: every warp of
+            // this CTA has then finished the previous step, so a peer that races ahead on my data cannot overwrite a buffer
+            // still being read.
+            int pubs[C];
 #pragma unroll
             for (int j = 0; j < C; ++j) {
-                const int pub = (th.xinfo[j] & 0xFF) - 1;
-                if (pub >= 0) {
+                pubs[j] = (th.xinfo[j] & 0xFF) - 1;
+                if (pubs[j] >= 0) {
                     double val[L::EXN];
 #pragma unroll
                     for (int i = 0; i < 9; ++i) val[i] = Q[j][i];
@@ -481,18 +485,27 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
                         val[16 + i] = sm[L::PV + (3 * j + i) * R + t];
                     }
                     val[12] = radx[j];
-                    if (kCluster) {
-                        const int mask = XPM[pub];
-                        const uint32_t local = smem_addr(EXD + pub * L::EXW);
+#pragma unroll
+                    for (int i = 0; i < L::EXN; ++i) EXD[pubs[j] * L::EXW + i] = val[i];
+                }
+            }
+            if (kCluster) {
+                const int lane = threadIdx.x & 31;
+                __syncwarp();  // the stores above are visible to the other lanes of the warp
+#pragma unroll
+                for (int j = 0; j < C; ++j) {
+                    unsigned owners = __ballot_sync(0xffffffffu, pubs[j] >= 0);
+                    while (owners) {
+                        const int src = __ffs(owners) - 1;
+                        owners &= owners - 1;
+                        const int pub = __shfl_sync(0xffffffffu, pubs[j], src);
+                        const int mask = XPM[pub] & ~(1 << rank);
+                        const double *row = EXD + pub * L::EXW;
                         for (int r = 0; r < p.tile.n_ctas; ++r) {
                             if (!((mask >> r) & 1)) continue;
-                            const uint32_t dst = cluster_addr(local, r), bar = cluster_addr(xbar, r);
-#pragma unroll
-                            for (int i = 0; i < L::EXN; ++i) st_async_f64(dst + 8 * i, val[i], bar);
+                            if (lane < L::EXN)
+                                st_async_f64(cluster_addr(smem_addr(row + lane), r), row[lane], cluster_addr(xbar, r));
                         }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < L::EXN; ++i) EXD[pub * L::EXW + i] = val[i];
                     }
                 }
             }
@@ -622,7 +635,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
                 const double fac = fmin(1.0, time_mid / jd[3]);
                 JF[xj * 4 + i] = jd[i] * fac;
             } else {
-                if (kCluster) mbar_wait(xbar, xparity);  // everything pushed for this step has landed (one CTA: B2 did that)
+                if (kCluster && p.tile.xb_count[rank] > 0) mbar_wait(xbar, xparity);  // what other CTAs push has landed (own elements: B2)
                 const double *e1 = EXD + ja.x * L::EXW, *e2 = EXD + ja.y * L::EXW;
                 const double *q1 = EXD + jb.x * L::EXW, *q2 = EXD + jb.y * L::EXW;
                 const double kj = jd[0], nuj = jd[1];
@@ -713,7 +726,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
                 // (after the surface joints above have used the old director); sources are start-of-step values
                 const int ow = ((th.xinfo[j] >> 8) & 0xFF) - 1;
                 if (ow >= 0) {
-                    if (kCluster) mbar_wait(xbar, xparity);
+                    if (kCluster && p.tile.xb_count[rank] > 0) mbar_wait(xbar, xparity);
                     const double *src = EXD + ow * L::EXW;
 #pragma unroll
                     for (int i = 0; i < 9; ++i) Q[j][i] = src[i];
