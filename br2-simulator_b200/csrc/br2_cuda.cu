@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -441,22 +442,53 @@ bool make_tile_plan(const br2_program *p, int C, br2::TilePlan *plan, TileExtraT
     for (int xe = 0; xe < plan->n_xe; ++xe)
         for (int r = 0; r < plan->n_ctas; ++r)
             if ((xe_mask[xe] & (1 << r)) && xe_rank[xe] != r) ++plan->xb_count[r];  // (a CTA's own elements reach it by plain stores)
-    // The extra joints are evaluated one COMPONENT per thread, by consecutive threads of the CTA's LAST warps: a warp executes
-    // the joint code once whichever of its lanes take part, so packing them keeps the other warps' issue slots free.
-    // (Placing them on warps without any other duty in the extra-joint protocol was measured: no difference.)
+    // The extra joints are evaluated one COMPONENT per thread, by consecutive lanes of as few warps as possible: a warp
+    // executes the joint code once whichever of its lanes take part.  One CTA: the last warps' threads.  Cluster: ALL 32 lanes
+    // of the last warp, idle ones included (its rod-end threads put it on a lightly loaded sub-partition anyway, below), then
+    // the lanes of warp 0 (ditto) -- not a warp of a fully loaded sub-partition, where 800 more cycles per step would make
+    // it the slowest of the CTA.
     for (int rank = 0; rank < plan->n_ctas; ++rank) {
         const int ct = plan->cta_threads[rank], warps = (ct + 31) / 32;
-        const int last = ct - (warps - 1) * 32;  // threads in use in the last warp
+        const bool cluster = plan->n_ctas > 1 && !(getenv("BR2_TILE_WARP_MAP") && atoi(getenv("BR2_TILE_WARP_MAP")) == 0);
+        const int last = cluster ? 32 : ct - (warps - 1) * 32;  // lanes available in the last warp
         int used = 0;
         for (int xj = 0; xj < plan->n_xj; ++xj) {
             if (!(xj_ranks[xj] & (1 << rank))) continue;
             for (int comp = 0; comp < 3; ++comp) {
-                const int k = used++;  // k-th (joint, component) of this CTA: lanes 0.. of the last warp, then the one before, ...
-                const int t = (k < last) ? (warps - 1) * 32 + k : (warps - 2 - (k - last) / 32) * 32 + (k - last) % 32;
-                if (t < 0) return *why = "more extra joint components than threads", false;
+                const int k = used++;  // k-th (joint, component) of this CTA
+                int t;
+                if (k < last)
+                    t = (warps - 1) * 32 + k;
+                else if (cluster)
+                    t = (k - last < 32 && warps > 1) ? k - last : (warps - 2 - (k - last - 32) / 32) * 32 + (k - last) % 32;  // warp 0, then from the back
+                else
+                    t = (warps - 2 - (k - last) / 32) * 32 + (k - last) % 32;
+                if (t < 0 || t >= plan->xi_stride) return *why = "more extra joint components than threads", false;
                 xt->xi[(size_t)(rank * plan->xi_stride + t) * XN + BR2_TILE_XI_JOINT] = (xj << 2) | comp;
             }
         }
+    }
+    // Which hardware warp runs which logical warp (cluster kernels; see the kernel): hardware warp w is scheduled by
+    // sub-partition w % 4, so with W warps in the CTA some sub-partitions hold one warp less; the logical warps that carry
+    // rod ends (publish / overwrite / gather) -- then those that evaluate joint components -- go there.
+    for (int w = 0; w < 16; ++w) plan->warp_map[w] = w;
+    if (plan->n_ctas > 1 && !(getenv("BR2_TILE_WARP_MAP") && atoi(getenv("BR2_TILE_WARP_MAP")) == 0)) {
+        const int W = (threads + 31) / 32;
+        std::vector<int> score(W, 0);
+        for (int rank = 0; rank < plan->n_ctas; ++rank)
+            for (int t = 0; t < 32 * ((plan->cta_threads[rank] + 31) / 32); ++t) {
+                const int32_t *row = &xt->xi[(size_t)(rank * plan->xi_stride + t) * XN];
+                int s = row[BR2_TILE_XI_JOINT] >= 0 ? 1 : 0;
+                for (int j = 0; j < C; ++j)
+                    if (row[BR2_TILE_XI_PUB(C, j)] >= 0 || row[BR2_TILE_XI_OW(C, j)] >= 0 || row[BR2_TILE_XI_NCNT(C, j)] > 0) s |= 2;
+                score[t / 32] |= s;
+            }
+        std::vector<int> logical(W), hardware(W);
+        for (int w = 0; w < W; ++w) logical[w] = hardware[w] = w;
+        std::stable_sort(logical.begin(), logical.end(), [&](int a, int b) { return score[a] > score[b]; });
+        auto load = [&](int w) { return (W - (w % 4) + 3) / 4; };  // warps on hardware warp w's sub-partition
+        std::stable_sort(hardware.begin(), hardware.end(), [&](int a, int b) { return load(a) < load(b); });
+        for (int i = 0; i < W; ++i) plan->warp_map[hardware[i]] = logical[i];
     }
     // pack: one int per slot + the joint id per thread; node items in one compact array
     if (plan->n_xe > 254) return *why = "too many elements in extra joints", false;

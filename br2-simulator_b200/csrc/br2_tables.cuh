@@ -39,6 +39,7 @@ struct TilePlan {
     int rod_cta[BR2_TILE_MAX_RODS];         // cluster rank of the CTA that integrates the rod
     int cta_threads[8];                     // threads in use per rank
     int xi_stride;                          // rows of `xi` per rank
+    int warp_map[16];                       // cluster kernels: logical warp executed by each hardware warp (a permutation)
     int rod_t0[BR2_TILE_MAX_RODS + 1];      // first thread of each rod inside its CTA
     int partner[BR2_TILE_MAX_RODS];         // rod whose elements are rod one of the joints this rod's elements own, or -1
     int owner[BR2_TILE_MAX_RODS];           // rod whose elements own the joints in which this rod's elements are rod one, or -1

@@ -316,7 +316,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
     // in shared memory (smu: uni[BR2_FC_COUNT] then kd[12]), read as broadcasts, instead of from the constant bank
 #define KD(idx, expr) (kPerInst ? smu[BR2_FC_COUNT + (idx)] : p.kd[(idx)])
     TileWhere wh{};
-    if (kLast) wh = tile_where<C>(p, (int)threadIdx.x, b, rank);
+    if (kLast) wh = tile_where<C>(p, th.t - 1, b, rank);
     const int n = wh.n, np1 = wh.n + 1;
     double *const inst = wh.inst;
 #define UNI(idx) (kPerInst ? smu[(idx)] : p.uni[(idx)])
@@ -882,7 +882,11 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
 
     const DevTables &tb = p.t;
     const TilePlan &tp = p.tile;
-    const int t = threadIdx.x;
+    // Which logical warp a hardware warp executes (TilePlan::warp_map; identity unless the plan says otherwise): the warp
+    // scheduler a warp runs on is (hardware warp index % 4), and a 10-warp CTA alone on an SM loads the four schedulers
+    // 3, 3, 2, 2 -- per-warp clock64 timing shows a warp ~40 % slower on a 3-warp scheduler.  The plan puts the warps that
+    // carry the rods' ends (the tip-to-base protocol) on the 2-warp schedulers, where the slack absorbs it.
+    const int t = kCluster ? ((tp.warp_map[threadIdx.x >> 5] << 5) | (threadIdx.x & 31)) : (int)threadIdx.x;
     // kCluster: the CTAs of a thread-block cluster integrate one instance together, one group of ring-connected
     // rods (a segment) each; they exchange the tip-to-base joints' data through distributed shared memory (pushes + remote
     // mbarrier arrives, see tile_step) and meet at a cluster barrier only between work items.  The cluster, not the CTA,
@@ -1030,7 +1034,8 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
                     for (int i = 0; i < 3; ++i) th.w[j][i] = 0.0;
                 }
             }
-            th.xjoint = (kExtras && tp.n_xj > 0 && active) ? tp.xi[(rank * tp.xi_stride + t) * (C + 1) + C] : -1;
+            // (a cluster's idle lanes may evaluate joint components too: the plan fills the last warp)
+            th.xjoint = (kExtras && tp.n_xj > 0 && (active || kCluster)) ? tp.xi[(rank * tp.xi_stride + t) * (C + 1) + C] : -1;
             if (kExtras) {  // this CTA's copy of the extra joints' tables (layout: TileSmem)
                 double *const XJD = sm + L::EX + 2 * L::EXW * tp.n_xe + 4 * tp.n_xj;
                 int *const XJI = (int *)(XJD + 8 * tp.n_xj), *const XPM = XJI + 8 * tp.n_xj, *const XIT = XPM + ((tp.n_xe + 1) & ~1);
