@@ -236,7 +236,7 @@ int validate(const br2_program *p) {
 // Plan of the thread-coarsened kernel (br2_tile.cuh), or the reason the assembly does not qualify.
 struct TileExtraTables {
     std::vector<int32_t> xi, xj_i;   // xi: staging rows (BR2_TILE_XI_*), packed into xpack / xitems at the end
-    std::vector<int32_t> xpack, xitems, xe_mask;
+    std::vector<int32_t> xpack, xjt, xe_mask;
     std::vector<double> xj_d;
 };
 
@@ -490,22 +490,45 @@ bool make_tile_plan(const br2_program *p, int C, br2::TilePlan *plan, TileExtraT
         std::stable_sort(hardware.begin(), hardware.end(), [&](int a, int b) { return load(a) < load(b); });
         for (int i = 0; i < W; ++i) plan->warp_map[hardware[i]] = logical[i];
     }
-    // pack: one int per slot + the joint id per thread; node items in one compact array
+    // pack: one int per slot + the joint component per thread.  A node that takes extra-joint forces gets a NODE ROW: the
+    // threads that evaluate the joints scatter their (signed) half forces into the rows of the joint's four nodes, item by
+    // item in the order the reference applies them, and the node's thread adds its row up -- one level of loads at fixed
+    // offsets instead of item list -> joint id -> force.  xjt: per rank and joint, the four nodes' row positions (or -1 when
+    // the node lives in another CTA of the cluster).
     if (plan->n_xe > 254) return *why = "too many elements in extra joints", false;
+    int max_cnt = 1;
+    for (int t = 0; t < xrows; ++t)
+        for (int j = 0; j < C; ++j) max_cnt = std::max(max_cnt, (int)xt->xi[(size_t)t * XN + BR2_TILE_XI_NCNT(C, j)]);
+    plan->nf_items = max_cnt;
+    xt->xjt.assign((size_t)plan->n_ctas * plan->n_xj * 4, -1);
     xt->xpack.assign((size_t)xrows * (C + 1), 0);
+    std::vector<int> rows_of_rank(plan->n_ctas, 0);
+    plan->n_nr = 0;
     for (int t = 0; t < xrows; ++t) {
         const int32_t *row = &xt->xi[(size_t)t * XN];
+        const int rank = t / plan->xi_stride;
         for (int j = 0; j < C; ++j) {
             const int cnt = row[BR2_TILE_XI_NCNT(C, j)];
-            const int base = (int)xt->xitems.size();
-            for (int q = 0; q < cnt; ++q) xt->xitems.push_back(row[BR2_TILE_XI_NITEM(C, j, q)]);
-            if (base + cnt > 4095) return *why = "too many extra joint forces", false;
+            int nr = 0;
+            if (cnt) {
+                nr = rows_of_rank[rank]++;  // (row ids are per CTA: every CTA has its own array)
+                if (nr > 4095) return *why = "too many nodes with extra joint forces", false;
+                for (int q = 0; q < cnt; ++q) {
+                    const int item = row[BR2_TILE_XI_NITEM(C, j, q)], xj = item >> 1;
+                    int32_t *tg = &xt->xjt[((size_t)rank * plan->n_xj + xj) * 4];
+                    // which of the joint's four nodes is this?  rod one's two nodes carry sign 0, rod two's sign 1; the first
+                    // free place of that sign (a node appears once per joint)
+                    const int m0 = (item & 1) ? 2 : 0;
+                    const int m = tg[m0] < 0 ? m0 : m0 + 1;
+                    tg[m] = (nr * max_cnt + q) * 4;
+                }
+            }
             xt->xpack[(size_t)t * (C + 1) + j] = (row[BR2_TILE_XI_PUB(C, j)] + 1) | ((row[BR2_TILE_XI_OW(C, j)] + 1) << 8) |
-                                                 (cnt << 16) | ((cnt ? base : 0) << 20);
+                                                 (cnt << 16) | (nr << 20);
         }
         xt->xpack[(size_t)t * (C + 1) + C] = row[BR2_TILE_XI_JOINT];
     }
-    plan->n_xitems = (int)xt->xitems.size();
+    for (int r = 0; r < plan->n_ctas; ++r) plan->n_nr = std::max(plan->n_nr, rows_of_rank[r]);
     return true;
 }
 
@@ -587,7 +610,7 @@ int br2_create(const br2_program *p, int device, br2_handle *out) {
         h->tile_ok = h->fast_ok && make_tile_plan(p, BR2_TILE_C, &h->tile, &xt, &h->tile_why);
         if (h->tile_ok && h->tile.n_xj > 0) {
             rc = upload(h, xt.xpack.data(), xt.xpack.size(), &h->tile.xi);
-            if (rc == BR2_OK) rc = upload(h, xt.xitems.data(), xt.xitems.size(), &h->tile.xitems);
+            if (rc == BR2_OK) rc = upload(h, xt.xjt.data(), xt.xjt.size(), &h->tile.xjt);
             if (rc == BR2_OK) rc = upload(h, xt.xj_i.data(), xt.xj_i.size(), &h->tile.xj_i);
             if (rc == BR2_OK) rc = upload(h, xt.xj_d.data(), xt.xj_d.size(), &h->tile.xj_d);
             if (rc == BR2_OK) rc = upload(h, xt.xe_mask.data(), xt.xe_mask.size(), &h->tile.xe_mask);
@@ -656,8 +679,9 @@ int br2_select_kernel(br2_handle h, int32_t variant) {
         smem = sizeof(double) * (30 * S + 9 * (size_t)h->t.n_joints + 32);
     else if (variant == 3)  // rows, then the extra-joint area (layout: TileSmem)
         smem = sizeof(double) * ((size_t)br2::TileSmem<BR2_TILE_C, 0>::ROWS_END * (size_t)(pick.threads + 1) +
-                                 2 * br2::TileSmem<BR2_TILE_C, 0>::EXW * (size_t)h->tile.n_xe + (4 + 8 + 4) * (size_t)h->tile.n_xj +
-                                 ((size_t)h->tile.n_xe + 1) / 2 + ((size_t)h->tile.n_xitems + 1) / 2);
+                                 2 * br2::TileSmem<BR2_TILE_C, 0>::EXW * (size_t)h->tile.n_xe +
+                                 4 * (size_t)h->tile.n_nr * (size_t)h->tile.nf_items + (8 + 4 + 2) * (size_t)h->tile.n_xj +
+                                 ((size_t)h->tile.n_xe + 1) / 2);
     else
     {
         // fixed part: 45 T doubles + two [3][T+8] accumulators + O1 (T ints); tail (omega, extra-joint rows,

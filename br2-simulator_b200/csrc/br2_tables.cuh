@@ -47,14 +47,15 @@ struct TilePlan {
     // "extra" joints: tip-to-base joints between segments (TipToTipStraightJoint).  Few per
     // assembly; evaluated by designated threads from data their elements publish; none for single-segment assemblies.
     int n_xe, n_xj;                         // elements that publish director / omega / radius / node sums; extra joints
-    int n_xitems;                           // entries of `xitems`
+    int n_nr, nf_items;                     // node rows per CTA (nodes that add extra-joint forces) and items per row
     int xb_count[8];                        // per rank: published elements of OTHER CTAs whose data the CTA consumes (x 152 bytes per step on its XB barrier)
     const int *xe_mask;                     // [n_xe] bit r: the CTA of rank r consumes the element's data (device)
     const int *xi;                          // [n_ctas][xi_stride][C + 1] per thread: packed info of each slot (published xe + 1
-                                            // | overwrite source xe + 1 << 8 | node items << 16 | first item << 20), then the
+                                            // | overwrite source xe + 1 << 8 | node items << 16 | node row << 20), then the
                                             // extra joint component the thread evaluates (joint << 2 | component) or -1 (device).
                                             // A joint between two CTAs of a cluster is evaluated by BOTH (each for its own nodes)
-    const int *xitems;                      // node items (joint << 1 | sign), grouped per slot (device; copied to shared memory)
+    const int *xjt;                         // [n_ctas][n_xj][4] where in the CTA's node rows the joint's half force goes: rod
+                                            // one's two nodes (+), rod two's two nodes (-); -1: not in this CTA (device)
     const int *xj_i;                        // [n_xj][12] rank1, row1, j1, rank2, row2, j2 of the joined elements; xe of Q1, Q2, radius one, radius two
     const double *xj_d;                     // [n_xj][8] k, nu, l1[3], l2[3]
 };

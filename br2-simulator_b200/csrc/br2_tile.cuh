@@ -208,11 +208,12 @@ struct TileSmem {
     // after the rows (host: TileSmem<C, 0>::ROWS_END * (threads + 1) words), the extra-joint area of a kExtras kernel;
     // every CTA has its own complete copy, filled by the elements' owners (pushes through distributed shared memory):
     //   EXD [2][n_xe][20]  by step parity, per published element: director 9 | omega 3 | radius | x_k + x_{k+1} 3 | v_k + v_{k+1} 3
-    //   JF  [n_xj][4]      half force of each extra joint this CTA evaluates
+    //   NF  [n_nr][items][4] node rows: the signed half forces a node adds, item by item (scattered there by the threads
+    //                      that evaluate the joints, in the order the reference applies them)
     //   XJD [n_xj][8]      k, nu, l1[3], l2[3]   (point force: F[3], ramp_up_time)
     //   XJI [n_xj][8] int  published element of: rod one's element, rod two's element, director one, director two; type
+    //   XJT [n_xj][4] int  where in NF the joint's half force goes: rod one's two nodes (+), rod two's (-); -1 = another CTA's
     //   XPM [n_xe]    int  bit r set: the CTA of cluster rank r consumes the element's data
-    //   XIT [n_xitems] int node items (joint << 1 | sign)
     static constexpr int EX = ROWS_END;
     static constexpr int EXW = 20;                // doubles per published element (row stride)
     static constexpr int EXN = 19;                // ... of which in use
@@ -229,7 +230,7 @@ struct TileThread {
     int t, tn, t1, to;  // rows: own, next run (or own), partner as rod one of my joints (or 0), owner of the joints in which I am rod one (or 0)
     int rod;
     // extra joints (kExtras kernels): per slot published xe + 1 | overwrite source xe + 1 << 8 | node items << 16 |
-    // first item << 20; the extra joint component this thread evaluates (joint << 2 | component) or -1
+    // node row << 20; the extra joint component this thread evaluates (joint << 2 | component) or -1
     int xinfo[C], xjoint;
     int bad;  // bit 0: rotation angle, bit 1: curvature angle, bit 2: strain left its series' range (or NaN)
 };
@@ -334,9 +335,10 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
     const int n_xe = kExtras ? p.tile.n_xe : 0, n_xj = kExtras ? p.tile.n_xj : 0;
     const int buf = gstep & 1;
     double *const EXD = sm + L::EX + buf * (L::EXW * n_xe);           // this step's buffer of pushed element data
-    double *const JF = sm + L::EX + 2 * L::EXW * n_xe;
-    const double *const XJD = JF + 4 * n_xj;
-    const int *const XJI = (const int *)(XJD + 8 * n_xj), *const XPM = XJI + 8 * n_xj, *const XIT = XPM + ((n_xe + 1) & ~1);
+    double *const NF = sm + L::EX + 2 * L::EXW * n_xe;
+    const int nf_row = 4 * (kExtras ? p.tile.nf_items : 0);
+    const double *const XJD = NF + nf_row * (kExtras ? p.tile.n_nr : 0);
+    const int *const XJI = (const int *)(XJD + 8 * n_xj), *const XJT = XJI + 8 * n_xj, *const XPM = XJT + 4 * n_xj;
     const uint32_t xbar = bars.xb + 8u * (uint32_t)buf, xparity = ((uint32_t)gstep >> 1) & 1u;
 
     // =============================== P1: publish the run's first node / element ==============
@@ -630,10 +632,11 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
             const int xj = th.xjoint >> 2, i = th.xjoint & 3;
             const int2 ja = *(const int2 *)(XJI + xj * 8), jb = *(const int2 *)(XJI + xj * 8 + 2);
             const double *jd = XJD + xj * 8;
+            double f;
             if (XJI[xj * 8 + 4] == 1) {
                 // point force (custom_activation.PointForces): F min(1, t / ramp_up_time) on one node
                 const double fac = fmin(1.0, time_mid / jd[3]);
-                JF[xj * 4 + i] = jd[i] * fac;
+                f = jd[i] * fac;
             } else {
                 if (kCluster && p.tile.xb_count[rank] > 0) mbar_wait(xbar, xparity);  // what other CTAs push has landed (own elements: B2)
                 const double *e1 = EXD + ja.x * L::EXW, *e2 = EXD + ja.y * L::EXW;
@@ -644,8 +647,14 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
                 const double a1 = fma(q1[i], jd[2], fma(q1[3 + i], jd[3], q1[6 + i] * jd[4])) * e1[12];
                 const double a2 = fma(q2[i], jd[5], fma(q2[3 + i], jd[6], q2[6 + i] * jd[7])) * e2[12];
                 const double gap = (c2 + a2) - (c1 + a1);
-                JF[xj * 4 + i] = 0.5 * fma(kj, gap, -nuj * vrel);
+                f = 0.5 * fma(kj, gap, -nuj * vrel);
             }
+            // into the rows of the joint's nodes that live in this CTA: rod one's take +F/2, rod two's -F/2
+            const int2 ta = *(const int2 *)(XJT + xj * 4), tb2 = *(const int2 *)(XJT + xj * 4 + 2);
+            if (ta.x >= 0) NF[ta.x + i] = f;
+            if (ta.y >= 0) NF[ta.y + i] = f;
+            if (tb2.x >= 0) NF[tb2.x + i] = -f;
+            if (tb2.y >= 0) NF[tb2.y + i] = -f;
         }
         if (kSplit) mbar_arrive_warp(bars.b4);  // (CTA barriers: B3 below orders the joint forces before their readers)
     }
@@ -708,15 +717,14 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
 #pragma unroll
             for (int i = 0; i < 3; ++i) text[i] = fma(TAV(j, i), ramp, text[i]);
             if (kExtras && (th.xinfo[j] >> 8) != 0) {
-                if (kLast) {  // half forces of the extra joints on this node (every other step: after the rotation below)
-                    const int cnt = (th.xinfo[j] >> 16) & 0xF, first = th.xinfo[j] >> 20;
+                if (kLast) {  // half forces of the extra joints on this node (every other step: before the rotations below)
+                    const int cnt = (th.xinfo[j] >> 16) & 0xF;
+                    const double *nf = NF + (th.xinfo[j] >> 20) * nf_row;
                     if (kSplit && cnt) mbar_wait(bars.b4, (uint32_t)gstep & 1u);
                     for (int q = 0; q < cnt; ++q) {
-                        const int item = XIT[first + q];
-                        const double sgn = (item & 1) ? -1.0 : 1.0;
 #pragma unroll
                         for (int i = 0; i < 3; ++i) {
-                            const double f = sgn * JF[(item >> 1) * 4 + i];
+                            const double f = nf[4 * q + i];
                             v[j][i] = fma(th.dtmc[j], f, v[j][i]);
                             r_fext[j][i] += f;
                         }
@@ -823,31 +831,25 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
             if (kSplit && any) mbar_wait(bars.b4, (uint32_t)gstep & 1u);
 #pragma unroll
             for (int j = 0; j < C; ++j) {
-                const int cnt = (th.xinfo[j] >> 16) & 0xF, first = th.xinfo[j] >> 20;
+                const int cnt = (th.xinfo[j] >> 16) & 0xF;
                 if (cnt) {
-                    // the first three items (a joined element's node has three: one per rod of the other segment) without a
-                    // branch between them, so that their loads are in flight together; same order of summation as the loop
-                    int item[3];
+                    // the node's row: item q at 4 q (a joined element's node has three items, one per rod of the other segment);
+                    // the first three without a branch between them, same order of summation as the loop
+                    const double *nf = NF + (th.xinfo[j] >> 20) * nf_row;
                     double f[3][3];
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) item[q] = XIT[first + min(q, cnt - 1)];
 #pragma unroll
                     for (int q = 0; q < 3; ++q)
 #pragma unroll
-                        for (int i = 0; i < 3; ++i) f[q][i] = JF[(item[q] >> 1) * 4 + i];
+                        for (int i = 0; i < 3; ++i) f[q][i] = nf[4 * min(q, cnt - 1) + i];
 #pragma unroll
                     for (int q = 0; q < 3; ++q) {
-                        const double sd = (item[q] & 1) ? -th.dtmc[j] : th.dtmc[j];
-                        const double s = (q < cnt) ? sd : 0.0;
+                        const double s = (q < cnt) ? th.dtmc[j] : 0.0;
 #pragma unroll
                         for (int i = 0; i < 3; ++i) v[j][i] = fma(s, f[q][i], v[j][i]);
                     }
-                    for (int q = 3; q < cnt; ++q) {
-                        const int it = XIT[first + q];
-                        const double sgn = (it & 1) ? -1.0 : 1.0;
+                    for (int q = 3; q < cnt; ++q)
 #pragma unroll
-                        for (int i = 0; i < 3; ++i) v[j][i] = fma(th.dtmc[j] * sgn, JF[(it >> 1) * 4 + i], v[j][i]);
-                    }
+                        for (int i = 0; i < 3; ++i) v[j][i] = fma(th.dtmc[j], nf[4 * q + i], v[j][i]);
                 }
             }
         }
@@ -1035,10 +1037,11 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
                 }
             }
             // (a cluster's idle lanes may evaluate joint components too: the plan fills the last warp)
-            th.xjoint = (kExtras && tp.n_xj > 0 && (active || kCluster)) ? tp.xi[(rank * tp.xi_stride + t) * (C + 1) + C] : -1;
+            const bool in_last_warp = kCluster && t < 32 * ((tp.cta_threads[rank] + 31) / 32);
+            th.xjoint = (kExtras && tp.n_xj > 0 && (active || in_last_warp)) ? tp.xi[(rank * tp.xi_stride + t) * (C + 1) + C] : -1;
             if (kExtras) {  // this CTA's copy of the extra joints' tables (layout: TileSmem)
-                double *const XJD = sm + L::EX + 2 * L::EXW * tp.n_xe + 4 * tp.n_xj;
-                int *const XJI = (int *)(XJD + 8 * tp.n_xj), *const XPM = XJI + 8 * tp.n_xj, *const XIT = XPM + ((tp.n_xe + 1) & ~1);
+                double *const XJD = sm + L::EX + 2 * L::EXW * tp.n_xe + 4 * tp.nf_items * tp.n_nr;
+                int *const XJI = (int *)(XJD + 8 * tp.n_xj), *const XJT = XJI + 8 * tp.n_xj, *const XPM = XJT + 4 * tp.n_xj;
                 for (int i = t; i < 8 * tp.n_xj; i += NT) {
                     // (a tip-to-base joint's stiffness is proportional to Young's modulus: free_simulator.py:220-228)
                     const bool stiffness = kPerInst && (i & 7) == 0 && tp.xj_i[12 * (i >> 3) + 10] == 0;
@@ -1053,7 +1056,7 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
                     XJI[8 * i + 4] = row[10];  // type: 0 tip-to-base joint, 1 point force
                 }
                 for (int i = t; i < tp.n_xe; i += NT) XPM[i] = tp.xe_mask[i];
-                for (int i = t; i < tp.n_xitems; i += NT) XIT[i] = tp.xitems[i];
+                for (int i = t; i < 4 * tp.n_xj; i += NT) XJT[i] = tp.xjt[(size_t)rank * 4 * tp.n_xj + i];
             }
             th.rod = rod;  // indexes the per-rod joint descriptors in the constant bank (TilePlan::jd)
         }
