@@ -127,6 +127,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 #ifndef BR2_TILE_SHUFFLE
 #define BR2_TILE_SHUFFLE 0  // A/B: the next run's first node / element through warp shuffles where it is the next lane (measured: DESIGN.md)
 #endif
+#ifndef BR2_TILE_GATHER_MERGED
+#define BR2_TILE_GATHER_MERGED 1  // tip-to-base forces: one warp-level branch, both slots' rows loaded together (A/B: 0)
+#endif
 #ifndef BR2_TILE_HOIST_DAMPER
 #define BR2_TILE_HOIST_DAMPER 0  // damper exponentials before the third wait (costs registers: measured)
 #endif
@@ -828,6 +831,40 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
             bool any = false;
 #pragma unroll
             for (int j = 0; j < C; ++j) any = any || ((th.xinfo[j] >> 16) & 0xF) != 0;
+#if BR2_TILE_GATHER_MERGED
+            // One branch per WARP (most warps of a large CTA hold no rod end), and inside it both slots' rows without a branch
+            // between them: the 18 loads are in flight together and the additions of a slot without items are masked (s = 0),
+            // instead of two divergent blocks with a load-to-use bubble each.  Same order of summation per node.
+            if (__any_sync(0xffffffffu, any)) {
+                if (kSplit && any) mbar_wait(bars.b4, (uint32_t)gstep & 1u);
+                int cnt[C];
+                double f[C][3][3];
+#pragma unroll
+                for (int j = 0; j < C; ++j) {
+                    cnt[j] = (th.xinfo[j] >> 16) & 0xF;
+                    const double *nf = NF + (th.xinfo[j] >> 20) * nf_row;  // (row 0 for a slot without items: finite, masked)
+#pragma unroll
+                    for (int q = 0; q < 3; ++q)
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) f[j][q][i] = nf[4 * min(q, max(cnt[j] - 1, 0)) + i];
+                }
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+#pragma unroll
+                    for (int j = 0; j < C; ++j) {
+                        const double s = (q < cnt[j]) ? th.dtmc[j] : 0.0;
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) v[j][i] = fma(s, f[j][q][i], v[j][i]);
+                    }
+#pragma unroll
+                for (int j = 0; j < C; ++j) {
+                    const double *nf = NF + (th.xinfo[j] >> 20) * nf_row;
+                    for (int q = 3; q < cnt[j]; ++q)
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) v[j][i] = fma(th.dtmc[j], nf[4 * q + i], v[j][i]);
+                }
+            }
+#else
             if (kSplit && any) mbar_wait(bars.b4, (uint32_t)gstep & 1u);
 #pragma unroll
             for (int j = 0; j < C; ++j) {
@@ -852,6 +889,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
                         for (int i = 0; i < 3; ++i) v[j][i] = fma(th.dtmc[j], nf[4 * q + i], v[j][i]);
                 }
             }
+#endif
         }
         const double hmult = kEnd ? hdt : dt;
 #pragma unroll
