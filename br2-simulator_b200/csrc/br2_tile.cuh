@@ -24,9 +24,10 @@
 // after the first, all Voronoi couples after the second, the tip-to-base joints and the damper exponentials after the
 // third) and waits only where it reads a neighbour's rows.  Tip-to-base joints between segments no longer use the
 // hardware cluster barrier at all: the few elements involved PUSH director, omega, radius and node sums into the
-// consuming CTAs' shared memory (distributed shared memory stores) and arrive on the consumer's mbarrier with
-// release.cluster; both CTAs of an interface evaluate its joints themselves (bit-identical arithmetic), so the forces
-// never travel back.  The small single-segment kernel (two warps per CTA, six CTAs per SM) keeps __syncthreads.
+// consuming CTAs' shared memory with asynchronous distributed-shared-memory stores that count their bytes off the
+// consumer's mbarrier (st.async ... complete_tx: no cluster-scope fence anywhere); both CTAs of an interface evaluate its
+// joints themselves (bit-identical arithmetic), so the forces never travel back.  The kernels with several CTAs per SM
+// (single-segment: two warps per CTA, six CTAs per SM; double / triple on one CTA) keep __syncthreads: measured.
 //
 // Semantics are those of br2_fast.cuh / br2_generic.cuh; the optimistic-series
 // protocol is the same: a CTA that leaves a series' validity range flags its instance and does not write back;
@@ -928,8 +929,8 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
     // carry the rods' ends (the tip-to-base protocol) on the 2-warp schedulers, where the slack absorbs it.
     const int t = kCluster ? ((tp.warp_map[threadIdx.x >> 5] << 5) | (threadIdx.x & 31)) : (int)threadIdx.x;
     // kCluster: the CTAs of a thread-block cluster integrate one instance together, one group of ring-connected
-    // rods (a segment) each; they exchange the tip-to-base joints' data through distributed shared memory (pushes + remote
-    // mbarrier arrives, see tile_step) and meet at a cluster barrier only between work items.  The cluster, not the CTA,
+    // rods (a segment) each; they exchange the tip-to-base joints' data through distributed shared memory (asynchronous
+    // pushes that count themselves off the consumer's mbarrier, see tile_step) and meet at a cluster barrier only between work items.  The cluster, not the CTA,
     // pulls work items.
     const int rank = kCluster ? (int)cooperative_groups::this_cluster().block_rank() : 0;
     const long long total_items = p.batch * (long long)p.n_chunks;
