@@ -176,6 +176,7 @@ struct br2_handle_s {
     const double *inst_uni = nullptr;          // per-instance material constants (borrowed device buffers), or nullptr
     const double *inst_act_d = nullptr;
     const double *inst_joint_scale = nullptr;
+    const double *cls_uni = nullptr;           // [n_cls][BR2_FC_COUNT] constants per class of rods (assemblies with several)
     int n_act = 0;
     double *scratch_state = nullptr;  // br2_step_host
     double *scratch_pressures = nullptr;
@@ -243,9 +244,40 @@ struct TileExtraTables {
 bool make_tile_plan(const br2_program *p, int C, br2::TilePlan *plan, TileExtraTables *xt, std::string *why) {
     *plan = br2::TilePlan{};
     plan->C = C;
-    if (!p->fast_ok || !p->fast_uniform) return *why = "assembly constants are not uniform", false;
+    if (!p->fast_ok) return *why = "assembly outside the fast path's pattern", false;
     if (p->n_rods > BR2_TILE_MAX_RODS) return *why = "too many rods", false;
     const size_t S = (size_t)p->n_slots;
+    // Element constants: one set per CLASS of rods (all elements of a rod equal, rods compared by their first slot; the same
+    // 1e-12 the lowering uses for "uniform").  One class: the kernels take the constants from the constant bank; several
+    // (segments of different element count or material): the instantiations that read a shared-memory copy, indexed by class.
+    plan->n_cls = 0;
+    {
+        int first_of_cls[BR2_TILE_MAX_CLS];
+        auto same = [&](size_t a, size_t b) {
+            for (int i = 0; i < BR2_FC_PIN; ++i) {
+                const double x = p->fast_c[(size_t)i * S + a], y = p->fast_c[(size_t)i * S + b];
+                if (fabs(x - y) > 1e-12 * std::max(fabs(x), 1e-300)) return false;
+            }
+            return true;
+        };
+        for (int r = 0; r < p->n_rods; ++r) {
+            const int32_t *ri = p->rod_i + r * BR2_ROD_NI;
+            const size_t s0 = (size_t)ri[BR2_ROD_SLOT0];
+            for (int k = 1; k < ri[BR2_ROD_N]; ++k)  // (element slots; the node-only last slot carries padding)
+                if (!same(s0, s0 + k)) return *why = "element constants vary along a rod", false;
+            int cls = -1;
+            for (int c = 0; c < plan->n_cls && cls < 0; ++c)
+                if (same((size_t)first_of_cls[c], s0)) cls = c;
+            if (cls < 0) {
+                if (plan->n_cls == BR2_TILE_MAX_CLS) return *why = "more than " + std::to_string(BR2_TILE_MAX_CLS) + " classes of rod constants", false;
+                cls = plan->n_cls++;
+                first_of_cls[cls] = (int)s0;
+            }
+            plan->rod_cls[r] = cls;
+            plan->cls_slot[cls] = (int)s0;
+        }
+        if (plan->n_cls == 1 && !p->fast_uniform) return *why = "assembly constants are not uniform", false;  // (cannot happen)
+    }
     // ring-connected rods (a segment) must share a CTA: union-find over the owned surface joints
     int group[BR2_TILE_MAX_RODS];
     for (int r = 0; r < p->n_rods; ++r) group[r] = r;
@@ -317,15 +349,18 @@ bool make_tile_plan(const br2_program *p, int C, br2::TilePlan *plan, TileExtraT
                 if (!same) return *why = "joint descriptors vary along a rod", false;
             }
             // the per-joint parameters must be the uniform ones the kernel reads from the constant bank
-            const double *fc = p->fast_c;
+            const double *fc = p->fast_c + slot0;  // (the owning rod's constants)
             if (jd[0] != fc[(size_t)BR2_FC_JK * S] || jd[1] != fc[(size_t)BR2_FC_JNU * S] || jd[2] != fc[(size_t)BR2_FC_JKREP * S])
                 return *why = "joint parameters are not uniform", false;
         }
         if (owned != 0 && owned != n) return *why = "only some elements of a rod own a joint", false;
     }
-    const double *fc = p->fast_c;
-    const double l0 = fc[(size_t)BR2_FC_LN_CR * S], l1 = fc[(size_t)(BR2_FC_LN_CR + 1) * S], l2 = fc[(size_t)(BR2_FC_LN_CR + 2) * S];
-    plan->round_section = (l0 == l1 && fabs(l0 - 2.0 * l2) <= 1e-13 * fabs(l0)) ? 1 : 0;
+    plan->round_section = 1;
+    for (int c = 0; c < plan->n_cls; ++c) {
+        const double *fc = p->fast_c + plan->cls_slot[c];
+        const double l0 = fc[(size_t)BR2_FC_LN_CR * S], l1 = fc[(size_t)(BR2_FC_LN_CR + 1) * S], l2 = fc[(size_t)(BR2_FC_LN_CR + 2) * S];
+        if (!(l0 == l1 && fabs(l0 - 2.0 * l2) <= 1e-13 * fabs(l0))) plan->round_section = 0;
+    }
     for (int r = 0; r < p->n_rods; ++r)
         if (plan->jd[r][2] != 0.0 || plan->jd[r][6] != 0.0)
             return *why = "a surface joint's direction vector has a component along the rod axis", false;
@@ -608,6 +643,16 @@ int br2_create(const br2_program *p, int device, br2_handle *out) {
     {
         TileExtraTables xt;
         h->tile_ok = h->fast_ok && make_tile_plan(p, BR2_TILE_C, &h->tile, &xt, &h->tile_why);
+        if (h->tile_ok && h->tile.n_cls > 1) {  // one column of constants per class of rods, read by the kPerInst kernels
+            std::vector<double> cls((size_t)h->tile.n_cls * BR2_FC_COUNT);
+            for (int c = 0; c < h->tile.n_cls; ++c)
+                for (int i = 0; i < BR2_FC_COUNT; ++i) cls[(size_t)c * BR2_FC_COUNT + i] = p->fast_c[(size_t)i * S + h->tile.cls_slot[c]];
+            rc = upload(h, cls.data(), cls.size(), &h->cls_uni);
+            if (rc != BR2_OK) {
+                br2_destroy(h);
+                return rc;
+            }
+        }
         if (h->tile_ok && h->tile.n_xj > 0) {
             rc = upload(h, xt.xpack.data(), xt.xpack.size(), &h->tile.xi);
             if (rc == BR2_OK) rc = upload(h, xt.xjt.data(), xt.xjt.size(), &h->tile.xjt);
@@ -795,6 +840,9 @@ int br2_set_instance_params(br2_handle h, const double *dev_uni, const double *d
         return fail(BR2_ESTATE, "br2_set_instance_params: only the tile kernel reads per-instance constants (" +
                                     (h->tile_ok ? std::string("select variant 3") : h->tile_why) + ")");
     if ((h->n_act > 0 && !dev_act_d) || !dev_joint_scale) return fail(BR2_EINVAL, "br2_set_instance_params: NULL table");
+    if (h->tile.n_cls > 1)
+        return fail(BR2_ESTATE, "br2_set_instance_params: the assembly's rods differ in their constants; per-instance tables "
+                                "are defined for assemblies with one set of element constants");
     h->inst_uni = dev_uni;
     h->inst_act_d = dev_act_d;
     h->inst_joint_scale = dev_joint_scale;
@@ -882,12 +930,19 @@ int br2_step(br2_handle h, int64_t n_steps, double t0, double dt, void *stream, 
     sp.inst_uni = h->inst_uni;
     sp.inst_act_d = h->inst_act_d;
     sp.inst_joint_scale = h->inst_joint_scale;
+    sp.inst_stride = 1;
     sp.n_act = h->n_act;
     const bool per_instance = h->inst_uni != nullptr;
+    // rods that differ in their constants: the same kernels, every instance reading the one table of classes
+    const bool per_class = !per_instance && h->variant == 3 && h->tile.n_cls > 1;
+    if (per_class) {
+        sp.inst_uni = h->cls_uni;
+        sp.inst_stride = 0;
+    }
     if (per_instance && (h->variant != 3 || !h->kernel.fn_pi))
         return fail(BR2_ESTATE, "br2_step: per-instance material parameters need the tile kernel (br2_select_kernel 3)");
-    const void *step_fn = per_instance ? (const void *)h->kernel.fn_pi : (const void *)h->kernel.fn;
-    const void *exact_fn = per_instance ? (const void *)h->exact.fn_pi : (const void *)h->exact.fn;
+    const void *step_fn = (per_instance || per_class) ? (const void *)h->kernel.fn_pi : (const void *)h->kernel.fn;
+    const void *exact_fn = (per_instance || per_class) ? (const void *)h->exact.fn_pi : (const void *)h->exact.fn;
     sp.status = h->status;
     sp.replays = h->replays;
     sp.only_flagged = 0;
@@ -1060,6 +1115,7 @@ int br2_describe_plan(const br2_program *p, char *buf, int64_t buf_len) {
         for (int c = 0; c < plan.n_ctas; ++c) text += (c ? ", " : " of ") + std::to_string(plan.cta_threads[c]);
         text += " threads (" + std::to_string(BR2_TILE_C) + " slots per thread), " + std::to_string(plan.n_xj) +
                 " tip-to-base joint(s) / point force(s)";
+        if (plan.n_cls > 1) text += ", " + std::to_string(plan.n_cls) + " classes of rod constants (shared-memory copy)";
     } else if (p->fast_ok && p->fast_i && p->fast_c) {
         text = p->fast_point_forces ? "generic: table-interpreting kernel (tile kernel refused: " + why + ")"
                                     : std::string(p->fast_uniform ? "fast-uniform" : "fast") + ": one slot per thread (tile kernel refused: " + why + ")";

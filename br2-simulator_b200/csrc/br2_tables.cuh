@@ -31,6 +31,7 @@ struct DevTables {
 // Thread-coarsened ("tile") kernel: every thread owns C consecutive slots of one rod (br2_tile.cuh).
 #define BR2_TILE_MAX_RODS 12
 #define BR2_MAX_CHUNKS 8
+#define BR2_TILE_MAX_CLS 4   // classes of rods with equal element constants (rods of different length: one class per length)
 struct TilePlan {
     int C;                                  // slots per thread
     int round_section;                      // ln c_r1 = ln c_r2 = 2 ln c_r3: one exponential per element and step
@@ -41,6 +42,9 @@ struct TilePlan {
     int xi_stride;                          // rows of `xi` per rank
     int warp_map[16];                       // cluster kernels: logical warp executed by each hardware warp (a permutation)
     int rod_t0[BR2_TILE_MAX_RODS + 1];      // first thread of each rod inside its CTA
+    int n_cls;                              // classes of rods with equal element constants (1: the constant bank serves all)
+    int rod_cls[BR2_TILE_MAX_RODS];         // class of each rod
+    int cls_slot[BR2_TILE_MAX_CLS];         // a table slot that carries the class's constants (host side)
     int partner[BR2_TILE_MAX_RODS];         // rod whose elements are rod one of the joints this rod's elements own, or -1
     int owner[BR2_TILE_MAX_RODS];           // rod whose elements own the joints in which this rod's elements are rod one, or -1
     double jd[BR2_TILE_MAX_RODS][8];        // {dv2[3], offset/2} of the joints the rod owns, {dv1[3], offset/2} as rod one
@@ -87,7 +91,9 @@ struct StepParams {
     long long queue_group;                // instances per group of the tile kernel's work queue (see the kernel)
     double chunk_t0[BR2_MAX_CHUNKS];      // fp64-accumulated start time of each chunk
     // per-instance material parameters (tile kernels' kPerInst instantiations; br2_set_instance_params)
-    const double *inst_uni;               // [batch][BR2_FC_COUNT] what `uni` holds, per instance
+    const double *inst_uni;               // [batch or 1][n_cls][BR2_FC_COUNT] what `uni` holds, per instance and class of rods
+    long long inst_stride;                // rows of inst_uni per instance: n_cls, or 0 when every instance reads the same table
+                                          // (assemblies whose rods differ in their constants, e.g. segments of different length)
     const double *inst_act_d;             // [batch][n_act][3] actuation torque per unit pressure, per instance
     const double *inst_joint_scale;       // [batch] factor on the tip-to-base joints' stiffness
     int n_act;

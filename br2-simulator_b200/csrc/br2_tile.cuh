@@ -233,6 +233,7 @@ struct TileThread {
     int fl[C];
     int t, tn, t1, to;  // rows: own, next run (or own), partner as rod one of my joints (or 0), owner of the joints in which I am rod one (or 0)
     int rod;
+    int uoff;  // kPerInst kernels: where my rod's class of constants starts in the CTA's shared-memory copy
     // extra joints (kExtras kernels): per slot published xe + 1 | overwrite source xe + 1 << 8 | node items << 16 |
     // node row << 20; the extra joint component this thread evaluates (joint << 2 | component) or -1
     int xinfo[C], xjoint;
@@ -919,7 +920,8 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
     __shared__ int s_chunk;
     __shared__ int s_why;
     __shared__ unsigned long long s_bar[6];  // B1, B2, B3, B4 (joint forces ready), XB[2] (pushed element data, by step parity)
-    __shared__ double s_uni[kPerInst ? BR2_FC_COUNT + 12 : 1];  // kPerInst: this instance's constants (uni, then kd)
+    // kPerInst: this instance's constants (uni, then kd), one block per class of rods
+    __shared__ double s_uni[kPerInst ? BR2_TILE_MAX_CLS * (BR2_FC_COUNT + 12) : 1];
 
     const DevTables &tb = p.t;
     const TilePlan &tp = p.tile;
@@ -1039,7 +1041,7 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
                 if (valid && fi[BR2_FAST_SOFTFIX_ROW] >= 0) f |= TILE_F_SOFTFIX;
                 th.fl[j] = f;
                 th.xinfo[j] = (kExtras && tp.n_xj > 0 && active) ? tp.xi[(rank * tp.xi_stride + t) * (C + 1) + j] : 0;
-                const double c_t = kPerInst ? p.inst_uni[b * BR2_FC_COUNT + BR2_FC_CT] : p.uni[BR2_FC_CT];
+                const double c_t = kPerInst ? p.inst_uni[(b * p.inst_stride + tp.rod_cls[rod]) * BR2_FC_COUNT + BR2_FC_CT] : p.uni[BR2_FC_CT];
                 th.dtmc[j] = dt * c_t / tb.slot_c[(long long)BR2_SC_MASS * S + sc];
                 double ta[3] = {0.0, 0.0, 0.0};
                 if (valid) {
@@ -1047,7 +1049,7 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
                         const double P = p.pressures[(long long)tb.act_i[r] * p.batch + b];
 #pragma unroll
                         for (int i = 0; i < 3; ++i)
-                            ta[i] = fma(P, kPerInst ? p.inst_act_d[(b * p.n_act + r) * 3 + i] : tb.act_d[r * 3 + i], ta[i]);
+                            ta[i] = fma(P, (kPerInst && p.inst_act_d) ? p.inst_act_d[(b * p.n_act + r) * 3 + i] : tb.act_d[r * 3 + i], ta[i]);
                     }
                 }
 #pragma unroll
@@ -1083,7 +1085,7 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
                 int *const XJI = (int *)(XJD + 8 * tp.n_xj), *const XJT = XJI + 8 * tp.n_xj, *const XPM = XJT + 4 * tp.n_xj;
                 for (int i = t; i < 8 * tp.n_xj; i += NT) {
                     // (a tip-to-base joint's stiffness is proportional to Young's modulus: free_simulator.py:220-228)
-                    const bool stiffness = kPerInst && (i & 7) == 0 && tp.xj_i[12 * (i >> 3) + 10] == 0;
+                    const bool stiffness = kPerInst && p.inst_joint_scale && (i & 7) == 0 && tp.xj_i[12 * (i >> 3) + 10] == 0;
                     XJD[i] = stiffness ? tp.xj_d[i] * p.inst_joint_scale[b] : tp.xj_d[i];
                 }
                 for (int i = t; i < tp.n_xj; i += NT) {
@@ -1098,14 +1100,20 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
                 for (int i = t; i < 4 * tp.n_xj; i += NT) XJT[i] = tp.xjt[(size_t)rank * 4 * tp.n_xj + i];
             }
             th.rod = rod;  // indexes the per-rod joint descriptors in the constant bank (TilePlan::jd)
+            th.uoff = kPerInst ? tp.rod_cls[rod] * (BR2_FC_COUNT + 12) : 0;
         }
         // zero the exchange arrays (the zero row stays zero for the whole chunk)
         for (int i = t; i < L::ZERO_END; i += NT) sm[i] = 0.0;
         if (kPerInst) {
             // this instance's constants, and the products br2_step forms on the host for the shared ones (same expressions)
-            for (int i = t; i < BR2_FC_COUNT; i += NT) s_uni[i] = p.inst_uni[b * BR2_FC_COUNT + i];
-            if (t < 12) {
-                const double *u = p.inst_uni + b * BR2_FC_COUNT;
+            // (one block per class of rods with equal constants; inst_stride = 0: every instance reads the same table)
+            for (int i = t; i < tp.n_cls * BR2_FC_COUNT; i += NT) {
+                const int c = i / BR2_FC_COUNT, k = i - c * BR2_FC_COUNT;
+                s_uni[c * (BR2_FC_COUNT + 12) + k] = p.inst_uni[(b * p.inst_stride + c) * BR2_FC_COUNT + k];
+            }
+            for (int tt = t; tt < 12 * tp.n_cls; tt += NT) {
+                const int c = tt / 12, t = tt - 12 * c;
+                const double *u = p.inst_uni + (b * p.inst_stride + c) * BR2_FC_COUNT;
                 const double dt = p.dt;
                 double kd = 0.5 * dt;                                                   // [11]
                 if (t < 3) kd = dt * u[BR2_FC_CT] * u[BR2_FC_GRAVITY + t];
@@ -1115,7 +1123,7 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
                 else if (t == 6) kd = 0.5 * u[BR2_FC_JK];
                 else if (t == 7) kd = -0.5 * u[BR2_FC_JKREP];
                 else if (t < 11) kd = dt * u[BR2_FC_JINV + (t - 8)];
-                s_uni[BR2_FC_COUNT + t] = kd;
+                s_uni[c * (BR2_FC_COUNT + 12) + BR2_FC_COUNT + t] = kd;
             }
         }
         tile_sync<kCluster>();
@@ -1132,14 +1140,14 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
             th.bad |= TileMath<kExact>::rotate(th.Q[j], th.w[j], hdt, hdt) ? 1 : 0;
         }
         for (int step = 0; step < n_steps - 1; ++step) {
-            tile_step<C, NT, false, false, kExtras, kCluster, kExact, kSplit, kPerInst>(p, sm, s_uni, th, time + hdt, b, rank, gstep, bars);
+            tile_step<C, NT, false, false, kExtras, kCluster, kExact, kSplit, kPerInst>(p, sm, s_uni + th.uoff, th, time + hdt, b, rank, gstep, bars);
             time = (time + hdt) + hdt;
             ++gstep;
         }
         if (final_chunk)
-            tile_step<C, NT, true, true, kExtras, kCluster, kExact, kSplit, kPerInst>(p, sm, s_uni, th, time + hdt, b, rank, gstep, bars);
+            tile_step<C, NT, true, true, kExtras, kCluster, kExact, kSplit, kPerInst>(p, sm, s_uni + th.uoff, th, time + hdt, b, rank, gstep, bars);
         else
-            tile_step<C, NT, true, false, kExtras, kCluster, kExact, kSplit, kPerInst>(p, sm, s_uni, th, time + hdt, b, rank, gstep, bars);
+            tile_step<C, NT, true, false, kExtras, kCluster, kExact, kSplit, kPerInst>(p, sm, s_uni + th.uoff, th, time + hdt, b, rank, gstep, bars);
         ++gstep;
 
         // a CTA that left the series' validity range keeps the chunk-start state and asks for the exact path, which

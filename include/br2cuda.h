@@ -214,7 +214,9 @@ int br2_set_actuation(br2_handle h, const double *dev_pressures);
  * [batch][n_act][3] = per instance act_d; dev_joint_scale [batch] = factor on the tip-to-base joints' stiffness (it is
  * proportional to Young's modulus, :220-228).  dev_uni == NULL returns to the shared constants.  Geometry, masses and the
  * joint direction vectors stay common to the batch.  The exact-path replay of one-CTA assemblies reads the shared tables,
- * so a per-instance run that leaves the optimistic kernel's range is reported by br2_unresolved_count instead of redone. */
+ * so a per-instance run that leaves the optimistic kernel's range is reported by br2_unresolved_count instead of redone.
+ * Defined for assemblies with ONE set of element constants; an assembly whose rods differ in their constants (segments of
+ * different element count) already runs on class tables of its own and refuses per-instance ones (BR2_ESTATE). */
 int br2_set_instance_params(br2_handle h, const double *dev_uni, const double *dev_act_d, const double *dev_joint_scale);
 
 /* Advance every bound instance n_steps PositionVerlet steps starting at time t0 (replaces n_steps

@@ -225,9 +225,11 @@ def test_kernel_plan_of_the_baseline_assemblies(tmp_path):
         _native.describe_plan(assy.simulator.lower())
 
 
-def test_ragged_assembly_lowers_to_the_per_slot_constant_kernel(tmp_path):
+def test_ragged_assembly_lowers_to_the_tile_kernel_with_classes_of_constants(tmp_path):
     """Segments whose rods differ in element count and length: rest lengths are no longer
-    uniform, so the tile kernel declines and the one-slot-per-thread kernel with per-slot constants takes the assembly."""
+    uniform over the assembly, but they are over every rod: the tile plan groups the rods into classes of equal constants
+    (two here) and the kernels read the class tables from shared memory.  A rod whose elements differ among themselves
+    still goes to the one-slot-per-thread kernel with per-slot constants."""
     from br2 import _native
 
     library = json.load(open(ROD_DB))
@@ -242,5 +244,10 @@ def test_ragged_assembly_lowers_to_the_per_slot_constant_kernel(tmp_path):
     assy.build(str(rod_db), str(path), verbose=False)
     program = assy.simulator.lower()
     assert program.n_slots == 3 * 42 + 3 * 31 and program.fast["ok"] and not program.fast["uniform"]
-    assert _native.describe_plan(program) == \
-        "fast: one slot per thread (tile kernel refused: assembly constants are not uniform)"
+    assert _native.describe_plan(program) == ("tile: 1 CTA(s) per instance of 111 threads (2 slots per thread), 9 tip-to-base "
+                                              "joint(s) / point force(s), 2 classes of rod constants (shared-memory copy)")
+    # a rod that is not uniform in itself (a tapered rod): element constants vary along it
+    tapered = assy.simulator.lower()
+    tapered.tables["fast_c"][0, 5] *= 1.01  # rest length of rod 0's sixth element
+    assert _native.describe_plan(tapered) == \
+        "fast: one slot per thread (tile kernel refused: element constants vary along a rod)"
