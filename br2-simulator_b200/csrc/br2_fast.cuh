@@ -481,12 +481,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) br2_step_fast_kernel(con
             const double dil4 = len4 * FC(BR2_FC_INV_REST_LEN);
             const double strain = (dil4 - 1.0) * elem_mask;
             const double e0 = strain * FC(BR2_FC_LN_CR), e1 = strain * FC(BR2_FC_LN_CR + 1), e2 = strain * FC(BR2_FC_LN_CR + 2);
-            bad |= !(e0 * e0 <= 4e-4) | !(e1 * e1 <= 4e-4) | !(e2 * e2 <= 4e-4);  // |e| <= 0.02
-            damp[0] = FC(BR2_FC_CR) * exp_small(e0) * keep_w;
+            // (the tile kernel's wider series, |e| <= 0.09: with the first generation's |e| <= 0.02 the strain waves that the
+            // tip-to-base springs send through a multi-segment assembly flagged EVERY instance in every launch, and the generic
+            // replay redid them all -- measured on double_br2: 8 replays for 8 instances)
+            bad |= !(e0 * e0 <= BR2_E2_MAX) | !(e1 * e1 <= BR2_E2_MAX) | !(e2 * e2 <= BR2_E2_MAX);
+            damp[0] = FC(BR2_FC_CR) * exp_tiny(e0) * keep_w;
             damp[1] = (FC(BR2_FC_LN_CR + 1) == FC(BR2_FC_LN_CR))   // I1 == I2 (round cross-section)
                           ? damp[0]
-                          : FC(BR2_FC_CR + 1) * exp_small(e1) * keep_w;
-            damp[2] = FC(BR2_FC_CR + 2) * exp_small(e2) * keep_w;
+                          : FC(BR2_FC_CR + 1) * exp_tiny(e1) * keep_w;
+            damp[2] = FC(BR2_FC_CR + 2) * exp_tiny(e2) * keep_w;
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 a[i] = (f_int[i] + f_ext[i]) * inv_mass;

@@ -111,6 +111,9 @@ def test_batched_random_pressures_match_oracle(assembly, kwargs, seed, n_steps, 
     status = env.run(action, duration=n_steps * dt - 0.5 * dt, disable_progress_bar=True, check_nan=True)
     assert round(env.time / dt) == n_steps
     assert not any(status.nan_per_instance[k].any() for k in status.nan_per_instance)
+    # every variant's OWN result: no instance went through the exact-path replay (the one-slot-per-thread kernels used to
+    # flag every instance of the multi-segment assemblies -- their strain waves left the first damper series' range)
+    assert env.engine.replay_count() == 0 and env.engine.unresolved_count() == 0
     fused, W = fused_reference(assembly, kwargs, pressures, n_steps, dt)
     x_scale = max(np.abs(fused.view(W, r, "x")).max() for r in range(len(env.simulator)))
     worst = {"x": 0.0, "Q": 0.0, "v": 0.0, "w": 0.0}
