@@ -641,9 +641,13 @@ def _ragged_inputs(tmp_path):
     return str(rod_db), str(path)
 
 
-@pytest.mark.parametrize("variant", ["generic", "fast", "tile"])
-def test_ragged_assembly_with_an_odd_batch_matches_oracle(tmp_path, variant):
+@pytest.mark.parametrize("variant", ["generic", "fast", "tile", "tile-as-cluster"])
+def test_ragged_assembly_with_an_odd_batch_matches_oracle(tmp_path, variant, monkeypatch):
     from br2.environment import Environment
+
+    if variant == "tile-as-cluster":  # one CTA per segment (63 and 48 threads), class tables in every CTA of the cluster
+        monkeypatch.setenv("BR2_TILE_ONE_CTA_THREADS", "100")
+        variant = "tile"
     from oracle import br2_port
     from oracle.fused import FusedOracle
 
