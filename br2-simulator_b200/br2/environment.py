@@ -200,6 +200,17 @@ class Environment:
             progress.close()
         self.time = time
 
+        # instances that left the optimistic kernel's validity range with no exact-path kernel to redo them (cluster-sized
+        # assemblies, per-instance material tables) stop advancing: never hand back their stale state silently.  One
+        # [batch]-int read-back; the verdict is OR-ed over the ranks so that all of them raise together instead of one
+        # rank leaving the others inside the gather below.
+        frozen = engine.unresolved_count()
+        if _dist.reduce_flags(frozen > 0):
+            raise RuntimeError(
+                "%d instance(s) of this rank left the fast kernel's validity range (|rotation angle|, |curvature angle| or "
+                "|damper exponent| beyond its series) and no exact-path kernel fits this assembly; their state stopped "
+                "advancing at that step -- reduce the time step or the load, or run them on a one-CTA assembly" % frozen)
+
         # ---- terminal checks (reference :289-349): one device kernel reduces the batch state to a few numbers per
         # instance (br2_metrics); one gather brings the ranks' rows together
         if check_steady_state in (1, 2) or check_nan:

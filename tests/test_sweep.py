@@ -105,3 +105,21 @@ def test_parameter_sweep_in_one_batch_matches_one_oracle_run_per_parameter_set(t
         spread = max(spread, np.abs(env.simulator[0].position_collection[b] - env.simulator[0].position_collection[0]).max())
     assert spread > 1e-4  # the parameter sets really lead to different motions
     env.close()
+
+
+@pytest.mark.gpu
+def test_run_raises_when_instances_froze_without_an_exact_path(tmp_path):
+    """With per-instance material tables the generic replay cannot redo an instance (it reads the shared tables): one that
+    leaves the fast kernel's validity range stays flagged and frozen.  ``Environment.run`` must say so instead of handing
+    back its stale state."""
+    from br2.environment import Environment
+
+    batch, dt = 4, 2.0e-5
+    env = Environment("sweep", batch=batch, create_dirs=False)
+    env.reset(ROD_DB, os.path.join(DATA, "assembly_single.json"), gravity=True, per_instance=sweep(batch, seed=3))
+    env.simulator._callback_ops = []
+    pressures = np.array([[30.0, 5.0e4, 10.0, 20.0], [20.0, 5.0e4, 5.0, 20.0], [10.0, 5.0e4, 0.0, 20.0]]) * PSI
+    with pytest.raises(RuntimeError, match="validity range"):
+        env.run({name: pressures[i] for i, name in enumerate(NAMES)}, duration=400 * dt - 0.5 * dt, disable_progress_bar=True)
+    assert env.engine.unresolved_count() >= 1
+    env.close()
