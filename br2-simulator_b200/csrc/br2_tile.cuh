@@ -131,9 +131,23 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 #ifndef BR2_TILE_GATHER_MERGED
 #define BR2_TILE_GATHER_MERGED 1  // tip-to-base forces: one warp-level branch, both slots' rows loaded together (A/B: 0)
 #endif
+#ifndef BR2_TILE_SCALAR_MASKS
+#define BR2_TILE_SCALAR_MASKS 1  // flag masks applied to scalar coefficients instead of to vector results, max(x, 0) as one select (A/B: 0)
+#endif
+#ifndef BR2_TILE_LEAN_FMA
+#define BR2_TILE_LEAN_FMA -1  // additions folded into neighbouring FMA chains: bit 0 rod-one joint torque, bit 1 tint + text; -1 = the kernels with
+                              // tip-to-base joints only (measured: +0.5 ... +1 % there, -0.5 % on the single-segment kernel)
+#endif
 #ifndef BR2_TILE_HOIST_DAMPER
 #define BR2_TILE_HOIST_DAMPER 0  // damper exponentials before the third wait (costs registers: measured)
 #endif
+// x > 0 ? x : 0 as ONE compare and one select (fmax(x, 0.0) compiles to DSETP.MAX plus a five-instruction NaN fix-up that
+// returns the same values: the non-NaN operand, and +0 for -0)
+__device__ __forceinline__ double sel_gt0(double x) {
+    double r;
+    asm("{\n.reg .pred p;\nsetp.gt.f64 p, %1, 0d0000000000000000;\nselp.f64 %0, %1, 0d0000000000000000, p;\n}" : "=d"(r) : "d"(x));
+    return r;
+}
 struct TileBars {
     uint32_t b1, b2, b3, b4, xb;  // shared-memory addresses: three phase barriers, joint forces ready, pushed data (xb, xb + 8 by step parity)
 };
@@ -313,6 +327,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
     static_assert(C >= 2, "slot 0's element must lie inside the thread's run");
     static_assert(kExtras || !kCluster, "the cluster kernels carry the extra-joint code");
     using M = TileMath<kExact>;
+    constexpr int kLeanFma = BR2_TILE_LEAN_FMA < 0 ? (kExtras ? 3 : 0) : BR2_TILE_LEAN_FMA;
     const DevTables &tb = p.t;
     const int t = th.t;
     const double dt = p.dt, hdt = p.kd[11];
@@ -429,17 +444,24 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
             // sigma = e Q t - d3 = Q d / l_hat - d3 (the 1/|d| of the tangent cancels against the dilatation);
             // nL holds n_L / e, which is what both the nodal force Q^T n_L / e and the couple (Q t x n_L) l_hat need
             double qd[3], nL[3];
+#if BR2_TILE_SCALAR_MASKS
+            const double inv_dil_s = elem ? inv_dil : 0.0;
+#endif
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 qd[i] = fma(Q[j][3 * i], d[0], fma(Q[j][3 * i + 1], d[1], Q[j][3 * i + 2] * d[2]));
                 const double sigma = fma(inv_rest_len, qd[i], (i == 2) ? -1.0 : 0.0);
+#if BR2_TILE_SCALAR_MASKS
+                nL[i] = (UNI(BR2_FC_SHEAR + i) * inv_dil_s) * sigma;  // 0 in the node-only slot (sigma is finite there: d2 = 1)
+#else
                 nL[i] = (UNI(BR2_FC_SHEAR + i) * inv_dil) * sigma;
+#endif
             }
             // damping and gravity first (the update is linear), then the shear forces of elements k and k-1
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 const double raw = fma(Q[j][i], nL[0], fma(Q[j][3 + i], nL[1], Q[j][6 + i] * nL[2]));
-                const double sk = elem ? raw : 0.0;
+                const double sk = BR2_TILE_SCALAR_MASKS ? raw : (elem ? raw : 0.0);
                 const double fi = (j == 0) ? sk : sk - skp[i];
                 skp[i] = sk;
                 v[j][i] = fma(th.dtmc[j], fi, fma(v[j][i], UNI(BR2_FC_CT), dtg[i]));
@@ -602,15 +624,30 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
         // Hertz-like repulsion when the surfaces interpenetrate: -k_rep pen^1.5 along the centre line
         const double cn2 = fma(cd2[0], cd2[0], fma(cd2[1], cd2[1], cd2[2] * cd2[2])) + BR2_TINY;  // 4 |cd|^2
         const double rcn = M::rsqrt(cn2);                                 // 1 / (2 |cd|)
+#if BR2_TILE_SCALAR_MASKS
+        const double pen_raw = sel_gt0(fma(-0.5 * cn2, rcn, ra1 + ra2[j]));  // max(r1 + r2 - |cd|, 0); NaN -> 0 like fmax
+#else
         const double pen_raw = fmax(fma(-0.5 * cn2, rcn, ra1 + ra2[j]), 0.0);  // max(r1 + r2 - |cd|, 0)
+#endif
         const double pen = rint(pen_raw * BR2_PEN_SCALE) * BR2_PEN_INV_SCALE;  // np.round_(penetration_strain, 12)
         const double hmag = KD(7, -0.5 * UNI(BR2_FC_JKREP)) * (pen * M::sqrt_lo(pen)) * rcn;  // times cd2 = half the repulsion
         double fs[3];
+#if BR2_TILE_SCALAR_MASKS
+        // a slot without a joint of its own (the rod's last node, padding) is masked through the three scalar coefficients
+        // instead of through the six results: every row it read is a row some thread writes each step, so dvec and cd2 are
+        // finite and 0 * finite = 0
+        const double hcoef_m = own ? hcoef : 0.0, hmag_m = own ? hmag : 0.0, jk_m = own ? jk : 0.0;
+#endif
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
+#if BR2_TILE_SCALAR_MASKS
+            const double hf = fma(hcoef_m, dvec[i], hmag_m * cd2[i]);
+            fs[i] = jk_m * dvec[i];
+#else
             const double h = fma(hcoef, dvec[i], hmag * cd2[i]);
             const double hf = own ? h : 0.0;
             fs[i] = own ? jk * dvec[i] : 0.0;
+#endif
             sm[L::HF + (3 * j + i) * R + t] = hf;
             sm[L::FS + (3 * j + i) * R + t] = fs[i];
             // rod two takes -F: half on each node of the element (node k+1 of the run's last element belongs
@@ -712,13 +749,23 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
                     rd1[i] = sm[L::PR + (3 * j + i) * R + t];
                 }
                 // rod-one side of the joint owned by my partner: +(rd1 x k d); then both into my material frame
-                tw[j][0] += fma(rd1[1], fso[2], -rd1[2] * fso[1]);
-                tw[j][1] += fma(rd1[2], fso[0], -rd1[0] * fso[2]);
-                tw[j][2] += fma(rd1[0], fso[1], -rd1[1] * fso[0]);
+                if (kLeanFma & 1) {  // the cross product accumulated straight onto the own joint's torque: two FMAs per component
+                    tw[j][0] = fma(rd1[1], fso[2], fma(-rd1[2], fso[1], tw[j][0]));
+                    tw[j][1] = fma(rd1[2], fso[0], fma(-rd1[0], fso[2], tw[j][1]));
+                    tw[j][2] = fma(rd1[0], fso[1], fma(-rd1[1], fso[0], tw[j][2]));
+                } else {
+                    tw[j][0] += fma(rd1[1], fso[2], -rd1[2] * fso[1]);
+                    tw[j][1] += fma(rd1[2], fso[0], -rd1[0] * fso[2]);
+                    tw[j][2] += fma(rd1[0], fso[1], -rd1[1] * fso[0]);
+                }
             }
+            // (lean: the internal couple rides at the end of the rotation's FMA chain, so tsum = tint + text costs no addition;
+            // the launch's last step, which reports the two separately, keeps them apart)
+            constexpr bool kSum = (kLeanFma & 2) && !kLast;
 #pragma unroll
             for (int i = 0; i < 3; ++i)
-                text[i] = fma(Q[j][3 * i], tw[j][0], fma(Q[j][3 * i + 1], tw[j][1], Q[j][3 * i + 2] * tw[j][2]));
+                text[i] = fma(Q[j][3 * i], tw[j][0], fma(Q[j][3 * i + 1], tw[j][1],
+                              kSum ? fma(Q[j][3 * i + 2], tw[j][2], tint[j][i]) : Q[j][3 * i + 2] * tw[j][2]));
 #pragma unroll
             for (int i = 0; i < 3; ++i) text[i] = fma(TAV(j, i), ramp, text[i]);
             if (kExtras && (th.xinfo[j] >> 8) != 0) {
@@ -764,21 +811,30 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
                     const double e2 = strain * UNI(BR2_FC_LN_CR + 2);
                     if (!kExact) th.bad |= (e2 * e2 <= BR2_E2_MAX) ? 0 : 4;
                     const double ex = M::exp(e2);
+#if BR2_TILE_SCALAR_MASKS
+                    // an element whose angular velocity is held at zero (and the node-only slot): the mask goes onto the one
+                    // exponential instead of onto the three results (the bracket below is finite, so 0 * it = 0)
+                    const double ex_m = (th.fl[j] & TILE_F_ZERO_W) ? 0.0 : ex;
+                    damp[2] = UNI(BR2_FC_CR + 2) * ex_m;
+                    damp[0] = damp[1] = UNI(BR2_FC_CR) * (ex_m * ex);
+#else
                     damp[2] = UNI(BR2_FC_CR + 2) * ex;
                     damp[0] = damp[1] = UNI(BR2_FC_CR) * (ex * ex);
+#endif
                 } else {
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
                         const double e = strain * UNI(BR2_FC_LN_CR + i);
                         if (!kExact) th.bad |= (e * e <= BR2_E2_MAX) ? 0 : 4;
                         damp[i] = UNI(BR2_FC_CR + i) * M::exp(e);
+                        if (BR2_TILE_SCALAR_MASKS) damp[i] = (th.fl[j] & TILE_F_ZERO_W) ? 0.0 : damp[i];
                     }
                 }
             }
             double wnew[3];
 #pragma unroll
             for (int i = 0; i < 3; ++i)
-                wnew[i] = fma(KD(8 + i, dt * UNI(BR2_FC_JINV + i)) * dil, tint[j][i] + text[i], w[j][i]) * damp[i];
+                wnew[i] = fma(KD(8 + i, dt * UNI(BR2_FC_JINV + i)) * dil, kSum ? text[i] : tint[j][i] + text[i], w[j][i]) * damp[i];
             if (kLast && (th.fl[j] & TILE_F_VALID)) {
                 // quantities the reference's callbacks report (free_simulator.py:56-72), as of this step
                 const double mass = tb.slot_c[(long long)BR2_SC_MASS * tb.n_slots + wh.s0 + j];
@@ -820,7 +876,8 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
             }
             // rate constraints
 #pragma unroll
-            for (int i = 0; i < 3; ++i) w[j][i] = (th.fl[j] & TILE_F_ZERO_W) ? 0.0 : wnew[i];
+            for (int i = 0; i < 3; ++i)  // (scalar masks: already zero through damp[])
+                w[j][i] = (BR2_TILE_SCALAR_MASKS && !kHoistDamper) ? wnew[i] : ((th.fl[j] & TILE_F_ZERO_W) ? 0.0 : wnew[i]);
         }
         // node rates are complete only now (the element after a node lives in the same thread, later in the loop):
         // constraints, then the trailing kinematic half step of this step fused with the leading half step of the
