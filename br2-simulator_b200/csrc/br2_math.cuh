@@ -77,6 +77,15 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
     return fma(y * e, c, y);                  // y (1 + e/2 + 3 e^2/8)
 }
 
+// sqrt(x), x > 0: the same cubic step applied to s = x y (one multiplication less than x * fast_rsqrt(x)).
+__device__ __forceinline__ double fast_sqrt(double x) {
+    const double y = seed_rsqrt(x);
+    const double s = x * y;
+    const double e = fma(-s, y, 1.0);         // 1 - x y^2
+    const double c = fma(kMisc[5], e, 0.5);   // 1/2 + 3/8 e
+    return fma(s * e, c, s);                  // s (1 + e/2 + 3 e^2/8)
+}
+
 // sinc(theta) = sin(theta)/theta and cosc(theta) = (1 - cos(theta))/theta^2 as functions of
 // t = theta^2, for t <= 0.01 (|theta| <= 0.1 rad per step, i.e. |omega| <= 5e3 rad/s at dt=2e-5).
 // Truncation error < 3e-18.

@@ -138,6 +138,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 #define BR2_TILE_LEAN_FMA -1  // additions folded into neighbouring FMA chains: bit 0 rod-one joint torque, bit 1 tint + text; -1 = the kernels with
                               // tip-to-base joints only (measured: +0.5 ... +1 % there, -0.5 % on the single-segment kernel)
 #endif
+#ifndef BR2_TILE_LEAN_SQRT
+#define BR2_TILE_LEAN_SQRT 1  // radius as sqrt (cubic step from the rsqrt seed) instead of x * rsqrt(x); strain rate over |d|^2 (A/B: 0)
+#endif
 #ifndef BR2_TILE_HOIST_DAMPER
 #define BR2_TILE_HOIST_DAMPER 0  // damper exponentials before the third wait (costs registers: measured)
 #endif
@@ -169,6 +172,7 @@ struct TileMath {
     static __device__ __forceinline__ double rsqrt_lo(double x) { return kExact ? 1.0 / sqrt(x) : seed_rsqrt(x); }
     static __device__ __forceinline__ double rcp_lo(double x) { return kExact ? 1.0 / x : seed_rcp(x); }
     static __device__ __forceinline__ double sqrt_lo(double x) { return kExact ? sqrt(x) : sqrt_mid(x); }
+    static __device__ __forceinline__ double sqrt(double x) { return kExact ? ::sqrt(x) : fast_sqrt(x); }
     static __device__ __forceinline__ double exp(double d) { return kExact ? ::exp(d) : exp_tiny(d); }
     // theta / sin(theta + 1e-14) from y = 1 - cos(theta)
     static __device__ __forceinline__ double logmap_ratio(double y) {
@@ -415,6 +419,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
                 sm[L::PC + (3 * j + i) * R + t] = xn + x[j][i];
                 sm[L::PV + (3 * j + i) * R + t] = vn + v[j][i];
             }
+            const double rest_len = UNI(BR2_FC_REST_LEN), inv_rest_len = UNI(BR2_FC_INV_REST_LEN);
             double rs;
             if (kSplit && j == 0) {
                 rs = rs0;
@@ -426,9 +431,8 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
                 len[j] = fma(d2, rs, BR2_EPS_LEN);
             }
             const double inv_len = rs * fma(-BR2_EPS_LEN, rs, 1.0);  // 1/(|d| + 1e-14), second order 1e-23
-            const double rest_len = UNI(BR2_FC_REST_LEN), inv_rest_len = UNI(BR2_FC_INV_REST_LEN);
             const double r2 = UNI(BR2_FC_VOL_OVER_PI) * inv_len;
-            const double rad = r2 * M::rsqrt(r2);
+            const double rad = BR2_TILE_LEAN_SQRT ? M::sqrt(r2) : r2 * M::rsqrt(r2);
             const double dil = len[j] * inv_rest_len;
             const double inv_dil = rest_len * inv_len;
             // only thins the ~1e-8 m rest gap of a joint: 2^-20 relative is ample.  (1 / sqrt(e) is also radius x a constant;
@@ -469,11 +473,18 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
             }
             {
                 // d(e)/dt = (x_{k+1} - x_k).(v_{k+1} - v_k) / l / l_hat  (expanded form in the reference)
+#if BR2_TILE_LEAN_SQRT
+                // e_dot / e = (d . dv) / |d|^2: the rest length cancels between the strain rate and the dilatation
+                const double ue = fma(d[0], dv[0], fma(d[1], dv[1], d[2] * dv[2])) * (inv_len * inv_len);
+#else
                 const double edot = fma(d[0], dv[0], fma(d[1], dv[1], d[2] * dv[2])) * inv_len * inv_rest_len;
+#endif
                 double jw[3];
 #pragma unroll
                 for (int i = 0; i < 3; ++i) jw[i] = UNI(BR2_FC_J + i) * w[j][i] * inv_dil;
+#if !BR2_TILE_LEAN_SQRT
                 const double ue = edot * inv_dil;
+#endif
                 tint[j][0] = fma(jw[1], w[j][2], fma(-jw[2], w[j][1], fma(jw[0], ue, fma(qd[1], nL[2], -qd[2] * nL[1]))));
                 tint[j][1] = fma(jw[2], w[j][0], fma(-jw[0], w[j][2], fma(jw[1], ue, fma(qd[2], nL[0], -qd[0] * nL[2]))));
                 tint[j][2] = fma(jw[0], w[j][1], fma(-jw[1], w[j][0], fma(jw[2], ue, fma(qd[0], nL[1], -qd[1] * nL[0]))));
@@ -607,8 +618,9 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             rd2[i] = fma(Q[j][i], b0, Q[j][3 + i] * b1);  // Q^T dv2 (r + o)
-            const double xn = (j + 1 < C) ? x[(j + 1) % C][i] : sm[L::XF + i * R + th.tn];
-            const double xs = xn + x[j][i];  // x_k + x_{k+1} of my element
+            // x_k + x_{k+1} of my element: the run's last slot published exactly this sum in P2 (its own PC row)
+            const double xs = (j + 1 < C) ? x[(j + 1) % C][i] + x[j][i]
+                              : BR2_TILE_LEAN_SQRT ? sm[L::PC + (3 * j + i) * R + t] : sm[L::XF + i * R + th.tn] + x[j][i];
             cd2[i] = xs - sm[L::PC + (3 * j + i) * R + th.t1];       // 2 (c2 - c1)
             const double g = rd2[i] - sm[L::PR + (3 * j + i) * R + th.t1];
             // (c2 + rd2) - (c1 + rd1), rounded to 12 decimals like np.round_(x, 12)
