@@ -925,6 +925,8 @@ int br2_step(br2_handle h, int64_t n_steps, double t0, double dt, void *stream, 
         sp.kd[6] = 0.5 * u[BR2_FC_JK];
         sp.kd[7] = -0.5 * u[BR2_FC_JKREP];
         sp.kd[11] = 0.5 * dt;
+        sp.kd[12] = u[BR2_FC_SHEAR] * u[BR2_FC_INV_REST_LEN];
+        sp.kd[13] = u[BR2_FC_SHEAR + 1] * u[BR2_FC_INV_REST_LEN];
     }
     sp.tile = h->tile;
     sp.inst_uni = h->inst_uni;

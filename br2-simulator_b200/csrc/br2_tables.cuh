@@ -72,6 +72,7 @@ struct TilePlan {
 #define BR2_TILE_XI_NITEM(C, j, q) (1 + 3 * (C) + (j) * BR2_FAST_NODE_ITEMS + (q))
 #define BR2_TILE_XI_N(C) (1 + 3 * (C) + (C) * BR2_FAST_NODE_ITEMS)
 
+#define BR2_KD_COUNT 14  // [0..2] dt c_t g, [3..4] +-0.5 / rest Voronoi length, [5] -nu_j / 4, [6] k_j / 2, [7] -k_rep / 2, [8..10] dt / J, [11] dt / 2, [12..13] shear stiffness / rest length
 struct StepParams {
     DevTables t;
     double *state;
@@ -83,7 +84,7 @@ struct StepParams {
     int only_flagged;   // generic kernel: integrate only instances whose status is set, then clear it
     unsigned long long *replays;  // counts instance-launches redone by the exact path
     double uni[BR2_FC_COUNT];  // uniform copy of fast_c (all element slots identical), constant bank
-    double kd[12];             // loop-invariant products of uni and dt for the tile kernel (br2_step fills them)
+    double kd[BR2_KD_COUNT];   // loop-invariant products of uni and dt for the tile kernel (br2_step fills them)
     TilePlan tile;
     // launch chunking (tile kernel's work queue; the exact-path replay resumes at the chunk that failed:
     // status = 1 + chunk).  One chunk = the whole launch for the other kernels.

@@ -338,7 +338,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
     // loop-invariant products of the uniform constants and dt come from the constant bank (StepParams::kd, filled by br2_step
     // with the very expressions quoted here) instead of being hoisted into registers that then spill
     // kPerInst (material parameters that differ between the instances of a batch): both tables come from this CTA's copy
-    // in shared memory (smu: uni[BR2_FC_COUNT] then kd[12]), read as broadcasts, instead of from the constant bank
+    // in shared memory (smu: uni[BR2_FC_COUNT] then kd[BR2_KD_COUNT]), read as broadcasts, instead of from the constant bank
 #define KD(idx, expr) (kPerInst ? smu[BR2_FC_COUNT + (idx)] : p.kd[(idx)])
     TileWhere wh{};
     if (kLast) wh = tile_where<C>(p, th.t - 1, b, rank);
@@ -456,7 +456,12 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
                 qd[i] = fma(Q[j][3 * i], d[0], fma(Q[j][3 * i + 1], d[1], Q[j][3 * i + 2] * d[2]));
                 const double sigma = fma(inv_rest_len, qd[i], (i == 2) ? -1.0 : 0.0);
 #if BR2_TILE_SCALAR_MASKS
-                nL[i] = (UNI(BR2_FC_SHEAR + i) * inv_dil_s) * sigma;  // 0 in the node-only slot (sigma is finite there: d2 = 1)
+                // 0 in the node-only slot (sigma is finite there: d2 = 1); the two shear components, whose sigma is a plain
+                // product, take the rest length from the constant (S_i / l_hat) instead of from sigma: one FMA less each
+                if (BR2_TILE_LEAN_SQRT && i < 2)
+                    nL[i] = (KD(12 + i, UNI(BR2_FC_SHEAR + i) * inv_rest_len) * inv_dil_s) * qd[i];
+                else
+                    nL[i] = (UNI(BR2_FC_SHEAR + i) * inv_dil_s) * sigma;
 #else
                 nL[i] = (UNI(BR2_FC_SHEAR + i) * inv_dil) * sigma;
 #endif
@@ -990,7 +995,7 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
     __shared__ int s_why;
     __shared__ unsigned long long s_bar[6];  // B1, B2, B3, B4 (joint forces ready), XB[2] (pushed element data, by step parity)
     // kPerInst: this instance's constants (uni, then kd), one block per class of rods
-    __shared__ double s_uni[kPerInst ? BR2_TILE_MAX_CLS * (BR2_FC_COUNT + 12) : 1];
+    __shared__ double s_uni[kPerInst ? BR2_TILE_MAX_CLS * (BR2_FC_COUNT + BR2_KD_COUNT) : 1];
 
     const DevTables &tb = p.t;
     const TilePlan &tp = p.tile;
@@ -1169,7 +1174,7 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
                 for (int i = t; i < 4 * tp.n_xj; i += NT) XJT[i] = tp.xjt[(size_t)rank * 4 * tp.n_xj + i];
             }
             th.rod = rod;  // indexes the per-rod joint descriptors in the constant bank (TilePlan::jd)
-            th.uoff = kPerInst ? tp.rod_cls[rod] * (BR2_FC_COUNT + 12) : 0;
+            th.uoff = kPerInst ? tp.rod_cls[rod] * (BR2_FC_COUNT + BR2_KD_COUNT) : 0;
         }
         // zero the exchange arrays (the zero row stays zero for the whole chunk)
         for (int i = t; i < L::ZERO_END; i += NT) sm[i] = 0.0;
@@ -1178,10 +1183,10 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
             // (one block per class of rods with equal constants; inst_stride = 0: every instance reads the same table)
             for (int i = t; i < tp.n_cls * BR2_FC_COUNT; i += NT) {
                 const int c = i / BR2_FC_COUNT, k = i - c * BR2_FC_COUNT;
-                s_uni[c * (BR2_FC_COUNT + 12) + k] = p.inst_uni[(b * p.inst_stride + c) * BR2_FC_COUNT + k];
+                s_uni[c * (BR2_FC_COUNT + BR2_KD_COUNT) + k] = p.inst_uni[(b * p.inst_stride + c) * BR2_FC_COUNT + k];
             }
-            for (int tt = t; tt < 12 * tp.n_cls; tt += NT) {
-                const int c = tt / 12, t = tt - 12 * c;
+            for (int tt = t; tt < BR2_KD_COUNT * tp.n_cls; tt += NT) {
+                const int c = tt / BR2_KD_COUNT, t = tt - BR2_KD_COUNT * c;
                 const double *u = p.inst_uni + (b * p.inst_stride + c) * BR2_FC_COUNT;
                 const double dt = p.dt;
                 double kd = 0.5 * dt;                                                   // [11]
@@ -1192,7 +1197,8 @@ __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __g
                 else if (t == 6) kd = 0.5 * u[BR2_FC_JK];
                 else if (t == 7) kd = -0.5 * u[BR2_FC_JKREP];
                 else if (t < 11) kd = dt * u[BR2_FC_JINV + (t - 8)];
-                s_uni[c * (BR2_FC_COUNT + 12) + BR2_FC_COUNT + t] = kd;
+                else if (t >= 12) kd = u[BR2_FC_SHEAR + (t - 12)] * u[BR2_FC_INV_REST_LEN];
+                s_uni[c * (BR2_FC_COUNT + BR2_KD_COUNT) + BR2_FC_COUNT + t] = kd;
             }
         }
         tile_sync<kCluster>();
