@@ -141,6 +141,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 #ifndef BR2_TILE_LEAN_SQRT
 #define BR2_TILE_LEAN_SQRT 1  // radius as sqrt (cubic step from the rsqrt seed) instead of x * rsqrt(x); strain rate over |d|^2 (A/B: 0)
 #endif
+#ifndef BR2_TILE_AOS_PUB
+#define BR2_TILE_AOS_PUB -1  // what an element publishes for its joints (node sums 3 + 3, lever arm 3, arm length) as ONE 80-byte row per
+                             // slot, stored and loaded 16 bytes at a time, instead of one component-major row per double: 26 LDS / STS
+                             // fewer per warp-step; -1 = cluster kernels only (measured: +1.7 % there, -1.2 % single, -1.8 % double:
+                             // the wide accesses constrain ptxas' register allocation -- predicted by the issue model for single)
+#endif
 #ifndef BR2_TILE_HOIST_DAMPER
 #define BR2_TILE_HOIST_DAMPER 0  // damper exponentials before the third wait (costs registers: measured)
 #endif
@@ -332,6 +338,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
     static_assert(kExtras || !kCluster, "the cluster kernels carry the extra-joint code");
     using M = TileMath<kExact>;
     constexpr int kLeanFma = BR2_TILE_LEAN_FMA < 0 ? (kExtras ? 3 : 0) : BR2_TILE_LEAN_FMA;
+    constexpr bool kAosPub = BR2_TILE_AOS_PUB < 0 ? kCluster : (BR2_TILE_AOS_PUB != 0);
     const DevTables &tb = p.t;
     const int t = th.t;
     const double dt = p.dt, hdt = p.kd[11];
@@ -407,7 +414,8 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
         for (int j = 0; j < C; ++j) {
             if (kSplit && j == C - 1) mbar_wait(bars.b1, (uint32_t)gstep & 1u);  // B1
             const bool elem = th.fl[j] & TILE_F_ELEM;
-            double d[3], dv[3];
+            double d[3], dv[3], pcs[3], pvs[3];
+            double2 *const pub = (double2 *)(sm + L::PC + (j * R + t) * 10);  // (AOS_PUB) my slot's published row
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 const double xn = (j + 1 < C) ? x[(j + 1) % C][i]
@@ -416,8 +424,17 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
                                   : BR2_TILE_SHUFFLE ? tile_next(v0_start[i], &sm[L::VF + i * R + th.tn], next_via_row) : sm[L::VF + i * R + th.tn];
                 d[i] = (kSplit && j == 0) ? d0[i] : xn - x[j][i];
                 dv[i] = vn - v[j][i];
-                sm[L::PC + (3 * j + i) * R + t] = xn + x[j][i];
-                sm[L::PV + (3 * j + i) * R + t] = vn + v[j][i];
+                pcs[i] = xn + x[j][i];
+                pvs[i] = vn + v[j][i];
+                if (!kAosPub) {
+                    sm[L::PC + (3 * j + i) * R + t] = pcs[i];
+                    sm[L::PV + (3 * j + i) * R + t] = pvs[i];
+                }
+            }
+            if (kAosPub) {
+                pub[0] = make_double2(pcs[0], pcs[1]);
+                pub[1] = make_double2(pcs[2], pvs[0]);
+                pub[2] = make_double2(pvs[1], pvs[2]);
             }
             const double rest_len = UNI(BR2_FC_REST_LEN), inv_rest_len = UNI(BR2_FC_INV_REST_LEN);
             double rs;
@@ -497,10 +514,17 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
             // what the joint in which this element is rod one needs from it
             const double ra1 = fma(JDV(7), rse, rad);
             const double a0 = JDV(4) * ra1, a1 = JDV(5) * ra1;  // planar arms: no d3 component (tile plan requirement)
-            sm[L::PA + j * R + t] = ra1;
+            double prs[3];
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
-                sm[L::PR + (3 * j + i) * R + t] = fma(Q[j][i], a0, Q[j][3 + i] * a1);  // Q^T dv1 (r + o)
+            for (int i = 0; i < 3; ++i) prs[i] = fma(Q[j][i], a0, Q[j][3 + i] * a1);  // Q^T dv1 (r + o)
+            if (kAosPub) {
+                pub[3] = make_double2(prs[0], prs[1]);
+                pub[4] = make_double2(prs[2], ra1);
+            } else {
+                sm[L::PA + j * R + t] = ra1;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) sm[L::PR + (3 * j + i) * R + t] = prs[i];
+            }
             if (kExtras) radx[j] = rad;  // (an element of a tip-to-base joint pushes it below)
         }
         if (!kSplit) sm[L::LF + t] = len[0];
@@ -526,8 +550,8 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
                         val[9 + i] = w[j][i];
-                        val[13 + i] = sm[L::PC + (3 * j + i) * R + t];
-                        val[16 + i] = sm[L::PV + (3 * j + i) * R + t];
+                        val[13 + i] = kAosPub ? sm[L::PC + (j * R + t) * 10 + i] : sm[L::PC + (3 * j + i) * R + t];
+                        val[16 + i] = kAosPub ? sm[L::PC + (j * R + t) * 10 + 3 + i] : sm[L::PV + (3 * j + i) * R + t];
                     }
                     val[12] = radx[j];
 #pragma unroll
@@ -617,20 +641,43 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
     for (int j = 0; j < C; ++j) {
         const bool own = th.fl[j] & TILE_F_OWN;
         const double b0 = JDV(0) * ra2[j], b1 = JDV(1) * ra2[j];
-        const double ra1 = sm[L::PA + j * R + th.t1];
         double rd2[3], cd2[3], dvec[3];
         double proj2 = 0.0;
+        // my partner's published row (rod one of the joint I own) and, of my own, the node sums
+        double pc1[3], pv1[3], pr1[3], pc_own[3], pv_own[3], ra1;
+        if (kAosPub) {
+            const double2 *const his = (const double2 *)(sm + L::PC + (j * R + th.t1) * 10);
+            const double2 *const mine = (const double2 *)(sm + L::PC + (j * R + t) * 10);
+            const double2 h0 = his[0], h1 = his[1], h2 = his[2], h3 = his[3], h4 = his[4];
+            pc1[0] = h0.x, pc1[1] = h0.y, pc1[2] = h1.x, pv1[0] = h1.y, pv1[1] = h2.x, pv1[2] = h2.y;
+            pr1[0] = h3.x, pr1[1] = h3.y, pr1[2] = h4.x, ra1 = h4.y;
+            const double2 m1 = mine[1], m2 = mine[2];
+            pc_own[2] = m1.x, pv_own[0] = m1.y, pv_own[1] = m2.x, pv_own[2] = m2.y;
+            if (j + 1 == C) {
+                const double2 m0 = mine[0];
+                pc_own[0] = m0.x, pc_own[1] = m0.y;
+            }
+        } else {
+            ra1 = sm[L::PA + j * R + th.t1];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                pc1[i] = sm[L::PC + (3 * j + i) * R + th.t1];
+                pr1[i] = sm[L::PR + (3 * j + i) * R + th.t1];
+                pv1[i] = sm[L::PV + (3 * j + i) * R + th.t1];
+                pv_own[i] = sm[L::PV + (3 * j + i) * R + t];
+                if (j + 1 == C) pc_own[i] = BR2_TILE_LEAN_SQRT ? sm[L::PC + (3 * j + i) * R + t] : sm[L::XF + i * R + th.tn] + x[j][i];
+            }
+        }
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             rd2[i] = fma(Q[j][i], b0, Q[j][3 + i] * b1);  // Q^T dv2 (r + o)
-            // x_k + x_{k+1} of my element: the run's last slot published exactly this sum in P2 (its own PC row)
-            const double xs = (j + 1 < C) ? x[(j + 1) % C][i] + x[j][i]
-                              : BR2_TILE_LEAN_SQRT ? sm[L::PC + (3 * j + i) * R + t] : sm[L::XF + i * R + th.tn] + x[j][i];
-            cd2[i] = xs - sm[L::PC + (3 * j + i) * R + th.t1];       // 2 (c2 - c1)
-            const double g = rd2[i] - sm[L::PR + (3 * j + i) * R + th.t1];
+            // x_k + x_{k+1} of my element: the run's last slot published exactly this sum in P2 (its own row)
+            const double xs = (j + 1 < C) ? x[(j + 1) % C][i] + x[j][i] : pc_own[i];
+            cd2[i] = xs - pc1[i];       // 2 (c2 - c1)
+            const double g = rd2[i] - pr1[i];
             // (c2 + rd2) - (c1 + rd1), rounded to 12 decimals like np.round_(x, 12)
             dvec[i] = rint(fma(0.5, cd2[i], g) * BR2_1E12) * BR2_1EM12;
-            const double vr2 = sm[L::PV + (3 * j + i) * R + t] - sm[L::PV + (3 * j + i) * R + th.t1];  // 2 v_rel
+            const double vr2 = pv_own[i] - pv1[i];  // 2 v_rel
             proj2 = fma(vr2, dvec[i], proj2);
         }
         const double dist2 = fma(dvec[0], dvec[0], fma(dvec[1], dvec[1], dvec[2] * dvec[2]));
@@ -763,7 +810,12 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
                         if (j + 1 < C) r_fext[(j + 1) % C][i] += fo;
                     }
                     fso[i] = sm[L::FS + (3 * j + i) * R + th.to];
-                    rd1[i] = sm[L::PR + (3 * j + i) * R + t];
+                    if (!kAosPub) rd1[i] = sm[L::PR + (3 * j + i) * R + t];
+                }
+                if (kAosPub) {
+                    const double2 *const mine = (const double2 *)(sm + L::PC + (j * R + t) * 10);
+                    const double2 m3 = mine[3], m4 = mine[4];
+                    rd1[0] = m3.x, rd1[1] = m3.y, rd1[2] = m4.x;
                 }
                 // rod-one side of the joint owned by my partner: +(rd1 x k d); then both into my material frame
                 if (kLeanFma & 1) {  // the cross product accumulated straight onto the own joint's torque: two FMAs per component
@@ -989,7 +1041,7 @@ template <int C, int NT, int kMinBlocks, bool kExtras, bool kCluster, bool kExac
 __global__ void __launch_bounds__(NT, kMinBlocks) br2_step_tile_kernel(const __grid_constant__ StepParams p) {
     using L = TileSmem<C, NT>;
     constexpr int R = L::R;
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
     __shared__ long long s_item;
     __shared__ int s_chunk;
     __shared__ int s_why;
