@@ -595,6 +595,7 @@ __global__ void selftest_math_kernel(int which, const double *in, double *out, l
     case 8: y = -0.5 * logmap_ratio_tiny(1.0 - x); break;
     case 9: y = exp_tiny(x); break;
     case 10: y = sqrt_mid(x); break;
+    case 12: y = fast_sqrt(x); break;
     default: {  // 11: angle of rotate_directors_tiny for omega = (0, 0, x), half step 1e-5: atan2(R10, R00)
         double Q[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
         const double w[3] = {0.0, 0.0, x};

@@ -95,6 +95,9 @@ def test_tile_exp_and_sqrt():
     x = np.concatenate([10.0 ** rng.uniform(-30, 2, 100000), [1.0, 4.0]])
     assert relerr(run(10, x), np.sqrt(x)).max() <= 2.0 ** -38
     assert run(10, np.zeros(4)).tolist() == [0.0] * 4
+    # the radius' square root (cubic step on x * rsqrt-seed): full precision over anything a cross-section area can be
+    y = np.concatenate([10.0 ** rng.uniform(-12, 4, 200000), [1.0, 4.0, 2.5e-5]])
+    assert relerr(run(12, y), np.sqrt(y)).max() <= ULP4
 
 
 def test_tile_rotation_angle_keeps_the_reference_guard():
