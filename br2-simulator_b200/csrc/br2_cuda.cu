@@ -1159,6 +1159,7 @@ int br2_metrics(br2_handle h, const double *dev_previous, double *dev_out, void 
     br2::MetricsParams mp;
     mp.t = h->t;
     mp.state = h->state;
+    if (h->t.n_rods > BR2_METRICS_MAX_RODS) return fail(BR2_ELIMIT, "br2_metrics: more rods than the metrics kernel's table holds");
     mp.previous = dev_previous;
     mp.out = dev_out;
     mp.batch = h->batch;
