@@ -46,7 +46,7 @@ FLOP_PER_ELEMENT_STEP = 695.0  # SURVEY.md Appendix B (single-BR2-type assembly,
 # capture of exactly this command; keyed by (workload, instances on the GPU, steps per launch) and by the capture file, so
 # a line for any other workload carries null instead of a stale figure.  (Algorithmic bytes are computed live: `hbm`.)
 NCU_DRAM_BYTES_PER_LAUNCH = {
-    ("single", 4096, 2000): (216809472.0, "profiles/r02_dram_2000step_launch.csv (ncu capture of this command on the final round-2 kernel: 76.0 MB read + 140.9 MB written; part of the last write-back is still in the L2 when the kernel ends)"),
+    ("single", 4096, 2000): (223571200.0, "profiles/r02_dram_2000step_launch.csv (ncu capture of this command on the final round-2 kernel: 76.2 MB read + 147.3 MB written; part of the last write-back is still in the L2 when the kernel ends)"),
 }
 WORKLOADS = {
     # BASELINE.json configs[1]

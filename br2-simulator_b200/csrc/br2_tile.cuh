@@ -135,8 +135,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 #define BR2_TILE_SCALAR_MASKS 1  // flag masks applied to scalar coefficients instead of to vector results, max(x, 0) as one select (A/B: 0)
 #endif
 #ifndef BR2_TILE_LEAN_FMA
-#define BR2_TILE_LEAN_FMA -1  // additions folded into neighbouring FMA chains: bit 0 rod-one joint torque, bit 1 tint + text; -1 = the kernels with
-                              // tip-to-base joints only (measured: +0.5 ... +1 % there, -0.5 % on the single-segment kernel)
+#define BR2_TILE_LEAN_FMA -1  // additions folded into neighbouring FMA chains: bit 0 rod-one joint torque, bit 1 tint + text; -1 = both on the
+                              // kernels with tip-to-base joints (+0.5 ... +1 %), bit 0 on the single-segment kernel (bit 1: -1.5 % there)
 #endif
 #ifndef BR2_TILE_LEAN_SQRT
 #define BR2_TILE_LEAN_SQRT 1  // radius as sqrt (cubic step from the rsqrt seed) instead of x * rsqrt(x); strain rate over |d|^2 (A/B: 0)
@@ -337,7 +337,7 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
     static_assert(C >= 2, "slot 0's element must lie inside the thread's run");
     static_assert(kExtras || !kCluster, "the cluster kernels carry the extra-joint code");
     using M = TileMath<kExact>;
-    constexpr int kLeanFma = BR2_TILE_LEAN_FMA < 0 ? (kExtras ? 3 : 0) : BR2_TILE_LEAN_FMA;
+    constexpr int kLeanFma = BR2_TILE_LEAN_FMA < 0 ? (kExtras ? 3 : 1) : BR2_TILE_LEAN_FMA;
     constexpr bool kAosPub = BR2_TILE_AOS_PUB < 0 ? kCluster : (BR2_TILE_AOS_PUB != 0);
     const DevTables &tb = p.t;
     const int t = th.t;
@@ -585,6 +585,10 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
 
     // =============================== P3a: Voronoi couples (own registers + rows published before B1) ==========
     double tw[C][3];  // world-frame joint torque on my element (own joint now, rod-one joint in P4)
+    // range checks of both slots merged into th.bad once per step (one-CTA kernels: +0.5 ... +1 % together with the folded
+    // joint torque; the cluster kernel measured 1 % slower with it and keeps one update per check)
+    constexpr bool kMergeFlags = !kCluster;
+    bool ok_y = true, ok_e = true;
     {
         double ap[3], cp[3];  // previous cell's A and C
 #pragma unroll
@@ -606,7 +610,10 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
                               fma(Qn[5], q[5], fma(Qn[6], q[6], fma(Qn[7], q[7], Qn[8] * q[8]))))))));
             // y = 1 - cos(theta) with the reference's -1e-10 guard; a benign value off the rod
             const double y = vor ? fma(-0.5, tr, kMisc[7]) : kMisc2[3];
-            if (!kExact) th.bad |= (y <= BR2_Y_MAX && y > 0.0) ? 0 : 2;
+            if (!kExact) {
+                if (kMergeFlags) ok_y = ok_y && (y <= BR2_Y_MAX && y > 0.0);
+                else th.bad |= (y <= BR2_Y_MAX && y > 0.0) ? 0 : 2;
+            }
             const double ksr = M::logmap_ratio(y) * KD(4, -0.5 * UNI(BR2_FC_INV_REST_VLEN));
             const double ks = vor ? ksr : 0.0;
             const double vdil = (lenn + len[j]) * KD(3, 0.5 * UNI(BR2_FC_INV_REST_VLEN));
@@ -878,7 +885,10 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
                 const double strain = (th.fl[j] & TILE_F_ELEM) ? dil - 1.0 : 0.0;
                 if (p.tile.round_section) {
                     const double e2 = strain * UNI(BR2_FC_LN_CR + 2);
-                    if (!kExact) th.bad |= (e2 * e2 <= BR2_E2_MAX) ? 0 : 4;
+                    if (!kExact) {
+                        if (kMergeFlags) ok_e = ok_e && (e2 * e2 <= BR2_E2_MAX);
+                        else th.bad |= (e2 * e2 <= BR2_E2_MAX) ? 0 : 4;
+                    }
                     const double ex = M::exp(e2);
 #if BR2_TILE_SCALAR_MASKS
                     // an element whose angular velocity is held at zero (and the node-only slot): the mask goes onto the one
@@ -894,7 +904,10 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
                         const double e = strain * UNI(BR2_FC_LN_CR + i);
-                        if (!kExact) th.bad |= (e * e <= BR2_E2_MAX) ? 0 : 4;
+                        if (!kExact) {
+                            if (kMergeFlags) ok_e = ok_e && (e * e <= BR2_E2_MAX);
+                            else th.bad |= (e * e <= BR2_E2_MAX) ? 0 : 4;
+                        }
                         damp[i] = UNI(BR2_FC_CR + i) * M::exp(e);
                         if (BR2_TILE_SCALAR_MASKS) damp[i] = (th.fl[j] & TILE_F_ZERO_W) ? 0.0 : damp[i];
                     }
@@ -1020,8 +1033,14 @@ __device__ __forceinline__ void tile_step(const StepParams &p, double *sm, const
 #endif
         }
         const double hmult = kEnd ? hdt : dt;
+        bool bad_r = false;
 #pragma unroll
-        for (int j = 0; j < C; ++j) th.bad |= M::rotate(Q[j], w[j], hdt, hmult) ? 1 : 0;
+        for (int j = 0; j < C; ++j) {
+            const bool out_of_range = M::rotate(Q[j], w[j], hdt, hmult);
+            if (kMergeFlags) bad_r = out_of_range || bad_r;
+            else th.bad |= out_of_range ? 1 : 0;
+        }
+        if (kMergeFlags) th.bad |= (bad_r ? 1 : 0) | (ok_y ? 0 : 2) | (ok_e ? 0 : 4);
 #pragma unroll
         for (int j = 0; j < C; ++j) {
 #pragma unroll
